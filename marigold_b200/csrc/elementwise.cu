@@ -1,0 +1,315 @@
+// Streaming (HBM-bound) helpers around the tensor-core kernels: layout changes that feed TMA
+// (space-to-depth parity planes for stride-2 convs, nearest x2 upsampling, channel concat, latent
+// packing), the ABI's NCHW<->NHWC conversions, the tiny dense layers (time MLP, text K/V), the 2-key
+// cross attention and a row softmax. All use 128-bit accesses where the layout allows.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace mgb {
+
+static inline int grid_for(size_t n, int threads) {
+  size_t b = (n + threads - 1) / threads;
+  const size_t cap = 148 * 16;
+  return int(b < cap ? (b ? b : 1) : cap);
+}
+#define MGB_LAUNCH_CHECK(name)                                       \
+  do {                                                               \
+    cudaError_t _e = cudaGetLastError();                             \
+    if (_e != cudaSuccess) {                                         \
+      set_error(name " launch: %s", cudaGetErrorString(_e));         \
+      return MGB_ERR_CUDA;                                           \
+    }                                                                \
+    return MGB_OK;                                                   \
+  } while (0)
+
+// x fp32 [NB, H, W, C] -> y bf16 [NB, 4, H/2, W/2, C], plane = (h & 1) * 2 + (w & 1)
+__global__ void s2d_kernel(const float4* __restrict__ x, uint2* __restrict__ y, int NB, int H, int W, int Q) {
+  const size_t total = (size_t)NB * H * W * Q;
+  const int H2 = H / 2, W2 = W / 2;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int q = int(i % Q);
+    size_t r = i / Q;
+    const int w = int(r % W); r /= W;
+    const int h = int(r % H);
+    const int n = int(r / H);
+    const float4 v = __ldg(x + i);
+    const int plane = (h & 1) * 2 + (w & 1);
+    const size_t o = ((((size_t)n * 4 + plane) * H2 + (h >> 1)) * W2 + (w >> 1)) * Q + q;
+    y[o] = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+  }
+}
+int launch_space_to_depth(const float* x, bf16* y, int NB, int H, int W, int C, cudaStream_t stream) {
+  if ((H | W) & 1 || C % 4) { set_error("space_to_depth: H, W must be even, C %% 4 == 0"); return MGB_ERR_INVALID; }
+  const size_t n = (size_t)NB * H * W * (C / 4);
+  s2d_kernel<<<grid_for(n, 256), 256, 0, stream>>>(reinterpret_cast<const float4*>(x), reinterpret_cast<uint2*>(y),
+                                                   NB, H, W, C / 4);
+  MGB_LAUNCH_CHECK("space_to_depth");
+}
+
+// nearest x2: x fp32 [NB, H, W, C] -> y bf16 [NB, 2H, 2W, C]   (F.interpolate(scale_factor=2, mode="nearest"))
+__global__ void upsample2x_kernel(const float4* __restrict__ x, uint2* __restrict__ y, int NB, int H, int W, int Q) {
+  const size_t total = (size_t)NB * H * W * Q;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int q = int(i % Q);
+    size_t r = i / Q;
+    const int w = int(r % W); r /= W;
+    const int h = int(r % H);
+    const int n = int(r / H);
+    const float4 v = __ldg(x + i);
+    const uint2 o = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+    const size_t row0 = (((size_t)n * 2 * H + 2 * h) * 2 * W + 2 * w) * Q + q;
+    const size_t row1 = row0 + (size_t)2 * W * Q;
+    y[row0] = o; y[row0 + Q] = o; y[row1] = o; y[row1 + Q] = o;
+  }
+}
+int launch_upsample2x(const float* x, bf16* y, int NB, int H, int W, int C, cudaStream_t stream) {
+  if (C % 4) { set_error("upsample2x: C %% 4 != 0"); return MGB_ERR_INVALID; }
+  const size_t n = (size_t)NB * H * W * (C / 4);
+  upsample2x_kernel<<<grid_for(n, 256), 256, 0, stream>>>(reinterpret_cast<const float4*>(x),
+                                                          reinterpret_cast<uint2*>(y), NB, H, W, C / 4);
+  MGB_LAUNCH_CHECK("upsample2x");
+}
+
+// out[M, Ca + Cb] = [a | b]  (torch.cat(dim=1) in NHWC)
+__global__ void concat_kernel(const float4* __restrict__ a, const float4* __restrict__ b, float4* __restrict__ out,
+                              size_t M, int Qa, int Qb) {
+  const int Qo = Qa + Qb;
+  const size_t total = M * Qo;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t m = i / Qo;
+    const int q = int(i - m * Qo);
+    out[i] = q < Qa ? __ldg(a + m * Qa + q) : __ldg(b + m * Qb + (q - Qa));
+  }
+}
+int launch_concat(const float* a, const float* b, float* out, int M, int Ca, int Cb, cudaStream_t stream) {
+  if ((Ca | Cb) % 4) { set_error("concat: channels %% 4 != 0"); return MGB_ERR_INVALID; }
+  const size_t n = (size_t)M * ((Ca + Cb) / 4);
+  concat_kernel<<<grid_for(n, 256), 256, 0, stream>>>(reinterpret_cast<const float4*>(a),
+                                                      reinterpret_cast<const float4*>(b),
+                                                      reinterpret_cast<float4*>(out), size_t(M), Ca / 4, Cb / 4);
+  MGB_LAUNCH_CHECK("concat");
+}
+
+__global__ void cast_bf16_kernel(const float4* __restrict__ x, uint2* __restrict__ y, size_t n4) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    const float4 v = __ldg(x + i);
+    y[i] = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+  }
+}
+int launch_cast_bf16(const float* x, bf16* y, size_t n, cudaStream_t stream) {
+  if (n % 4) { set_error("cast_bf16: n %% 4 != 0"); return MGB_ERR_INVALID; }
+  cast_bf16_kernel<<<grid_for(n / 4, 256), 256, 0, stream>>>(reinterpret_cast<const float4*>(x),
+                                                             reinterpret_cast<uint2*>(y), n / 4);
+  MGB_LAUNCH_CHECK("cast_bf16");
+}
+
+// UNet conv_in operand (reference marigold_depth_pipeline.py:456-458: rgb latent FIRST):
+// out bf16 [M, 64] = [rgb(4) | target(4) | 0 x 56]
+__global__ void pack_latents_kernel(const float4* __restrict__ rgb, const float4* __restrict__ tgt,
+                                    uint4* __restrict__ out, int M) {
+  const int total = M * 8;  // 8 x 16 B per 64-channel row
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int m = i >> 3, part = i & 7;
+    uint4 o = make_uint4(0, 0, 0, 0);
+    if (part == 0) {
+      const float4 a = __ldg(rgb + m), b = __ldg(tgt + m);
+      o = make_uint4(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w), pack_bf16x2(b.x, b.y), pack_bf16x2(b.z, b.w));
+    }
+    out[i] = o;
+  }
+}
+int launch_pack_latents(const float* rgb, const float* tgt, bf16* out, int M, cudaStream_t stream) {
+  pack_latents_kernel<<<grid_for(size_t(M) * 8, 256), 256, 0, stream>>>(
+      reinterpret_cast<const float4*>(rgb), reinterpret_cast<const float4*>(tgt), reinterpret_cast<uint4*>(out), M);
+  MGB_LAUNCH_CHECK("pack_latents");
+}
+
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, float* __restrict__ y, int NB, int C, int HW,
+                                    float scale) {
+  const size_t total = (size_t)NB * C * HW;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int c = int(i % C);
+    const size_t r = i / C;
+    const size_t p = r % HW, n = r / HW;
+    y[i] = __ldg(x + (n * C + c) * HW + p) * scale;
+  }
+}
+int launch_nchw_to_nhwc(const float* x, float* y, int NB, int C, int HW, float scale, cudaStream_t stream) {
+  nchw_to_nhwc_kernel<<<grid_for((size_t)NB * C * HW, 256), 256, 0, stream>>>(x, y, NB, C, HW, scale);
+  MGB_LAUNCH_CHECK("nchw_to_nhwc");
+}
+__global__ void nhwc_to_nchw_kernel(const float* __restrict__ x, float* __restrict__ y, int NB, int C, int HW,
+                                    float scale) {
+  const size_t total = (size_t)NB * C * HW;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t p = i % HW;
+    const size_t r = i / HW;
+    const int c = int(r % C);
+    const size_t n = r / C;
+    y[i] = __ldg(x + (n * HW + p) * C + c) * scale;
+  }
+}
+int launch_nhwc_to_nchw(const float* x, float* y, int NB, int C, int HW, float scale, cudaStream_t stream) {
+  nhwc_to_nchw_kernel<<<grid_for((size_t)NB * C * HW, 256), 256, 0, stream>>>(x, y, NB, C, HW, scale);
+  MGB_LAUNCH_CHECK("nhwc_to_nchw");
+}
+
+// rgb fp32 NCHW [NB, 3, HW] -> bf16 NHWC-64 (3 real channels + zeros): the VAE encoder conv_in operand
+__global__ void pack_rgb_kernel(const float* __restrict__ rgb, uint4* __restrict__ out, int NB, size_t HW) {
+  const size_t total = (size_t)NB * HW * 8;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t m = i >> 3;
+    const int part = int(i & 7);
+    uint4 o = make_uint4(0, 0, 0, 0);
+    if (part == 0) {
+      const size_t n = m / HW, p = m % HW;
+      const float r = __ldg(rgb + (n * 3 + 0) * HW + p), g = __ldg(rgb + (n * 3 + 1) * HW + p),
+                  b = __ldg(rgb + (n * 3 + 2) * HW + p);
+      o.x = pack_bf16x2(r, g);
+      o.y = pack_bf16x2(b, 0.f);
+    }
+    out[i] = o;
+  }
+}
+int launch_pack_rgb(const float* rgb_nchw, bf16* out, int NB, int HW, cudaStream_t stream) {
+  pack_rgb_kernel<<<grid_for((size_t)NB * HW * 8, 256), 256, 0, stream>>>(rgb_nchw, reinterpret_cast<uint4*>(out), NB,
+                                                                         size_t(HW));
+  MGB_LAUNCH_CHECK("pack_rgb");
+}
+
+// Cross attention against n_ctx == 2 pre-projected keys/values (the empty-prompt BOS/EOS tokens,
+// reference marigold_depth_pipeline.py:381-394). One warp per (token, head): 64-dim dots, 2-way softmax.
+// q bf16 [M, C]; kv fp32 [2 (k|v), 2 (ctx token), C]; out bf16 [M, C]
+__global__ void __launch_bounds__(256) cross_attn2_kernel(const bf16* __restrict__ q, const float* __restrict__ kv,
+                                                          bf16* __restrict__ out, int M, int C, float scale) {
+  const int heads = C / 64;
+  const long long gw = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (gw >= (long long)M * heads) return;
+  const long long m = gw / heads;
+  const int h = int(gw - m * heads);
+  const int c = h * 64 + lane * 2;
+  const __nv_bfloat162 q2 = *reinterpret_cast<const __nv_bfloat162*>(q + m * C + c);
+  const float qa = __bfloat162float(q2.x), qb = __bfloat162float(q2.y);
+  const float2 k0 = *reinterpret_cast<const float2*>(kv + c), k1 = *reinterpret_cast<const float2*>(kv + C + c);
+  float s0 = qa * k0.x + qb * k0.y, s1 = qa * k1.x + qb * k1.y;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+    s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+  }
+  s0 *= scale; s1 *= scale;
+  const float mx = fmaxf(s0, s1);
+  const float e0 = __expf(s0 - mx), e1 = __expf(s1 - mx);
+  const float inv = 1.f / (e0 + e1);
+  const float2 v0 = *reinterpret_cast<const float2*>(kv + 2 * C + c),
+               v1 = *reinterpret_cast<const float2*>(kv + 3 * C + c);
+  const float oa = (e0 * v0.x + e1 * v1.x) * inv, ob = (e0 * v0.y + e1 * v1.y) * inv;
+  *reinterpret_cast<__nv_bfloat162*>(out + m * C + c) = __floats2bfloat162_rn(oa, ob);
+}
+int launch_cross_attn2(const bf16* q, const float* kv, bf16* out, int M, int C, float scale, cudaStream_t stream) {
+  if (C % 64) { set_error("cross_attn2: C %% 64 != 0"); return MGB_ERR_INVALID; }
+  const long long warps = (long long)M * (C / 64);
+  const int blocks = int((warps + 7) / 8);
+  cross_attn2_kernel<<<blocks, 256, 0, stream>>>(q, kv, out, M, C, scale);
+  MGB_LAUNCH_CHECK("cross_attn2");
+}
+
+// y[M, N] = act_out(act_in(x)[M, K] W[N, K]^T + b); fp32 everywhere; one warp per output element.
+__global__ void __launch_bounds__(256) linear_small_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                           const float* __restrict__ b, float* __restrict__ y, int M,
+                                                           int N, int K, int silu_in, int silu_out) {
+  const long long gw = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (gw >= (long long)M * N) return;
+  const int m = int(gw / N), n = int(gw - (long long)m * N);
+  float acc = 0.f;
+  for (int k = lane; k < K; k += 32) {
+    float xv = __ldg(x + (size_t)m * K + k);
+    if (silu_in) xv = xv / (1.0f + expf(-xv));
+    acc += xv * __ldg(w + (size_t)n * K + k);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) {
+    acc += b ? __ldg(b + n) : 0.f;
+    if (silu_out) acc = acc / (1.0f + expf(-acc));
+    y[(size_t)m * N + n] = acc;
+  }
+}
+int launch_linear_small(const float* x, const float* w, const float* b, float* y, int M, int N, int K, int silu_in,
+                        int silu_out, cudaStream_t stream) {
+  const long long warps = (long long)M * N;
+  linear_small_kernel<<<int((warps + 7) / 8), 256, 0, stream>>>(x, w, b, y, M, N, K, silu_in, silu_out);
+  MGB_LAUNCH_CHECK("linear_small");
+}
+
+// diffusers get_timestep_embedding(flip_sin_to_cos=True, downscale_freq_shift=0): emb = [cos(t f) | sin(t f)],
+// f_i = exp(-ln(10000) * i / half)   
+__global__ void timestep_embedding_kernel(const float* __restrict__ t, float* __restrict__ emb, int M, int dim) {
+  const int half = dim / 2;
+  const int total = M * half;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int m = i / half, j = i - m * half;
+    const float f = expf(-logf(10000.0f) * float(j) / float(half));
+    const float a = t[m] * f;
+    emb[(size_t)m * dim + j] = cosf(a);
+    emb[(size_t)m * dim + half + j] = sinf(a);
+  }
+}
+int launch_timestep_embedding(const float* t, float* emb, int M, int dim, cudaStream_t stream) {
+  timestep_embedding_kernel<<<grid_for(size_t(M) * dim / 2, 128), 128, 0, stream>>>(t, emb, M, dim);
+  MGB_LAUNCH_CHECK("timestep_embedding");
+}
+
+// In-place row softmax on bf16 scores (fp32 math): s[M, ld], first n columns valid. One CTA per row.
+__global__ void __launch_bounds__(256) softmax_rows_kernel(bf16* __restrict__ s, int n, int ld) {
+  __shared__ float red[32];
+  bf16* row = s + (size_t)blockIdx.x * ld;
+  float mx = -INFINITY;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) mx = fmaxf(mx, __bfloat162float(row[i]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  mx = red[0];
+  for (int i = 1; i < int(blockDim.x >> 5); ++i) mx = fmaxf(mx, red[i]);
+  __syncthreads();
+  float sum = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) sum += __expf(__bfloat162float(row[i]) - mx);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sum;
+  __syncthreads();
+  sum = 0.f;
+  for (int i = 0; i < int(blockDim.x >> 5); ++i) sum += red[i];
+  const float inv = 1.f / sum;
+  for (int i = threadIdx.x; i < n; i += blockDim.x)
+    row[i] = __float2bfloat16(__expf(__bfloat162float(row[i]) - mx) * inv);
+}
+int launch_softmax_rows(bf16* s, int M, int n, int ld, cudaStream_t stream) {
+  softmax_rows_kernel<<<M, 256, 0, stream>>>(s, n, ld);
+  MGB_LAUNCH_CHECK("softmax_rows");
+}
+
+// x bf16 [M, N] -> y bf16 [N, M] through a padded smem tile
+__global__ void transpose_bf16_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, int M, int N) {
+  __shared__ bf16 tile[32][33];
+  const int m0 = blockIdx.y * 32, n0 = blockIdx.x * 32;
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int m = m0 + r, n = n0 + threadIdx.x;
+    if (m < M && n < N) tile[r][threadIdx.x] = x[(size_t)m * N + n];
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int n = n0 + r, m = m0 + threadIdx.x;
+    if (m < M && n < N) y[(size_t)n * M + m] = tile[threadIdx.x][r];
+  }
+}
+int launch_transpose_bf16(const bf16* x, bf16* y, int M, int N, cudaStream_t stream) {
+  dim3 grid((N + 31) / 32, (M + 31) / 32), block(32, 8);
+  transpose_bf16_kernel<<<grid, block, 0, stream>>>(x, y, M, N);
+  MGB_LAUNCH_CHECK("transpose_bf16");
+}
+
+}  // namespace mgb

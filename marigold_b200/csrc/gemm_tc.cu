@@ -1,0 +1,479 @@
+// tcgen05 GEMM / implicit-GEMM convolution for sm_100a.
+//
+//   D[M, N] = A[M, K] * B[N, K]^T,  bf16 operands, fp32 accumulation in TMEM.
+//
+// One 128 x BLOCK_N output tile per CTA. Warp roles (192 threads):
+//   warp 0      TMA producer: A tile (128 rows x 64 K, SWIZZLE_128B) + B tile (BLOCK_N x 64 K)
+//               per pipeline stage, completion signalled on an mbarrier (complete_tx).
+//   warp 1      TMEM allocator + MMA issuer: one elected lane issues 4 x tcgen05.mma (K = 16 each)
+//               per stage and releases the stage with tcgen05.commit.
+//   warps 2..5  epilogue: tcgen05.ld the fp32 accumulator (one row per thread), apply the fused
+//               epilogue (bias / activation / GEGLU / residual / scheduler step / output cast), store.
+//
+// A operand addressing:
+//   mode 0  rows: 2D tensor map {K, M}; tile m covers rows [128 m, 128 m + 128).
+//   mode 1  conv: 5D tensor map {C, W, H, P, NB} over an NHWC image (P parity planes; P = 1 for
+//           stride-1). A CTA's 128 rows are a tile_h x tile_w pixel rectangle; K block kb maps to
+//           (tap, channel block); the tap shifts the box by (dy, dx) and TMA zero-fills the halo, so
+//           padding costs nothing and no im2col buffer exists.
+// Replaces (behaviourally) the cuDNN/cuBLAS calls under torch.nn.Conv2d / Linear reached from
+// reference marigold/marigold_depth_pipeline.py:461-463,491-492,512-513.
+#include <algorithm>
+#include "common.cuh"
+#include "kernels.h"
+
+namespace mgb {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;
+constexpr int UMMA_K = 16;
+constexpr int kGemmThreads = 192;
+
+__host__ __device__ constexpr int a_stage_bytes() { return BLOCK_M * BLOCK_K * 2; }
+__host__ __device__ constexpr int b_stage_bytes(int block_n) { return block_n * BLOCK_K * 2; }
+__host__ __device__ constexpr int tmem_cols_for(int n) { return n <= 32 ? 32 : n <= 64 ? 64 : n <= 128 ? 128 : 256; }
+
+size_t gemm_smem_bytes(int block_n, int stages) {
+  // 1024 B alignment slack + stages * (A + B) + barriers
+  return 1024 + size_t(stages) * (a_stage_bytes() + b_stage_bytes(block_n)) + 256;
+}
+
+// -------------------------------------------------------------------------------------------------
+// Fused epilogue for one row and one chunk of CH accumulator columns.
+// -------------------------------------------------------------------------------------------------
+struct RowCtx {
+  bool valid;    // row inside the problem
+  long long m;   // output row index (token / pixel)
+};
+
+template <int CH>
+__device__ __forceinline__ void epilogue_chunk(const GemmEpilogue& e, const RowCtx& rc, float (&v)[CH], int col0,
+                                               int n_valid /* valid output columns from col0 */) {
+  // v[] already holds activation-applied values for output columns col0 .. col0 + CH
+  if (!rc.valid || n_valid <= 0) return;
+  const long long base = rc.m * (long long)e.ldo + col0;
+  const bool full = (n_valid >= CH) && ((e.ldo & 3) == 0) && ((col0 & 3) == 0);
+  if (e.residual) {
+    if (full) {
+      const float4* r4 = reinterpret_cast<const float4*>(e.residual + base);
+#pragma unroll
+      for (int i = 0; i < CH / 4; ++i) {
+        float4 r = __ldg(r4 + i);
+        v[4 * i + 0] += r.x; v[4 * i + 1] += r.y; v[4 * i + 2] += r.z; v[4 * i + 3] += r.w;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < CH; ++i)
+        if (i < n_valid) v[i] += __ldg(e.residual + base + i);
+    }
+  }
+  if (e.out_f32) {
+    if (full) {
+      float4* o4 = reinterpret_cast<float4*>(e.out_f32 + base);
+#pragma unroll
+      for (int i = 0; i < CH / 4; ++i) o4[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < CH; ++i)
+        if (i < n_valid) e.out_f32[base + i] = v[i];
+    }
+  }
+  if (e.out_bf16) {
+    if (full && ((e.ldo & 7) == 0) && ((col0 & 7) == 0)) {
+      uint4* o4 = reinterpret_cast<uint4*>(e.out_bf16 + base);
+#pragma unroll
+      for (int i = 0; i < CH / 8; ++i)
+        o4[i] = make_uint4(pack_bf16x2(v[8 * i], v[8 * i + 1]), pack_bf16x2(v[8 * i + 2], v[8 * i + 3]),
+                           pack_bf16x2(v[8 * i + 4], v[8 * i + 5]), pack_bf16x2(v[8 * i + 6], v[8 * i + 7]));
+    } else {
+#pragma unroll
+      for (int i = 0; i < CH; ++i)
+        if (i < n_valid) e.out_bf16[base + i] = __float2bfloat16(v[i]);
+    }
+  }
+}
+
+// Special small-N epilogues (N <= 16 accumulator columns, whole row in one chunk).
+__device__ __forceinline__ void epilogue_special(const GemmEpilogue& e, const RowCtx& rc, float (&v)[16], int N) {
+  if (!rc.valid) return;
+  if (e.flags & EPI_SCHED) {
+    const float kx = __ldg(e.sched_k + 0), kv = __ldg(e.sched_k + 1), kz = __ldg(e.sched_k + 2);
+    const long long base = rc.m * (long long)e.ldo;
+    for (int c = 0; c < N; ++c) {
+      float x = __ldg(e.sched_x + base + c);
+      float z = e.sched_z ? __ldg(e.sched_z + base + c) : 0.0f;
+      // written so that kz == 0 with z == 0 is exact
+      e.out_f32[base + c] = kx * x + kv * v[c] + kz * z;
+    }
+    return;
+  }
+  const long long img = rc.m / e.hw, pix = rc.m % e.hw;
+  if (e.flags & EPI_DEPTH) {
+    // reference marigold_depth_pipeline.py:515 (channel mean), :473 (clip), :475 (shift to [0,1])
+    float d = (v[0] + v[1] + v[2]) / 3.0f;
+    d = fminf(fmaxf(d, -1.0f), 1.0f);
+    e.out_f32[img * e.hw + pix] = (d + 1.0f) / 2.0f;
+    return;
+  }
+  if (e.flags & EPI_NORMALS) {
+    // reference marigold_normals_pipeline.py:438-440
+    float a = fminf(fmaxf(v[0], -1.0f), 1.0f), b = fminf(fmaxf(v[1], -1.0f), 1.0f),
+          c = fminf(fmaxf(v[2], -1.0f), 1.0f);
+    float nrm = fmaxf(sqrtf(a * a + b * b + c * c), 1e-6f);
+    float* o = e.out_f32 + img * 3 * e.hw + pix;
+    o[0] = a / nrm; o[e.hw] = b / nrm; o[2 * (long long)e.hw] = c / nrm;
+    return;
+  }
+  if (e.flags & EPI_NCHW) {
+    for (int c = 0; c < N; ++c) e.out_f32[(img * N + c) * e.hw + pix] = v[c];
+    return;
+  }
+}
+
+// -------------------------------------------------------------------------------------------------
+// The kernel
+// -------------------------------------------------------------------------------------------------
+template <int BLOCK_N>
+__global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_constant__ GemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  // SWIZZLE_128B tiles need 1024 B alignment
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int stages = p.stages;
+  constexpr int kABytes = a_stage_bytes();
+  constexpr int kBBytes = b_stage_bytes(BLOCK_N);
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + size_t(stages) * kABytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_b + size_t(stages) * kBBytes);
+  uint64_t* empty_bar = full_bar + stages;
+  uint64_t* tmem_full_bar = empty_bar + stages;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int m_tile = blockIdx.x, n_tile = blockIdx.y, split = blockIdx.z;
+  const int kb0 = split * p.kb_per_split;
+  const int kb1 = min(p.num_kb, kb0 + p.kb_per_split);
+
+  // conv tile decomposition
+  int img = 0, ty = 0, tx = 0;
+  if (p.mode == 1) {
+    const int per_img = p.tiles_x * p.tiles_y;
+    img = m_tile / per_img;
+    const int r = m_tile - img * per_img;
+    ty = r / p.tiles_x;
+    tx = r - ty * p.tiles_x;
+  }
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tmap_a);
+    tma_prefetch_desc(&p.tmap_b);
+    for (int s = 0; s < stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    fence_mbar_init();
+  }
+  constexpr uint32_t kTmemCols = tmem_cols_for(BLOCK_N);
+  if (warp == 1) {
+    tmem_alloc(tmem_ptr_smem, kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        mbar_arrive_expect_tx(&full_bar[stage], kABytes + kBBytes);
+        void* sa = smem_a + size_t(stage) * kABytes;
+        void* sb = smem_b + size_t(stage) * kBBytes;
+        if (p.mode == 0) {
+          tma_load_2d(sa, &p.tmap_a, &full_bar[stage], kb * BLOCK_K, m_tile * BLOCK_M);
+        } else {
+          const int tap = kb / p.cblocks;
+          const int cb = kb - tap * p.cblocks;
+          tma_load_5d(sa, &p.tmap_a, &full_bar[stage], cb * BLOCK_K, tx * p.tile_w + p.tap_dx[tap],
+                      ty * p.tile_h + p.tap_dy[tap], p.tap_p[tap], img);
+        }
+        tma_load_2d(sb, &p.tmap_b, &full_bar[stage], kb * BLOCK_K, n_tile * BLOCK_N);
+        if (++stage == stages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t idesc = umma_idesc_bf16(BLOCK_M, BLOCK_N);
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int kb = kb0; kb < kb1; ++kb) {
+      mbar_wait(&full_bar[stage], phase);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint64_t da = umma_desc_sw128(smem_u32(smem_a + size_t(stage) * kABytes));
+        const uint64_t db = umma_desc_sw128(smem_u32(smem_b + size_t(stage) * kBBytes));
+#pragma unroll
+        for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+          // advance the start address by k * 32 B inside the 128 B swizzle atom
+          umma_bf16(tmem_base, da + uint64_t(k * 2), db + uint64_t(k * 2), idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+        }
+        umma_commit(&empty_bar[stage]);
+        if (kb == kb1 - 1) umma_commit(tmem_full_bar);
+      }
+      __syncwarp();
+      if (++stage == stages) { stage = 0; phase ^= 1; }
+    }
+  } else {
+    // ===================== epilogue =====================
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int row = q * 32 + lane;
+    RowCtx rc;
+    if (p.mode == 0) {
+      rc.m = (long long)m_tile * BLOCK_M + row;
+      rc.valid = rc.m < p.M;
+    } else {
+      const int hh = row / p.tile_w, ww = row - hh * p.tile_w;
+      const int h = ty * p.tile_h + hh, w = tx * p.tile_w + ww;
+      rc.valid = (h < p.H) && (w < p.W);
+      rc.m = ((long long)img * p.H + h) * p.W + w;
+    }
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+    const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16);
+    const GemmEpilogue& e = p.epi;
+    const int n0 = n_tile * BLOCK_N;
+
+    if (p.partial != nullptr) {
+      // split-K: raw accumulators to the workspace, epilogue deferred
+      float* dst = p.partial + ((long long)split * p.M + rc.m) * p.N + n0;
+      if constexpr (BLOCK_N >= 32) {
+#pragma unroll 1
+        for (int j = 0; j < BLOCK_N / 32; ++j) {
+          uint32_t r[32];
+          tmem_ld32(taddr + j * 32, r);
+          tmem_wait_ld();
+          if (rc.valid) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (n0 + j * 32 + i < p.N) dst[j * 32 + i] = __uint_as_float(r[i]);
+          }
+        }
+      } else {
+        uint32_t r[16];
+        tmem_ld16(taddr, r);
+        tmem_wait_ld();
+        if (rc.valid) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            if (n0 + i < p.N) dst[i] = __uint_as_float(r[i]);
+        }
+      }
+    } else if constexpr (BLOCK_N == 16) {
+      uint32_t r[16];
+      tmem_ld16(taddr, r);
+      tmem_wait_ld();
+      float v[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        v[i] = __uint_as_float(r[i]);
+        if (e.bias && (n0 + i) < p.N) v[i] += __ldg(e.bias + n0 + i);
+      }
+      if (e.flags & (EPI_SCHED | EPI_DEPTH | EPI_NORMALS | EPI_NCHW)) {
+        epilogue_special(e, rc, v, p.N);
+      } else {
+        epilogue_chunk<16>(e, rc, v, n0, p.N - n0);
+      }
+    } else if (e.flags & EPI_GEGLU) {
+      // tile = [BLOCK_N/2 value columns | BLOCK_N/2 gate columns]
+      if constexpr (BLOCK_N % 64 == 0) {
+        constexpr int HALF = BLOCK_N / 2;
+#pragma unroll 1
+        for (int j = 0; j < HALF / 32; ++j) {
+          uint32_t rv[32], rg[32];
+          tmem_ld32(taddr + j * 32, rv);
+          tmem_ld32(taddr + HALF + j * 32, rg);
+          tmem_wait_ld();
+          float v[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            float val = __uint_as_float(rv[i]) + __ldg(e.bias + n0 + j * 32 + i);
+            float gate = __uint_as_float(rg[i]) + __ldg(e.bias + n0 + HALF + j * 32 + i);
+            v[i] = val * gelu_erf_f(gate);
+          }
+          const int col0 = n_tile * HALF + j * 32;
+          epilogue_chunk<32>(e, rc, v, col0, p.N / 2 - col0);
+        }
+      }
+    } else {
+      if constexpr (BLOCK_N >= 32) {
+#pragma unroll 1
+        for (int j = 0; j < BLOCK_N / 32; ++j) {
+          uint32_t r[32];
+          tmem_ld32(taddr + j * 32, r);
+          tmem_wait_ld();
+          float v[32];
+          const int col0 = n0 + j * 32;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            float a = __uint_as_float(r[i]);
+            if (e.flags & EPI_SCALE) a *= e.scale;
+            if (e.bias && (col0 + i) < p.N) a += __ldg(e.bias + col0 + i);
+            if (e.flags & EPI_SILU) a = silu_f(a);
+            v[i] = a;
+          }
+          epilogue_chunk<32>(e, rc, v, col0, p.N - col0);
+        }
+      }
+    }
+    tc_fence_before();
+  }
+
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// -------------------------------------------------------------------------------------------------
+// Split-K deferred epilogue: sum partials, then the same fused epilogue on CUDA cores.
+// One thread per (row, 4 columns).
+// -------------------------------------------------------------------------------------------------
+__global__ void splitk_epilogue_kernel(const GemmParams p, int splits, int geglu_half /* BLOCK_N/2 or 0 */) {
+  const GemmEpilogue& e = p.epi;
+  const int n_out = geglu_half ? p.N / 2 : p.N;
+  const long long total = (long long)p.M * n_out;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const long long m = idx / n_out;
+    const int c = int(idx - m * n_out);
+    float out;
+    if (geglu_half) {
+      const int tile = c / geglu_half, within = c - tile * geglu_half;
+      const int cv = tile * 2 * geglu_half + within, cg = cv + geglu_half;
+      float v = 0.f, g = 0.f;
+      for (int s = 0; s < splits; ++s) {
+        v += p.partial[((long long)s * p.M + m) * p.N + cv];
+        g += p.partial[((long long)s * p.M + m) * p.N + cg];
+      }
+      v += __ldg(e.bias + cv);
+      g += __ldg(e.bias + cg);
+      out = v * gelu_erf_f(g);
+    } else {
+      float a = 0.f;
+      for (int s = 0; s < splits; ++s) a += p.partial[((long long)s * p.M + m) * p.N + c];
+      if (e.flags & EPI_SCALE) a *= e.scale;
+      if (e.bias) a += __ldg(e.bias + c);
+      if (e.flags & EPI_SILU) a = silu_f(a);
+      out = a;
+    }
+    const long long o = m * (long long)e.ldo + c;
+    if (e.residual) out += __ldg(e.residual + o);
+    if (e.out_f32) e.out_f32[o] = out;
+    if (e.out_bf16) e.out_bf16[o] = __float2bfloat16(out);
+  }
+}
+
+// -------------------------------------------------------------------------------------------------
+// host side
+// -------------------------------------------------------------------------------------------------
+template <int BN>
+static int launch_one(const GemmParams& p, int splits, cudaStream_t stream) {
+  const size_t smem = gemm_smem_bytes(BN, p.stages);
+  static bool attr_set = false;  // per template instantiation
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return int(e);
+    attr_set = true;
+  }
+  int m_tiles;
+  if (p.mode == 0) {
+    m_tiles = (p.M + BLOCK_M - 1) / BLOCK_M;
+  } else {
+    m_tiles = (p.M / (p.H * p.W)) * p.tiles_x * p.tiles_y;
+  }
+  dim3 grid(m_tiles, (p.N + BN - 1) / BN, splits);
+  gemm_tc_kernel<BN><<<grid, kGemmThreads, smem, stream>>>(p);
+  return int(cudaGetLastError());
+}
+
+int launch_gemm_tc(const GemmParams& p, int block_n, int splits, cudaStream_t stream) {
+  switch (block_n) {
+    case 16: return launch_one<16>(p, splits, stream);
+    case 32: return launch_one<32>(p, splits, stream);
+    case 64: return launch_one<64>(p, splits, stream);
+    case 128: return launch_one<128>(p, splits, stream);
+    case 160: return launch_one<160>(p, splits, stream);
+    case 256: return launch_one<256>(p, splits, stream);
+    default: return int(cudaErrorInvalidValue);
+  }
+}
+
+int launch_splitk_epilogue(const GemmParams& p, int block_n, int splits, cudaStream_t stream) {
+  const int n_out = (p.epi.flags & EPI_GEGLU) ? p.N / 2 : p.N;
+  const long long total = (long long)p.M * n_out;
+  int blocks = int(std::min<long long>((total + 255) / 256, 148 * 8));
+  splitk_epilogue_kernel<<<blocks, 256, 0, stream>>>(p, splits, (p.epi.flags & EPI_GEGLU) ? block_n / 2 : 0);
+  return int(cudaGetLastError());
+}
+
+// ---- tensor maps ----
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static PFN_encodeTiled get_encode() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(ptr);
+  }
+  return fn;
+}
+
+static int make_tmap(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides,
+                     const uint32_t* box) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled entry point unavailable");
+    return MGB_ERR_CUDA;
+  }
+  cuuint64_t gdim[5], gstr[4];
+  cuuint32_t bdim[5], estr[5];
+  for (int i = 0; i < rank; ++i) { gdim[i] = dims[i]; bdim[i] = box[i]; estr[i] = 1; }
+  for (int i = 0; i < rank - 1; ++i) gstr[i] = strides[i];
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(base), gdim, gstr, bdim, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (%d): rank=%d dims=[%llu,%llu,..] box=[%u,%u,..] base=%p", int(r), rank,
+              (unsigned long long)dims[0], (unsigned long long)dims[1], box[0], box[1], base);
+    return MGB_ERR_CUDA;
+  }
+  return MGB_OK;
+}
+
+int make_tmap_2d(CUtensorMap* out, const void* base, uint64_t inner, uint64_t outer, uint64_t row_stride_bytes,
+                 uint32_t box_inner, uint32_t box_outer) {
+  uint64_t dims[2] = {inner, outer};
+  uint64_t strides[1] = {row_stride_bytes};
+  uint32_t box[2] = {box_inner, box_outer};
+  return make_tmap(out, base, 2, dims, strides, box);
+}
+int make_tmap_3d(CUtensorMap* out, const void* base, const uint64_t dims[3], const uint64_t strides_bytes[2],
+                 const uint32_t box[3]) {
+  return make_tmap(out, base, 3, dims, strides_bytes, box);
+}
+int make_tmap_5d(CUtensorMap* out, const void* base, const uint64_t dims[5], const uint64_t strides_bytes[4],
+                 const uint32_t box[5]) {
+  return make_tmap(out, base, 5, dims, strides_bytes, box);
+}
+
+}  // namespace mgb

@@ -1,0 +1,130 @@
+// Host-visible declarations of every kernel launcher in libmarigold_b200. Plain C++ (no torch).
+// Tensors are NHWC ("tokens x channels") inside the library; NCHW only exists at the C ABI.
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/marigold_b200.h"
+
+namespace mgb {
+
+typedef __nv_bfloat16 bf16;
+
+// error plumbing (api.cu)
+void set_error(const char* fmt, ...);
+const char* get_error();
+
+// ---------------------------------------------------------------------------------------------
+// tcgen05 GEMM / implicit-GEMM convolution
+//   D[M, N] = A[M, K] * B[N, K]^T   (A, B bf16 K-major; fp32 accumulation in TMEM)
+// ---------------------------------------------------------------------------------------------
+enum : int {
+  EPI_GEGLU = 1,        // acc tile = [value | gate] halves; out = (v + bv) * gelu_erf(g + bg)
+  EPI_SCHED = 2,        // out_f32 = kx * sched_x + kv * (acc + bias) + kz * sched_z   (conv_out + DDIM/LCM step)
+  EPI_DEPTH = 4,        // N == 3: out_f32[img, h, w] = (clip(mean_c, -1, 1) + 1) / 2              (NCHW, 1 plane)
+  EPI_NORMALS = 8,      // N == 3: clip to [-1, 1], divide by max(||.||, 1e-6); out_f32 NCHW, 3 planes
+  EPI_NCHW = 16,        // out_f32 written as NCHW planes [img, c, h*w] (needs hw)
+  EPI_SILU = 32,        // out = silu(acc + bias)
+  EPI_SCALE = 64,       // acc *= scale before bias (used for attention-score GEMMs)
+};
+
+struct GemmEpilogue {
+  const float* bias;      // [N] in accumulator-column order, or nullptr
+  const float* residual;  // fp32 [M, ldo] added after activation, or nullptr
+  float* out_f32;         // fp32 [M, ldo] or nullptr
+  bf16* out_bf16;         // bf16 [M, ldo] or nullptr
+  int ldo;                // row stride of residual / outputs (elements)
+  int flags;
+  int hw;                 // pixels per image (EPI_NCHW / EPI_DEPTH / EPI_NORMALS)
+  float scale;            // EPI_SCALE
+  const float* sched_x;   // EPI_SCHED: current latent  [M, ldo]
+  const float* sched_z;   // EPI_SCHED: fresh noise     [M, ldo] or nullptr
+  const float* sched_k;   // EPI_SCHED: device pointer to {kx, kv, kz}
+};
+
+struct GemmParams {
+  CUtensorMap tmap_a;  // mode 0: 2D {K, M}; mode 1: 5D {C, W, H, P, NB}
+  CUtensorMap tmap_b;  // 2D {K, N}
+  int mode;            // 0 = row-major activations, 1 = implicit conv over an NHWC image
+  int M, N;            // logical GEMM rows / accumulator columns
+  int num_kb;          // total K blocks of 64
+  int kb_per_split;    // K blocks per blockIdx.z
+  int stages;          // smem pipeline depth
+  // conv geometry (mode 1)
+  int H, W;            // OUTPUT image size
+  int tile_w, tile_h;  // tile_w * tile_h == 128
+  int tiles_x, tiles_y;
+  int cblocks;         // Cin / 64
+  int ntaps;
+  int8_t tap_p[12], tap_dy[12], tap_dx[12];
+  float* partial;      // split-K: fp32 [splits, M, N] raw accumulators (epilogue deferred)
+  GemmEpilogue epi;
+};
+
+// Launch. block_n in {16, 32, 64, 128, 160, 256}. Returns cudaError_t as int.
+int launch_gemm_tc(const GemmParams& p, int block_n, int splits, cudaStream_t stream);
+// Deferred epilogue for split-K: sums `splits` partials and applies p.epi.
+int launch_splitk_epilogue(const GemmParams& p, int block_n, int splits, cudaStream_t stream);
+size_t gemm_smem_bytes(int block_n, int stages);
+
+// Tensor-map helpers (driver entry point fetched through the runtime; no -lcuda needed).
+int make_tmap_2d(CUtensorMap* out, const void* base, uint64_t inner, uint64_t outer, uint64_t row_stride_bytes,
+                 uint32_t box_inner, uint32_t box_outer);
+int make_tmap_3d(CUtensorMap* out, const void* base, const uint64_t dims[3], const uint64_t strides_bytes[2],
+                 const uint32_t box[3]);
+int make_tmap_5d(CUtensorMap* out, const void* base, const uint64_t dims[5], const uint64_t strides_bytes[4],
+                 const uint32_t box[5]);
+
+// ---------------------------------------------------------------------------------------------
+// Flash self-attention, head_dim 64 (attn_tc.cu)
+//   qkv: bf16 [NB * T, 3 * C] (Q | K | V blocks, head h at columns h*64..), out: bf16 [NB * T, C]
+// ---------------------------------------------------------------------------------------------
+int launch_flash_attn64(const bf16* qkv, bf16* out, int NB, int T, int C, float scale, cudaStream_t stream);
+
+// ---------------------------------------------------------------------------------------------
+// Memory-bound kernels (norm.cu, elementwise.cu)
+// ---------------------------------------------------------------------------------------------
+// GroupNorm over NHWC: stats over (pixels x C/G channels) per image and group.
+//   x_f32 [NB, HW, C] -> y_bf16 = act((x - mean) * rstd * gamma + beta); optional raw bf16 copy.
+int launch_groupnorm(const float* x, bf16* y, bf16* raw_copy, const float* gamma, const float* beta, float* ws,
+                     int NB, int HW, int C, int G, float eps, int silu, cudaStream_t stream);
+size_t groupnorm_ws_bytes(int NB, int HW, int C, int G);
+// LayerNorm over the channel dim: x_f32 [M, C] -> y_bf16 [M, C]
+int launch_layernorm(const float* x, bf16* y, const float* gamma, const float* beta, int M, int C, float eps,
+                     cudaStream_t stream);
+// y[NB, 4, H/2, W/2, C] (parity planes p = (h&1)*2 + (w&1)) from x fp32 [NB, H, W, C]
+int launch_space_to_depth(const float* x, bf16* y, int NB, int H, int W, int C, cudaStream_t stream);
+// nearest x2: x fp32 [NB, H, W, C] -> y bf16 [NB, 2H, 2W, C]
+int launch_upsample2x(const float* x, bf16* y, int NB, int H, int W, int C, cudaStream_t stream);
+// channel concat (fp32): out[M, Ca + Cb] = [a | b]
+int launch_concat(const float* a, const float* b, float* out, int M, int Ca, int Cb, cudaStream_t stream);
+// fp32 -> bf16 cast
+int launch_cast_bf16(const float* x, bf16* y, size_t n, cudaStream_t stream);
+// UNet conv_in operand: [rgb(4) | target(4) | zeros(56)] bf16 NHWC-64 from two fp32 NHWC-4 latents
+int launch_pack_latents(const float* rgb, const float* tgt, bf16* out, int M, cudaStream_t stream);
+// NCHW fp32 <-> NHWC fp32 (small tensors at the ABI)
+int launch_nchw_to_nhwc(const float* x, float* y, int NB, int C, int HW, float scale, cudaStream_t stream);
+int launch_nhwc_to_nchw(const float* x, float* y, int NB, int C, int HW, float scale, cudaStream_t stream);
+// rgb [NB,3,H,W] (fp32, already in [-1,1]) -> bf16 NHWC with 64 channels (3 real + zero padding)
+int launch_pack_rgb(const float* rgb_nchw, bf16* out, int NB, int HW, cudaStream_t stream);
+// 2-key cross attention with pre-projected K/V: q bf16 [M, C]; kv fp32 [2(k|v), 2(tokens), C]; out bf16 [M, C]
+int launch_cross_attn2(const bf16* q, const float* kv, bf16* out, int M, int C, float scale, cudaStream_t stream);
+// Tiny dense layer for M <= 16 rows (time MLP, text K/V): y[M,N] = act(x[M,K]) W[N,K]^T + b ; fp32
+int launch_linear_small(const float* x, const float* w, const float* b, float* y, int M, int N, int K,
+                        int silu_in, int silu_out, cudaStream_t stream);
+// sinusoidal timestep embedding (flip_sin_to_cos, shift 0): t[M] -> emb[M, dim] = [cos | sin]
+int launch_timestep_embedding(const float* t, float* emb, int M, int dim, cudaStream_t stream);
+// row softmax over bf16 scores in place: s[M, ld] (first n valid), fp32 math
+int launch_softmax_rows(bf16* s, int M, int n, int ld, cudaStream_t stream);
+// out[M, N] fp32 row-major -> bf16 transposed [N, M]
+int launch_transpose_bf16(const bf16* x, bf16* y, int M, int N, cudaStream_t stream);
+
+// ---------------------------------------------------------------------------------------------
+// Ensemble kernels (ensemble.cu)
+// ---------------------------------------------------------------------------------------------
+int launch_ens_depth_cost(const float* depth, const float* s, const float* t, int E, int HW, float* ws,
+                          double* out_host_pinned, cudaStream_t stream);
+
+}  // namespace mgb

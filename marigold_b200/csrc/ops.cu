@@ -1,0 +1,187 @@
+// Host-side operator builders: turn "linear" / "conv2d" requests into GemmParams (tensor maps, tile
+// geometry, tap tables) and pick tile shapes. Used by the network composition (net.cu) and by the
+// operator-level C ABI (api.cu).
+#include <algorithm>
+#include <cstring>
+
+#include "kernels.h"
+#include "ops.h"
+
+namespace mgb {
+
+static std::atomic<long long> g_launches{0};
+void count_launch(int n) { g_launches += n; }
+long long launch_count() { return g_launches.load(); }
+
+void conv_tile_shape(int Hout, int Wout, int* tile_w, int* tile_h) {
+  int best_w = 16, best_tiles = 1 << 30;
+  const int cands[5] = {128, 64, 32, 16, 8};
+  for (int tw : cands) {
+    const int th = 128 / tw;
+    const int tiles = ((Wout + tw - 1) / tw) * ((Hout + th - 1) / th);
+    if (tiles < best_tiles) { best_tiles = tiles; best_w = tw; }
+  }
+  *tile_w = best_w;
+  *tile_h = 128 / best_w;
+}
+
+int fill_linear_params(GemmParams* p, const bf16* a, const bf16* w, int M, int N, int K, int block_n, int splits,
+                       int stages) {
+  memset(p, 0, sizeof(*p));
+  if (K % 64 != 0 || M <= 0 || N <= 0) {
+    set_error("linear: need K %% 64 == 0 (got M=%d N=%d K=%d)", M, N, K);
+    return MGB_ERR_INVALID;
+  }
+  p->mode = 0;
+  p->M = M; p->N = N;
+  p->num_kb = K / 64;
+  if (splits < 1) splits = 1;
+  splits = std::min(splits, p->num_kb);
+  p->kb_per_split = (p->num_kb + splits - 1) / splits;
+  p->stages = stages;
+  int rc = make_tmap_2d(&p->tmap_a, a, uint64_t(K), uint64_t(M), uint64_t(K) * 2, 64, 128);
+  if (rc) return rc;
+  rc = make_tmap_2d(&p->tmap_b, w, uint64_t(K), uint64_t(N), uint64_t(K) * 2, 64, uint32_t(block_n));
+  return rc;
+}
+
+int fill_conv_params(GemmParams* p, const bf16* x, const bf16* w, int NB, int Hout, int Wout, int Cin, int Cout,
+                     int kind, int block_n, int splits, int stages) {
+  memset(p, 0, sizeof(*p));
+  if (Cin % 64 != 0 || NB <= 0 || Hout <= 0 || Wout <= 0) {
+    set_error("conv2d: need Cin %% 64 == 0 (got NB=%d H=%d W=%d Cin=%d)", NB, Hout, Wout, Cin);
+    return MGB_ERR_INVALID;
+  }
+  p->mode = 1;
+  p->M = NB * Hout * Wout;
+  p->N = Cout;
+  p->H = Hout; p->W = Wout;
+  conv_tile_shape(Hout, Wout, &p->tile_w, &p->tile_h);
+  p->tiles_x = (Wout + p->tile_w - 1) / p->tile_w;
+  p->tiles_y = (Hout + p->tile_h - 1) / p->tile_h;
+  p->cblocks = Cin / 64;
+  int planes = 1;
+  if (kind == 0) {
+    p->ntaps = 9;
+    for (int kh = 0; kh < 3; ++kh)
+      for (int kw = 0; kw < 3; ++kw) {
+        const int t = kh * 3 + kw;
+        p->tap_p[t] = 0; p->tap_dy[t] = int8_t(kh - 1); p->tap_dx[t] = int8_t(kw - 1);
+      }
+  } else if (kind == 1) {
+    p->ntaps = 1;
+  } else if (kind == 2 || kind == 3) {
+    // stride-2 over the 4 parity planes p = (h & 1) * 2 + (w & 1) of the input
+    //   kind 2 (pad 1):          input row 2*oh + kh - 1 -> kh=0: (odd, -1)  kh=1: (even, 0)  kh=2: (odd, 0)
+    //   kind 3 (pad (0,1,0,1)):  input row 2*oh + kh     -> kh=0: (even, 0)  kh=1: (odd, 0)   kh=2: (even, +1)
+    planes = 4;
+    p->ntaps = 9;
+    const int par2[3] = {1, 0, 1}, off2[3] = {-1, 0, 0};
+    const int par3[3] = {0, 1, 0}, off3[3] = {0, 0, 1};
+    for (int kh = 0; kh < 3; ++kh)
+      for (int kw = 0; kw < 3; ++kw) {
+        const int t = kh * 3 + kw;
+        const int ph = kind == 2 ? par2[kh] : par3[kh], pw = kind == 2 ? par2[kw] : par3[kw];
+        p->tap_p[t] = int8_t(ph * 2 + pw);
+        p->tap_dy[t] = int8_t(kind == 2 ? off2[kh] : off3[kh]);
+        p->tap_dx[t] = int8_t(kind == 2 ? off2[kw] : off3[kw]);
+      }
+  } else {
+    set_error("conv2d: unknown kind %d", kind);
+    return MGB_ERR_INVALID;
+  }
+  p->num_kb = p->ntaps * p->cblocks;
+  if (splits < 1) splits = 1;
+  splits = std::min(splits, p->num_kb);
+  p->kb_per_split = (p->num_kb + splits - 1) / splits;
+  p->stages = stages;
+
+  const uint64_t C2 = uint64_t(Cin) * 2;
+  const uint64_t dims[5] = {uint64_t(Cin), uint64_t(Wout), uint64_t(Hout), uint64_t(planes), uint64_t(NB)};
+  const uint64_t strides[4] = {C2, C2 * Wout, C2 * Wout * Hout, C2 * Wout * Hout * planes};
+  const uint32_t box[5] = {64, uint32_t(p->tile_w), uint32_t(p->tile_h), 1, 1};
+  int rc = make_tmap_5d(&p->tmap_a, x, dims, strides, box);
+  if (rc) return rc;
+  const uint64_t Ktot = uint64_t(p->ntaps) * Cin;
+  rc = make_tmap_2d(&p->tmap_b, w, Ktot, uint64_t(Cout), Ktot * 2, 64, uint32_t(block_n));
+  return rc;
+}
+
+int effective_splits(const GemmParams& p) { return (p.num_kb + p.kb_per_split - 1) / p.kb_per_split; }
+
+int run_gemm(GemmParams& p, int block_n, float* splitk_ws, cudaStream_t stream) {
+  const int splits = effective_splits(p);
+  if ((p.epi.flags & EPI_GEGLU) && (block_n % 64 != 0)) {
+    set_error("GEGLU epilogue needs block_n %% 64 == 0 (got %d)", block_n);
+    return MGB_ERR_INVALID;
+  }
+  if (p.stages < 2 || gemm_smem_bytes(block_n, p.stages) > 227 * 1024) {
+    set_error("gemm: stages=%d does not fit shared memory for block_n=%d", p.stages, block_n);
+    return MGB_ERR_INVALID;
+  }
+  if (splits > 1) {
+    if (!splitk_ws) {
+      set_error("split-K requested without a workspace");
+      return MGB_ERR_INVALID;
+    }
+    if (p.epi.flags & (EPI_SCHED | EPI_DEPTH | EPI_NORMALS | EPI_NCHW)) {
+      set_error("split-K is not supported with small-N special epilogues");
+      return MGB_ERR_INVALID;
+    }
+    p.partial = splitk_ws;
+  } else {
+    p.partial = nullptr;
+  }
+  int e = launch_gemm_tc(p, block_n, splits, stream);
+  if (e) {
+    set_error("gemm_tc launch failed: %s", cudaGetErrorString(cudaError_t(e)));
+    return MGB_ERR_CUDA;
+  }
+  count_launch(1);
+  if (splits > 1) {
+    e = launch_splitk_epilogue(p, block_n, splits, stream);
+    if (e) {
+      set_error("splitk epilogue launch failed: %s", cudaGetErrorString(cudaError_t(e)));
+      return MGB_ERR_CUDA;
+    }
+    count_launch(1);
+  }
+  return MGB_OK;
+}
+
+// Tile-shape heuristic. Cost model (cycles): per CTA  num_kb * 2*BN (tcgen05 floor at M=128)
+// + epilogue ~ 6*BN + fixed 3000; CTAs run in waves of 148 (1 CTA/SM).
+void choose_tile(int m_tiles, int N, int num_kb, bool geglu, bool allow_split, int* block_n, int* splits,
+                 int* stages) {
+  const int cands[6] = {256, 160, 128, 64, 32, 16};
+  double best = 1e30;
+  int bbn = 128, bsp = 1;
+  for (int bn : cands) {
+    if (geglu && (bn % 64 != 0)) continue;
+    if (bn > 64 && N < bn / 2 + 1) continue;  // mostly padding
+    const int n_tiles = (N + bn - 1) / bn;
+    const double waste = double(n_tiles) * bn / N;  // MMA work on padded columns is still paid
+    (void)waste;
+    for (int sp = 1; sp <= (allow_split ? 16 : 1); ++sp) {
+      if (sp > 1 && num_kb / sp < 4) break;
+      const long long ctas = (long long)m_tiles * n_tiles * sp;
+      const long long waves = (ctas + 147) / 148;
+      const int kb = (num_kb + sp - 1) / sp;
+      double cta_cycles = double(kb) * 2.0 * bn + 6.0 * bn + 3000.0;
+      // small tiles are smem-bandwidth bound: A (16 KB) + B per k-block at 128 B/cycle
+      const double smem_cycles = double(kb) * (16384.0 + bn * 128.0) / 128.0 + 6.0 * bn + 3000.0;
+      cta_cycles = std::max(cta_cycles, smem_cycles);
+      double t = waves * cta_cycles;
+      if (sp > 1) t += 4000.0 + double(m_tiles) * 128.0 * N * sp * 4.0 / (148.0 * 64.0);  // reduce pass
+      if (t < best) { best = t; bbn = bn; bsp = sp; }
+    }
+  }
+  *block_n = bbn;
+  *splits = bsp;
+  const int stage_bytes = 16384 + bbn * 128;
+  int st = int((200 * 1024) / stage_bytes);
+  st = std::max(2, std::min(st, 8));
+  *stages = st;
+}
+
+}  // namespace mgb
