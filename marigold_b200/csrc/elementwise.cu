@@ -312,4 +312,39 @@ int launch_transpose_bf16(const bf16* x, bf16* y, int M, int N, cudaStream_t str
   MGB_LAUNCH_CHECK("transpose_bf16");
 }
 
+// Decoder input: z = post_quant_conv(latent / scale) (1x1, 4 -> 4, fp32) packed as bf16 NHWC-64.
+// reference marigold_depth_pipeline.py:510-512. latent fp32 NCHW [NB, 4, HW].
+__global__ void pack_decoder_latent_kernel(const float* __restrict__ lat, const float* __restrict__ w,
+                                           const float* __restrict__ b, float inv_scale, uint4* __restrict__ out,
+                                           int NB, size_t HW) {
+  const size_t total = (size_t)NB * HW * 8;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t m = i >> 3;
+    const int part = int(i & 7);
+    uint4 o = make_uint4(0, 0, 0, 0);
+    if (part == 0) {
+      const size_t n = m / HW, p = m % HW;
+      float x[4], z[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) x[c] = __ldg(lat + (n * 4 + c) * HW + p) * inv_scale;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        float a = __ldg(b + c);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) a += __ldg(w + c * 4 + j) * x[j];
+        z[c] = a;
+      }
+      o.x = pack_bf16x2(z[0], z[1]);
+      o.y = pack_bf16x2(z[2], z[3]);
+    }
+    out[i] = o;
+  }
+}
+int launch_pack_decoder_latent(const float* latent_nchw, const float* w, const float* b, float inv_scale, bf16* out,
+                               int NB, int HW, cudaStream_t stream) {
+  pack_decoder_latent_kernel<<<grid_for((size_t)NB * HW * 8, 256), 256, 0, stream>>>(
+      latent_nchw, w, b, inv_scale, reinterpret_cast<uint4*>(out), NB, size_t(HW));
+  MGB_LAUNCH_CHECK("pack_decoder_latent");
+}
+
 }  // namespace mgb

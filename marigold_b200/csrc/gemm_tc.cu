@@ -102,6 +102,7 @@ __device__ __forceinline__ void epilogue_special(const GemmEpilogue& e, const Ro
     for (int c = 0; c < N; ++c) {
       float x = __ldg(e.sched_x + base + c);
       float z = e.sched_z ? __ldg(e.sched_z + base + c) : 0.0f;
+      if (e.aux_out) e.aux_out[base + c] = v[c];
       // written so that kz == 0 with z == 0 is exact
       e.out_f32[base + c] = kx * x + kv * v[c] + kz * z;
     }
@@ -281,6 +282,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
         v[i] = __uint_as_float(r[i]);
+        if (e.flags & EPI_SCALE) v[i] *= e.scale;
         if (e.bias && (n0 + i) < p.N) v[i] += __ldg(e.bias + n0 + i);
       }
       if (e.flags & (EPI_SCHED | EPI_DEPTH | EPI_NORMALS | EPI_NCHW)) {

@@ -42,6 +42,7 @@ struct GemmEpilogue {
   const float* sched_x;   // EPI_SCHED: current latent  [M, ldo]
   const float* sched_z;   // EPI_SCHED: fresh noise     [M, ldo] or nullptr
   const float* sched_k;   // EPI_SCHED: device pointer to {kx, kv, kz}
+  float* aux_out;         // EPI_SCHED: optional raw model output (acc + bias) [M, ldo], or nullptr
 };
 
 struct GemmParams {
@@ -109,6 +110,9 @@ int launch_nchw_to_nhwc(const float* x, float* y, int NB, int C, int HW, float s
 int launch_nhwc_to_nchw(const float* x, float* y, int NB, int C, int HW, float scale, cudaStream_t stream);
 // rgb [NB,3,H,W] (fp32, already in [-1,1]) -> bf16 NHWC with 64 channels (3 real + zero padding)
 int launch_pack_rgb(const float* rgb_nchw, bf16* out, int NB, int HW, cudaStream_t stream);
+// decoder input: post_quant_conv(latent / scale) -> bf16 NHWC-64; latent fp32 NCHW [NB,4,HW]; w fp32 [4,4]
+int launch_pack_decoder_latent(const float* latent_nchw, const float* w, const float* b, float inv_scale, bf16* out,
+                               int NB, int HW, cudaStream_t stream);
 // 2-key cross attention with pre-projected K/V: q bf16 [M, C]; kv fp32 [2(k|v), 2(tokens), C]; out bf16 [M, C]
 int launch_cross_attn2(const bf16* q, const float* kv, bf16* out, int M, int C, float scale, cudaStream_t stream);
 // Tiny dense layer for M <= 16 rows (time MLP, text K/V): y[M,N] = act(x[M,K]) W[N,K]^T + b ; fp32

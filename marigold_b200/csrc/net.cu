@@ -1,0 +1,434 @@
+// Forward graphs of the Marigold hot path, as sequences of kernels.h launches on one stream:
+//   UNet step   (diffusers UNet2DConditionModel, SD-2 config)   reference call: marigold_depth_pipeline.py:461-463
+//   VAE encode  (AutoencoderKL.encoder + quant_conv)            reference call: marigold_depth_pipeline.py:491-495
+//   VAE decode  (post_quant_conv + AutoencoderKL.decoder)       reference call: marigold_depth_pipeline.py:510-515
+// Architecture per SURVEY.md App. A (restated; diffusers itself is not available offline).
+//
+// Numerics: bf16 tensor-core operands, fp32 accumulation, fp32 residual trunk and latent state;
+// GroupNorm/LayerNorm/softmax statistics in fp32.
+#include <cmath>
+#include <cstring>
+
+#include "net.h"
+
+namespace mgb {
+
+#define TRY(expr)               \
+  do {                          \
+    int _rc = (expr);           \
+    if (_rc != MGB_OK) return _rc; \
+  } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// arena
+// ---------------------------------------------------------------------------------------------
+void* Arena::alloc(size_t bytes) {
+  const size_t a = (off + 1023) & ~size_t(1023);
+  off = a + bytes;
+  if (off > peak) peak = off;
+  if (dry) return reinterpret_cast<void*>(uintptr_t(0x100000) + a);
+  if (off > cap) { overflow = true; return nullptr; }
+  return base + a;
+}
+template <typename T>
+static T* aalloc(Ctx& c, size_t n) { return reinterpret_cast<T*>(c.arena->alloc(n * sizeof(T))); }
+
+// ---------------------------------------------------------------------------------------------
+// launch wrappers (skipped in dry-run mode, which only measures arena / split-K needs)
+// ---------------------------------------------------------------------------------------------
+struct Epi {
+  const float* bias = nullptr;
+  const float* residual = nullptr;
+  float* out_f32 = nullptr;
+  bf16* out_bf16 = nullptr;
+  int flags = 0;
+  float scale = 1.f;
+  int hw = 0;
+  const float* sched_x = nullptr;
+  const float* sched_z = nullptr;
+  const float* sched_k = nullptr;
+  float* aux_out = nullptr;
+};
+
+static void set_epi(GemmParams& p, const Epi& e, int ldo) {
+  p.epi.bias = e.bias; p.epi.residual = e.residual; p.epi.out_f32 = e.out_f32; p.epi.out_bf16 = e.out_bf16;
+  p.epi.ldo = ldo; p.epi.flags = e.flags; p.epi.hw = e.hw; p.epi.scale = e.scale;
+  p.epi.sched_x = e.sched_x; p.epi.sched_z = e.sched_z; p.epi.sched_k = e.sched_k; p.epi.aux_out = e.aux_out;
+}
+
+static int gemm_common(Ctx& c, GemmParams& p, int bn, int splits, const Epi& e, int ldo) {
+  set_epi(p, e, ldo);
+  if (splits > 1) {
+    const size_t need = size_t(splits) * p.M * p.N * sizeof(float);
+    if (need > c.splitk_cap) {
+      set_error("split-K workspace too small (%zu > %zu)", need, c.splitk_cap);
+      return MGB_ERR_STATE;
+    }
+  }
+  return run_gemm(p, bn, c.splitk_ws, c.stream);
+}
+
+// y = a[M,K] W^T (+ epilogue)
+static int linear(Ctx& c, const bf16* a, int M, const LinW& W, const Epi& e) {
+  int bn, sp, st;
+  const bool geglu = (e.flags & EPI_GEGLU) != 0;
+  choose_tile((M + 127) / 128, W.n, W.k / 64, geglu, true, &bn, &sp, &st);
+  if (geglu) bn = 256;
+  if (geglu) { sp = 1; st = 4; }
+  if (sp > 1) c.splitk_need = std::max(c.splitk_need, size_t(sp) * M * W.n * sizeof(float));
+  if (c.dry) return MGB_OK;
+  GemmParams p;
+  TRY(fill_linear_params(&p, a, W.w, M, W.n, W.k, bn, sp, st));
+  return gemm_common(c, p, bn, effective_splits(p), e, geglu ? W.n / 2 : W.n);
+}
+
+// generic A[M,K] x B[N,K]^T with raw pointers (attention score / PV GEMMs in the VAE)
+static int matmul_nt(Ctx& c, const bf16* a, const bf16* b, int M, int N, int K, const Epi& e) {
+  LinW W; W.w = const_cast<bf16*>(b); W.n = N; W.k = K;
+  return linear(c, a, M, W, e);
+}
+
+// 3x3 conv on NHWC bf16; Hout x Wout output; kind per ops.cu
+static int conv3x3(Ctx& c, const bf16* x, int NB, int Hout, int Wout, const ConvW& W, int kind, const Epi& e) {
+  int tw, th;
+  conv_tile_shape(Hout, Wout, &tw, &th);
+  const int m_tiles = NB * ((Wout + tw - 1) / tw) * ((Hout + th - 1) / th);
+  int bn, sp, st;
+  const bool special = (e.flags & (EPI_SCHED | EPI_DEPTH | EPI_NORMALS | EPI_NCHW)) != 0;
+  choose_tile(m_tiles, W.cout, 9 * W.cin_pad / 64, false, !special, &bn, &sp, &st);
+  if (special) bn = 16;
+  const size_t M = size_t(NB) * Hout * Wout;
+  if (sp > 1) c.splitk_need = std::max(c.splitk_need, size_t(sp) * M * W.cout * sizeof(float));
+  if (c.dry) return MGB_OK;
+  GemmParams p;
+  TRY(fill_conv_params(&p, x, W.w, NB, Hout, Wout, W.cin_pad, W.cout, kind, bn, sp, st));
+  Epi e2 = e;
+  e2.hw = Hout * Wout;
+  return gemm_common(c, p, bn, effective_splits(p), e2, W.cout);
+}
+
+#define LAUNCH(call, n)            \
+  do {                             \
+    if (!c.dry) {                  \
+      TRY(call);                   \
+      count_launch(n);             \
+    }                              \
+  } while (0)
+
+static int groupnorm(Ctx& c, const float* x, bf16* y, bf16* raw, const NormW& n, int NB, int HW, float eps, int silu,
+                     float* gn_ws) {
+  LAUNCH(launch_groupnorm(x, y, raw, n.g, n.b, gn_ws, NB, HW, n.c, c.groups, eps, silu, c.stream), 2);
+  return MGB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// ResnetBlock2D: GN -> SiLU -> conv3x3 (+temb) -> GN -> SiLU -> conv3x3 ; + (1x1 shortcut | x)
+//   x fp32 [M, cin] -> y fp32 [M, cout] (y preallocated by the caller)
+// ---------------------------------------------------------------------------------------------
+static int resnet_forward(Ctx& c, const ResnetW& R, const float* x, float* y, int NB, int H, int W, int step,
+                          float* gn_ws) {
+  const size_t M = size_t(NB) * H * W;
+  const size_t mk = c.arena->mark();
+  bf16* t1 = aalloc<bf16>(c, M * R.cin);
+  bf16* raw = R.has_sc ? aalloc<bf16>(c, M * R.cin) : nullptr;
+  float* h = aalloc<float>(c, M * R.cout);
+  bf16* t2 = aalloc<bf16>(c, M * R.cout);
+  float* sc = R.has_sc ? aalloc<float>(c, M * R.cout) : nullptr;
+  TRY(groupnorm(c, x, t1, raw, R.n1, NB, H * W, R.eps, 1, gn_ws));
+  Epi e1;
+  e1.bias = R.step_bias ? R.step_bias + size_t(step) * R.cout : R.c1.b;
+  e1.out_f32 = h;
+  TRY(conv3x3(c, t1, NB, H, W, R.c1, 0, e1));
+  TRY(groupnorm(c, h, t2, nullptr, R.n2, NB, H * W, R.eps, 1, gn_ws));
+  const float* residual = x;
+  if (R.has_sc) {
+    Epi es; es.bias = R.sc.b; es.out_f32 = sc;
+    TRY(linear(c, raw, int(M), R.sc, es));
+    residual = sc;
+  }
+  Epi e2; e2.bias = R.c2.b; e2.residual = residual; e2.out_f32 = y;
+  TRY(conv3x3(c, t2, NB, H, W, R.c2, 0, e2));
+  c.arena->release(mk);
+  return MGB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Transformer2DModel (1 BasicTransformerBlock, linear projections). x fp32 [M, C] -> y fp32 [M, C]
+// ---------------------------------------------------------------------------------------------
+static int xfmr_forward(Ctx& c, const XfmrW& X, const float* x, float* y, int NB, int T, float* gn_ws) {
+  const int C = X.C;
+  const size_t M = size_t(NB) * T;
+  const size_t mk = c.arena->mark();
+  bf16* a = aalloc<bf16>(c, M * C);          // normalised operand (reused)
+  float* hs0 = aalloc<float>(c, M * C);
+  float* hs1 = aalloc<float>(c, M * C);
+  bf16* qkv = aalloc<bf16>(c, M * 3 * C);
+  bf16* o = aalloc<bf16>(c, M * C);
+  bf16* ffm = aalloc<bf16>(c, M * 4 * C);
+  bf16* hsb = aalloc<bf16>(c, M * C);
+
+  TRY(groupnorm(c, x, a, nullptr, X.gn, NB, T, 1e-6f, 0, gn_ws));
+  { Epi e; e.bias = X.proj_in.b; e.out_f32 = hs0; TRY(linear(c, a, int(M), X.proj_in, e)); }
+  // self attention
+  LAUNCH(launch_layernorm(hs0, a, X.ln1.g, X.ln1.b, int(M), C, 1e-5f, c.stream), 1);
+  { Epi e; e.out_bf16 = qkv; TRY(linear(c, a, int(M), X.qkv, e)); }
+  LAUNCH(launch_flash_attn64(qkv, o, NB, T, C, 0.125f, c.stream), 1);
+  { Epi e; e.bias = X.o1.b; e.residual = hs0; e.out_f32 = hs1; TRY(linear(c, o, int(M), X.o1, e)); }
+  // cross attention against the folded empty-prompt K/V
+  LAUNCH(launch_layernorm(hs1, a, X.ln2.g, X.ln2.b, int(M), C, 1e-5f, c.stream), 1);
+  { Epi e; e.out_bf16 = qkv; TRY(linear(c, a, int(M), X.q2, e)); }  // q in the first M*C elements of qkv
+  LAUNCH(launch_cross_attn2(qkv, X.kv, o, int(M), C, 0.125f, c.stream), 1);
+  { Epi e; e.bias = X.o2.b; e.residual = hs1; e.out_f32 = hs0; TRY(linear(c, o, int(M), X.o2, e)); }
+  // GEGLU feed-forward
+  LAUNCH(launch_layernorm(hs0, a, X.ln3.g, X.ln3.b, int(M), C, 1e-5f, c.stream), 1);
+  { Epi e; e.bias = X.ff1.b; e.out_bf16 = ffm; e.flags = EPI_GEGLU; TRY(linear(c, a, int(M), X.ff1, e)); }
+  { Epi e; e.bias = X.ff2.b; e.residual = hs0; e.out_bf16 = hsb; TRY(linear(c, ffm, int(M), X.ff2, e)); }
+  { Epi e; e.bias = X.proj_out.b; e.residual = x; e.out_f32 = y; TRY(linear(c, hsb, int(M), X.proj_out, e)); }
+  c.arena->release(mk);
+  return MGB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// VAE mid-block attention: single head, dim C (512), over T = h*w tokens. x, y fp32 [NB*T, C].
+// Scores are materialised per image in bf16 (T x T), softmaxed in place, then P V via V^T.
+// ---------------------------------------------------------------------------------------------
+static int vae_attn_forward(Ctx& c, const VaeAttnW& A, const float* x, float* y, int NB, int T, float* gn_ws) {
+  const int C = A.C;
+  const size_t M = size_t(NB) * T;
+  const size_t mk = c.arena->mark();
+  bf16* a = aalloc<bf16>(c, M * C);
+  bf16* q = aalloc<bf16>(c, M * C);
+  bf16* k = aalloc<bf16>(c, M * C);
+  bf16* v = aalloc<bf16>(c, M * C);
+  bf16* vt = aalloc<bf16>(c, size_t(T) * C);
+  bf16* s = aalloc<bf16>(c, size_t(T) * T);
+  bf16* o = aalloc<bf16>(c, M * C);
+  TRY(groupnorm(c, x, a, nullptr, A.gn, NB, T, 1e-6f, 0, gn_ws));
+  { Epi e; e.bias = A.q.b; e.out_bf16 = q; TRY(linear(c, a, int(M), A.q, e)); }
+  { Epi e; e.bias = A.k.b; e.out_bf16 = k; TRY(linear(c, a, int(M), A.k, e)); }
+  { Epi e; e.bias = A.v.b; e.out_bf16 = v; TRY(linear(c, a, int(M), A.v, e)); }
+  const float scale = 1.0f / sqrtf(float(C));
+  for (int n = 0; n < NB; ++n) {
+    const size_t off = size_t(n) * T * C;
+    { Epi e; e.out_bf16 = s; e.flags = EPI_SCALE; e.scale = scale; TRY(matmul_nt(c, q + off, k + off, T, T, C, e)); }
+    LAUNCH(launch_softmax_rows(s, T, T, T, c.stream), 1);
+    LAUNCH(launch_transpose_bf16(v + off, vt, T, C, c.stream), 1);
+    { Epi e; e.out_bf16 = o + off; TRY(matmul_nt(c, s, vt, T, C, T, e)); }
+  }
+  { Epi e; e.bias = A.o.b; e.residual = x; e.out_f32 = y; TRY(linear(c, o, int(M), A.o, e)); }
+  c.arena->release(mk);
+  return MGB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// UNet step. rgb / tgt: fp32 NHWC [NB, lh, lw, 4]. tgt is updated in place by the fused
+// conv_out + scheduler epilogue. raw_out (or null): fp32 NHWC [NB, lh, lw, 4] model output.
+// ---------------------------------------------------------------------------------------------
+int unet_forward(mgb_handle* hd, Ctx& c, const float* rgb, float* tgt, const float* noise, float* raw_out, int step,
+                 int NB, int lh, int lw) {
+  const UNetW& U = hd->unet;
+  const mgb_config& cfg = hd->cfg;
+  const int L = cfg.unet_layers_per_block;
+  const int* ch = cfg.unet_block_channels;
+  float* gn_ws = hd->gn_ws;
+  int H = lh, W = lw;
+  size_t M = size_t(NB) * H * W;
+
+  struct Skip { float* p; int c; };
+  std::vector<Skip> skips;
+  size_t ri = 0, xi = 0;
+
+  bf16* x0 = aalloc<bf16>(c, M * 64);
+  LAUNCH(launch_pack_latents(rgb, tgt, x0, int(M), c.stream), 1);
+  float* h = aalloc<float>(c, M * ch[0]);
+  { Epi e; e.bias = U.conv_in.b; e.out_f32 = h; TRY(conv3x3(c, x0, NB, H, W, U.conv_in, 0, e)); }
+  skips.push_back({h, ch[0]});
+  int cur = ch[0];
+  // down path
+  for (int i = 0; i < 4; ++i) {
+    const bool last = i == 3;
+    for (int j = 0; j < L; ++j) {
+      float* y = aalloc<float>(c, M * ch[i]);
+      TRY(resnet_forward(c, U.resnets[ri++], h, y, NB, H, W, step, gn_ws));
+      h = y; cur = ch[i];
+      if (!last) {
+        float* y2 = aalloc<float>(c, M * cur);
+        TRY(xfmr_forward(c, U.xfmrs[xi++], h, y2, NB, H * W, gn_ws));
+        h = y2;
+      }
+      skips.push_back({h, cur});
+    }
+    if (!last) {
+      const size_t mk = c.arena->mark();
+      (void)mk;
+      bf16* planes = aalloc<bf16>(c, M * cur);
+      LAUNCH(launch_space_to_depth(h, planes, NB, H, W, cur, c.stream), 1);
+      H /= 2; W /= 2; M = size_t(NB) * H * W;
+      float* y = aalloc<float>(c, M * cur);
+      { Epi e; e.bias = U.downs[i].b; e.out_f32 = y; TRY(conv3x3(c, planes, NB, H, W, U.downs[i], 2, e)); }
+      h = y;
+      skips.push_back({h, cur});
+    }
+  }
+  // mid
+  {
+    float* y = aalloc<float>(c, M * cur);
+    TRY(resnet_forward(c, U.resnets[ri++], h, y, NB, H, W, step, gn_ws));
+    float* y2 = aalloc<float>(c, M * cur);
+    TRY(xfmr_forward(c, U.xfmrs[xi++], y, y2, NB, H * W, gn_ws));
+    float* y3 = aalloc<float>(c, M * cur);
+    TRY(resnet_forward(c, U.resnets[ri++], y2, y3, NB, H, W, step, gn_ws));
+    h = y3;
+  }
+  // up path
+  for (int i = 0; i < 4; ++i) {
+    const int cout = ch[3 - i];
+    for (int j = 0; j < L + 1; ++j) {
+      Skip s = skips.back();
+      skips.pop_back();
+      float* cat = aalloc<float>(c, M * (cur + s.c));
+      LAUNCH(launch_concat(h, s.p, cat, int(M), cur, s.c, c.stream), 1);
+      float* y = aalloc<float>(c, M * cout);
+      TRY(resnet_forward(c, U.resnets[ri++], cat, y, NB, H, W, step, gn_ws));
+      h = y; cur = cout;
+      if (i > 0) {
+        float* y2 = aalloc<float>(c, M * cur);
+        TRY(xfmr_forward(c, U.xfmrs[xi++], h, y2, NB, H * W, gn_ws));
+        h = y2;
+      }
+    }
+    if (i < 3) {
+      bf16* up = aalloc<bf16>(c, M * 4 * cur);
+      LAUNCH(launch_upsample2x(h, up, NB, H, W, cur, c.stream), 1);
+      H *= 2; W *= 2; M = size_t(NB) * H * W;
+      float* y = aalloc<float>(c, M * cur);
+      { Epi e; e.bias = U.ups[i].b; e.out_f32 = y; TRY(conv3x3(c, up, NB, H, W, U.ups[i], 0, e)); }
+      h = y;
+    }
+  }
+  // out: GN -> SiLU -> conv_out fused with the scheduler step
+  bf16* t = aalloc<bf16>(c, M * cur);
+  TRY(groupnorm(c, h, t, nullptr, U.norm_out, NB, H * W, 1e-5f, 1, gn_ws));
+  {
+    Epi e;
+    e.bias = U.conv_out.b;
+    e.flags = EPI_SCHED;
+    e.out_f32 = tgt; e.sched_x = tgt; e.sched_z = noise; e.aux_out = raw_out;
+    e.sched_k = hd->sched_k + size_t(step) * 3;
+    TRY(conv3x3(c, t, NB, H, W, U.conv_out, 0, e));
+  }
+  return MGB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// VAE encoder: rgb fp32 NCHW [NB,3,H,W] -> latent fp32 NCHW [NB,4,H/8,W/8] (mean * latent_scale)
+// ---------------------------------------------------------------------------------------------
+int vae_encode_forward(mgb_handle* hd, Ctx& c, const float* rgb, float* latent_out, int NB, int H, int W) {
+  const VaeW& V = hd->vae;
+  const mgb_config& cfg = hd->cfg;
+  const int* ch = cfg.vae_block_channels;
+  const int L = cfg.vae_layers_per_block;
+  float* gn_ws = hd->gn_ws;
+  size_t M = size_t(NB) * H * W;
+  size_t ri = 0;
+  const size_t mk0 = c.arena->mark();
+  bf16* x0 = aalloc<bf16>(c, M * 64);
+  LAUNCH(launch_pack_rgb(rgb, x0, NB, H * W, c.stream), 1);
+  float* h = aalloc<float>(c, M * ch[0]);
+  { Epi e; e.bias = V.enc_in.b; e.out_f32 = h; TRY(conv3x3(c, x0, NB, H, W, V.enc_in, 0, e)); }
+  int cur = ch[0];
+  for (int i = 0; i < 4; ++i) {
+    // ping-pong trunk buffers for this resolution
+    float* bufA = aalloc<float>(c, M * ch[i]);
+    float* bufB = aalloc<float>(c, M * ch[i]);
+    for (int j = 0; j < L; ++j) {
+      float* y = (j & 1) ? bufB : bufA;
+      TRY(resnet_forward(c, V.enc_res[ri++], h, y, NB, H, W, 0, gn_ws));
+      h = y; cur = ch[i];
+    }
+    if (i < 3) {
+      bf16* planes = aalloc<bf16>(c, M * cur);
+      LAUNCH(launch_space_to_depth(h, planes, NB, H, W, cur, c.stream), 1);
+      H /= 2; W /= 2; M = size_t(NB) * H * W;
+      float* y = aalloc<float>(c, M * cur);
+      { Epi e; e.bias = V.enc_down[i].b; e.out_f32 = y; TRY(conv3x3(c, planes, NB, H, W, V.enc_down[i], 3, e)); }
+      h = y;
+    }
+  }
+  {
+    float* y1 = aalloc<float>(c, M * cur);
+    TRY(resnet_forward(c, V.enc_res[ri++], h, y1, NB, H, W, 0, gn_ws));
+    float* y2 = aalloc<float>(c, M * cur);
+    TRY(vae_attn_forward(c, V.enc_attn, y1, y2, NB, H * W, gn_ws));
+    float* y3 = aalloc<float>(c, M * cur);
+    TRY(resnet_forward(c, V.enc_res[ri++], y2, y3, NB, H, W, 0, gn_ws));
+    h = y3;
+  }
+  bf16* t = aalloc<bf16>(c, M * cur);
+  TRY(groupnorm(c, h, t, nullptr, V.enc_norm_out, NB, H * W, 1e-6f, 1, gn_ws));
+  {
+    // conv_out with quant_conv folded in; mean half only; * latent_scale; NCHW output
+    Epi e; e.bias = V.enc_out.b; e.out_f32 = latent_out; e.flags = EPI_NCHW | EPI_SCALE; e.scale = cfg.latent_scale;
+    TRY(conv3x3(c, t, NB, H, W, V.enc_out, 0, e));
+  }
+  c.arena->release(mk0);
+  return MGB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// VAE decoder: latent fp32 NCHW [NB,4,lh,lw] -> out fp32 NCHW (depth: 1 plane, normals/raw: 3 planes)
+// ---------------------------------------------------------------------------------------------
+int vae_decode_forward(mgb_handle* hd, Ctx& c, const float* latent, float* out, int NB, int lh, int lw, int mode) {
+  const VaeW& V = hd->vae;
+  const mgb_config& cfg = hd->cfg;
+  const int* ch = cfg.vae_block_channels;
+  const int L = cfg.vae_layers_per_block;
+  float* gn_ws = hd->gn_ws;
+  int H = lh, W = lw;
+  size_t M = size_t(NB) * H * W;
+  size_t ri = 0;
+  const size_t mk0 = c.arena->mark();
+  bf16* z = aalloc<bf16>(c, M * 64);
+  LAUNCH(launch_pack_decoder_latent(latent, V.pq_w, V.pq_b, 1.0f / cfg.latent_scale, z, NB, H * W, c.stream), 1);
+  int cur = ch[3];
+  float* h = aalloc<float>(c, M * cur);
+  { Epi e; e.bias = V.dec_in.b; e.out_f32 = h; TRY(conv3x3(c, z, NB, H, W, V.dec_in, 0, e)); }
+  {
+    float* y1 = aalloc<float>(c, M * cur);
+    TRY(resnet_forward(c, V.dec_res[ri++], h, y1, NB, H, W, 0, gn_ws));
+    float* y2 = aalloc<float>(c, M * cur);
+    TRY(vae_attn_forward(c, V.dec_attn, y1, y2, NB, H * W, gn_ws));
+    float* y3 = aalloc<float>(c, M * cur);
+    TRY(resnet_forward(c, V.dec_res[ri++], y2, y3, NB, H, W, 0, gn_ws));
+    h = y3;
+  }
+  for (int i = 0; i < 4; ++i) {
+    const int cout = ch[3 - i];
+    float* bufA = aalloc<float>(c, M * cout);
+    float* bufB = aalloc<float>(c, M * cout);
+    for (int j = 0; j < L + 1; ++j) {
+      float* y = (j & 1) ? bufB : bufA;
+      TRY(resnet_forward(c, V.dec_res[ri++], h, y, NB, H, W, 0, gn_ws));
+      h = y; cur = cout;
+    }
+    if (i < 3) {
+      bf16* up = aalloc<bf16>(c, M * 4 * cur);
+      LAUNCH(launch_upsample2x(h, up, NB, H, W, cur, c.stream), 1);
+      H *= 2; W *= 2; M = size_t(NB) * H * W;
+      float* y = aalloc<float>(c, M * cur);
+      { Epi e; e.bias = V.dec_up[i].b; e.out_f32 = y; TRY(conv3x3(c, up, NB, H, W, V.dec_up[i], 0, e)); }
+      h = y;
+    }
+  }
+  bf16* t = aalloc<bf16>(c, M * cur);
+  TRY(groupnorm(c, h, t, nullptr, V.dec_norm_out, NB, H * W, 1e-6f, 1, gn_ws));
+  {
+    Epi e; e.bias = V.dec_out.b; e.out_f32 = out;
+    e.flags = mode == MGB_DECODE_DEPTH ? EPI_DEPTH : mode == MGB_DECODE_NORMALS ? EPI_NORMALS : EPI_NCHW;
+    TRY(conv3x3(c, t, NB, H, W, V.dec_out, 0, e));
+  }
+  c.arena->release(mk0);
+  return MGB_OK;
+}
+
+}  // namespace mgb

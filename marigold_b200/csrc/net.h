@@ -1,0 +1,131 @@
+// Network composition for the Marigold hot path: weights, activation arena, and the forward graphs of
+// the SD-2 UNet step and the SD VAE encoder / decoder, expressed as sequences of the kernels in
+// kernels.h. Host-side C++ only; no torch.
+#pragma once
+#include <map>
+#include <string>
+#include <vector>
+
+#include "kernels.h"
+#include "ops.h"
+
+namespace mgb {
+
+struct HostTensor {
+  std::vector<float> data;
+  std::vector<int64_t> shape;
+  size_t numel() const { return data.size(); }
+};
+
+// ---- device-side weights ------------------------------------------------------------------------
+struct ConvW {   // 3x3 conv, tap-major bf16 [cout, 9 * cin_pad]
+  bf16* w = nullptr;
+  float* b = nullptr;
+  int cin = 0, cin_pad = 0, cout = 0;
+};
+struct LinW {    // bf16 [n, k]
+  bf16* w = nullptr;
+  float* b = nullptr;
+  int n = 0, k = 0;
+  bool geglu = false;
+};
+struct NormW {
+  float* g = nullptr;
+  float* b = nullptr;
+  int c = 0;
+};
+struct ResnetW {
+  NormW n1, n2;
+  ConvW c1, c2;
+  LinW sc;              // 1x1 shortcut as a linear layer (cin != cout)
+  bool has_sc = false;
+  int cin = 0, cout = 0;
+  // time embedding projection (UNet only): fp32 [cout, temb_dim]; bias already includes conv1.bias
+  float* temb_w = nullptr;
+  float* temb_b = nullptr;
+  float* step_bias = nullptr;  // device [n_steps, cout]: conv1 bias + time_emb_proj(silu(temb_i))
+  float eps = 1e-5f;
+};
+struct XfmrW {
+  int C = 0;
+  NormW gn, ln1, ln2, ln3;
+  LinW proj_in, qkv, o1, q2, o2, ff1, ff2, proj_out;
+  float* k2w = nullptr;  // fp32 [C, ctx]
+  float* v2w = nullptr;
+  float* kv = nullptr;   // fp32 [2 (k|v), n_ctx, C], folded at set_text_embedding
+};
+struct VaeAttnW {
+  int C = 0;
+  NormW gn;
+  LinW q, k, v, o;
+};
+
+struct Arena {
+  char* base = nullptr;
+  size_t cap = 0, off = 0, peak = 0;
+  bool dry = false;
+  bool overflow = false;
+  void* alloc(size_t bytes);
+  size_t mark() const { return off; }
+  void release(size_t m) { off = m; }
+};
+
+struct Ctx {
+  cudaStream_t stream = nullptr;
+  Arena* arena = nullptr;
+  bool dry = false;
+  float* splitk_ws = nullptr;
+  size_t splitk_cap = 0;   // bytes available
+  size_t splitk_need = 0;  // bytes needed (dry run)
+  int groups = 32;
+};
+
+struct UNetW {
+  ConvW conv_in, conv_out;
+  NormW norm_out;
+  float *te_w1 = nullptr, *te_b1 = nullptr, *te_w2 = nullptr, *te_b2 = nullptr;
+  int temb_dim = 0;
+  std::vector<ResnetW> resnets;   // execution order
+  std::vector<XfmrW> xfmrs;       // execution order
+  std::vector<ConvW> downs, ups;
+};
+struct VaeW {
+  // encoder
+  ConvW enc_in, enc_out;          // enc_out has quant_conv folded in, mean half only
+  NormW enc_norm_out;
+  std::vector<ResnetW> enc_res;   // execution order (down blocks then mid 0, mid 1)
+  std::vector<ConvW> enc_down;
+  VaeAttnW enc_attn;
+  // decoder
+  float* pq_w = nullptr;          // post_quant_conv fp32 [4,4]
+  float* pq_b = nullptr;
+  ConvW dec_in, dec_out;
+  NormW dec_norm_out;
+  std::vector<ResnetW> dec_res;   // mid 0, mid 1, then up blocks
+  std::vector<ConvW> dec_up;
+  VaeAttnW dec_attn;
+};
+
+}  // namespace mgb
+
+struct mgb_handle {
+  mgb_config cfg;
+  std::map<std::string, mgb::HostTensor> host;  // until finalize
+  bool finalized = false;
+  std::vector<void*> dev_allocs;
+  mgb::UNetW unet;
+  mgb::VaeW vae;
+  mgb::Arena arena;
+  float* splitk_ws = nullptr;
+  size_t splitk_cap = 0;
+  // conditioning / schedule
+  int n_ctx = 0;
+  bool text_set = false;
+  int n_steps = 0;
+  std::vector<int> timesteps;
+  float* sched_k = nullptr;   // device [n_steps, 3]
+  std::vector<float> kz_host;
+  // small persistent buffers
+  float* gn_ws = nullptr;
+  size_t gn_ws_bytes = 0;
+};
