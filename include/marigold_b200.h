@@ -101,6 +101,10 @@ int mgb_unet_step(mgb_handle* h, const float* rgb_latent_dev, float* target_dev,
  * step_noise_dev: [n-1, B, 4, h, w] or NULL (required when any kz != 0). */
 int mgb_denoise(mgb_handle* h, const float* rgb_latent_dev, float* target_dev, const float* step_noise_dev,
                 int32_t B, int32_t lh, int32_t lw, void* stream);
+/* Steps [first_step, first_step + num_steps) of the current schedule only (bench.py times K steps of a
+ * longer schedule with it). step_noise_dev is indexed by absolute step: [n-1, B, 4, h, w]. */
+int mgb_denoise_range(mgb_handle* h, const float* rgb_latent_dev, float* target_dev, const float* step_noise_dev,
+                      int32_t first_step, int32_t num_steps, int32_t B, int32_t lh, int32_t lw, void* stream);
 /* decode_depth / decode_normals + the clip / shift / normalise that follow
  * (…depth_pipeline.py:498-516,473-475; …normals_pipeline.py:463-479,438-440).
  * out_dev: DEPTH [B,1,H,W] in [0,1]; NORMALS [B,3,H,W] unit vectors; RAW3 [B,3,H,W]. */

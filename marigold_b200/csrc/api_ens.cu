@@ -1,0 +1,110 @@
+// C ABI, ensembling part (reference marigold/util/ensemble.py).
+#include <algorithm>
+#include <cfloat>
+#include <vector>
+
+#include "net.h"
+
+using namespace mgb;
+
+#define CUDA_TRY(expr)                                                                   \
+  do {                                                                                   \
+    cudaError_t _e = (expr);                                                             \
+    if (_e != cudaSuccess) {                                                             \
+      set_error("%s:%d %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e));    \
+      return MGB_ERR_CUDA;                                                               \
+    }                                                                                    \
+  } while (0)
+
+static int ens_prepare(mgb_handle* h) {
+  if (!h) { set_error("null handle"); return MGB_ERR_INVALID; }
+  if (!h->ens_ws) {
+    CUDA_TRY(cudaMalloc(&h->ens_ws, std::max(ens_ws_bytes(), size_t(64 * 16 * 2 * 4))));
+    CUDA_TRY(cudaMallocHost(reinterpret_cast<void**>(&h->ens_pinned), 4096 * sizeof(double)));
+  }
+  return MGB_OK;
+}
+
+static int make_st(const double* param, int E, int scale_inv, int shift_inv, float* st) {
+  if (!scale_inv) {
+    // reference: "Pure shift-invariant ensembling is not supported" (ensemble.py:88-89) / "Unrecognized alignment"
+    set_error("ensemble_depth: alignment requires scale_invariant");
+    return MGB_ERR_INVALID;
+  }
+  for (int e = 0; e < E; ++e) {
+    st[e] = float(param[e]);                       // torch.from_numpy(s).to(depth): float64 -> float32
+    st[E + e] = shift_inv ? float(param[E + e]) : 0.f;
+  }
+  return MGB_OK;
+}
+
+extern "C" {
+
+int mgb_ens_depth_cost(mgb_handle* h, const float* depth, const double* param, int32_t E, int64_t HW,
+                       int32_t scale_inv, int32_t shift_inv, int32_t median, double reg, double* cost_out,
+                       void* stream) {
+  int rc = ens_prepare(h);
+  if (rc) return rc;
+  if (!depth || !param || !cost_out || HW <= 0) { set_error("ens_depth_cost: bad argument"); return MGB_ERR_INVALID; }
+  float st[64];
+  if (E > 16 || E < 2) { set_error("ensemble size %d outside [2,16]", E); return MGB_ERR_UNSUPPORTED; }
+  rc = make_st(param, E, scale_inv, shift_inv, st);
+  if (rc) return rc;
+  // st must outlive the async H2D copy: stage it in pinned memory
+  float* st_pinned = reinterpret_cast<float*>(h->ens_pinned + 8);
+  std::copy(st, st + 2 * E, st_pinned);
+  rc = launch_ens_depth_cost(depth, st_pinned, E, HW, shift_inv, median, reg, h->ens_ws, h->ens_pinned,
+                             reinterpret_cast<cudaStream_t>(stream));
+  if (rc) return rc;
+  count_launch(2);
+  *cost_out = h->ens_pinned[0];
+  return MGB_OK;
+}
+
+int mgb_ens_minmax(mgb_handle* h, const float* depth, int32_t E, int64_t HW, float* min_host, float* max_host,
+                   void* stream) {
+  int rc = ens_prepare(h);
+  if (rc) return rc;
+  if (!depth || !min_host || !max_host || E < 1 || E > 16 || HW <= 0) { set_error("ens_minmax: bad argument"); return MGB_ERR_INVALID; }
+  int blocks = 0;
+  float* hp = reinterpret_cast<float*>(h->ens_pinned);
+  rc = launch_ens_minmax(depth, E, HW, reinterpret_cast<float*>(h->ens_ws), hp, &blocks,
+                         reinterpret_cast<cudaStream_t>(stream));
+  if (rc) return rc;
+  count_launch(1);
+  for (int e = 0; e < E; ++e) {
+    float mn = FLT_MAX, mx = -FLT_MAX;
+    for (int b = 0; b < blocks; ++b) { mn = std::min(mn, hp[(e * blocks + b) * 2]); mx = std::max(mx, hp[(e * blocks + b) * 2 + 1]); }
+    min_host[e] = mn; max_host[e] = mx;
+  }
+  return MGB_OK;
+}
+
+int mgb_ens_depth_reduce(mgb_handle* h, const float* depth, const double* param, int32_t E, int64_t HW,
+                         int32_t scale_inv, int32_t shift_inv, int32_t median, float* pred, float* unc,
+                         int32_t* member_idx, void* stream) {
+  int rc = ens_prepare(h);
+  if (rc) return rc;
+  if (!depth || !param || !pred || HW <= 0) { set_error("ens_depth_reduce: bad argument"); return MGB_ERR_INVALID; }
+  if (E > 16 || E < 2) { set_error("ensemble size %d outside [2,16]", E); return MGB_ERR_UNSUPPORTED; }
+  float st[64];
+  rc = make_st(param, E, scale_inv, shift_inv, st);
+  if (rc) return rc;
+  float* st_pinned = reinterpret_cast<float*>(h->ens_pinned + 8);
+  CUDA_TRY(cudaStreamSynchronize(reinterpret_cast<cudaStream_t>(stream)));  // previous user of the staging area
+  std::copy(st, st + 2 * E, st_pinned);
+  rc = launch_ens_depth_reduce(depth, st_pinned, E, HW, shift_inv, median, shift_inv ? 1 : 0, pred, unc, member_idx,
+                               h->ens_ws, reinterpret_cast<cudaStream_t>(stream));
+  if (!rc) count_launch(2);
+  return rc;
+}
+
+int mgb_ens_normals(mgb_handle* h, const float* normals, int32_t E, int64_t HW, int32_t closest, float* out,
+                    float* unc, int32_t* member_idx, void* stream) {
+  if (!h || !normals || !out || HW <= 0) { set_error("ens_normals: bad argument"); return MGB_ERR_INVALID; }
+  int rc = launch_ens_normals(normals, E, HW, closest, out, unc, member_idx, reinterpret_cast<cudaStream_t>(stream));
+  if (!rc) count_launch(1);
+  return rc;
+}
+
+}  // extern "C"

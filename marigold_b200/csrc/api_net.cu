@@ -255,6 +255,8 @@ void mgb_destroy(mgb_handle* h) {
   if (h->splitk_ws) cudaFree(h->splitk_ws);
   if (h->sched_k) cudaFree(h->sched_k);
   if (h->gn_ws) cudaFree(h->gn_ws);
+  if (h->ens_ws) cudaFree(h->ens_ws);
+  if (h->ens_pinned) cudaFreeHost(h->ens_pinned);
   delete h;
 }
 
@@ -593,14 +595,18 @@ int mgb_unet_step(mgb_handle* h, const float* rgb_latent, float* target, const f
   return MGB_OK;
 }
 
-int mgb_denoise(mgb_handle* h, const float* rgb_latent, float* target, const float* step_noise, int32_t B, int32_t lh,
-                int32_t lw, void* stream) {
+int mgb_denoise_range(mgb_handle* h, const float* rgb_latent, float* target, const float* step_noise,
+                      int32_t first_step, int32_t num_steps, int32_t B, int32_t lh, int32_t lw, void* stream) {
   TRY(check_ready(h, true));
   if (!rgb_latent || !target || B <= 0 || lh <= 0 || lw <= 0 || lh % 8 || lw % 8) {
     set_error("mgb_denoise: latent H, W must be positive multiples of 8 (got %d x %d)", lh, lw);
     return MGB_ERR_INVALID;
   }
-  for (int i = 0; i < h->n_steps; ++i)
+  if (first_step < 0 || num_steps < 0 || first_step + num_steps > h->n_steps) {
+    set_error("mgb_denoise_range: steps [%d, %d) outside schedule of %d", first_step, first_step + num_steps, h->n_steps);
+    return MGB_ERR_INVALID;
+  }
+  for (int i = first_step; i < first_step + num_steps; ++i)
     if (h->kz_host[i] != 0.f && !step_noise) { set_error("schedule step %d injects noise but step_noise is NULL", i); return MGB_ERR_INVALID; }
   TRY(ensure_workspace(h, OP_UNET, B, lh, lw));
   Ctx c = make_ctx(h, stream);
@@ -615,7 +621,7 @@ int mgb_denoise(mgb_handle* h, const float* rgb_latent, float* target, const flo
   TRY(launch_nchw_to_nhwc(rgb_latent, rgb, B, 4, HW, 1.f, c.stream));
   TRY(launch_nchw_to_nhwc(target, tgt, B, 4, HW, 1.f, c.stream));
   count_launch(2);
-  for (int i = 0; i < h->n_steps; ++i) {
+  for (int i = first_step; i < first_step + num_steps; ++i) {
     const float* z = nullptr;
     if (h->kz_host[i] != 0.f) {
       TRY(launch_nchw_to_nhwc(step_noise + size_t(i) * n, nz, B, 4, HW, 1.f, c.stream));
@@ -629,6 +635,12 @@ int mgb_denoise(mgb_handle* h, const float* rgb_latent, float* target, const flo
   count_launch(1);
   if (h->arena.overflow) { set_error("arena overflow"); return MGB_ERR_NOMEM; }
   return MGB_OK;
+}
+
+int mgb_denoise(mgb_handle* h, const float* rgb_latent, float* target, const float* step_noise, int32_t B, int32_t lh,
+                int32_t lw, void* stream) {
+  if (!h) { set_error("null handle"); return MGB_ERR_INVALID; }
+  return mgb_denoise_range(h, rgb_latent, target, step_noise, 0, h->n_steps, B, lh, lw, stream);
 }
 
 int mgb_decode(mgb_handle* h, const float* latent, int32_t B, int32_t lh, int32_t lw, int32_t mode, float* out,

@@ -128,7 +128,15 @@ int launch_transpose_bf16(const bf16* x, bf16* y, int M, int N, cudaStream_t str
 // ---------------------------------------------------------------------------------------------
 // Ensemble kernels (ensemble.cu)
 // ---------------------------------------------------------------------------------------------
-int launch_ens_depth_cost(const float* depth, const float* s, const float* t, int E, int HW, float* ws,
-                          double* out_host_pinned, cudaStream_t stream);
+size_t ens_ws_bytes();
+// st_host: float [2E] = {s_0..s_{E-1}, t_0..t_{E-1}}; out_host_pinned: double[3] = {cost, min(pred), max(pred)}
+int launch_ens_depth_cost(const float* depth, const float* st_host, int E, long long HW, int shift, int median,
+                          double reg, void* ws, double* out_host_pinned, cudaStream_t stream);
+int launch_ens_minmax(const float* depth, int E, long long HW, float* ws, float* host_pinned, int* blocks_out,
+                      cudaStream_t stream);
+int launch_ens_depth_reduce(const float* depth, const float* st_host, int E, long long HW, int shift, int median,
+                            int use_min, float* pred, float* unc, int* idx, void* ws, cudaStream_t stream);
+int launch_ens_normals(const float* nrm, int E, long long HW, int closest, float* out, float* unc, int* idx,
+                       cudaStream_t stream);
 
 }  // namespace mgb

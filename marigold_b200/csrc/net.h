@@ -128,4 +128,7 @@ struct mgb_handle {
   // small persistent buffers
   float* gn_ws = nullptr;
   size_t gn_ws_bytes = 0;
+  // ensemble scratch
+  void* ens_ws = nullptr;
+  double* ens_pinned = nullptr;  // pinned host, 64 doubles
 };

@@ -143,6 +143,15 @@ class Engine:
                   "mgb_denoise")
         return target
 
+    def denoise_range_(self, rgb_latent, target, first_step: int, num_steps: int, step_noise=None) -> None:
+        """In place on `target` (fp32 CUDA, contiguous): steps [first_step, first_step + num_steps)."""
+        assert target.is_cuda and target.dtype == torch.float32 and target.is_contiguous()
+        assert rgb_latent.is_cuda and rgb_latent.dtype == torch.float32 and rgb_latent.is_contiguous()
+        B, _, lh, lw = target.shape
+        with torch.cuda.device(self.device):
+            check(self.lib.mgb_denoise_range(self._h, ptr(rgb_latent), ptr(target), ptr(step_noise), first_step,
+                                             num_steps, B, lh, lw, stream_ptr()), "mgb_denoise_range")
+
     def decode(self, latent, mode: int) -> torch.Tensor:
         latent = self._f32(latent)
         B, _, lh, lw = latent.shape

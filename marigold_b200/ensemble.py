@@ -1,0 +1,153 @@
+"""Drop-in `ensemble_depth` / `ensemble_normals` (reference marigold/util/ensemble.py:39-196, 199-249)
+backed by the CUDA kernels in csrc/ensemble.cu.
+
+Same signatures, defaults, error behaviour and return shapes as the reference. The scipy BFGS driver
+stays on the host exactly as in the reference (ensemble.py:165-171); what changes is the objective:
+one fused pass + one host sync per evaluation instead of C(E,2)+2 `.item()` syncs.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from functools import partial
+from typing import Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import check, ptr, stream_ptr
+
+_util_engine = None
+
+
+def _handle(engine=None):
+    """Any handle works for the ensemble entry points (they only use its scratch buffers)."""
+    global _util_engine
+    if engine is not None:
+        return engine
+    if _util_engine is None:
+        from .engine import Engine, EngineConfig
+
+        _util_engine = Engine(EngineConfig.tiny())
+    return _util_engine
+
+
+def _resize_max_res_nearest_exact(img: torch.Tensor, max_edge: int) -> torch.Tensor:
+    # reference resize_max_res (image_util.py:90-120) with NEAREST_EXACT (ensemble.py:158-161)
+    h, w = img.shape[-2:]
+    f = min(max_edge / w, max_edge / h)
+    return torch.nn.functional.interpolate(img, size=(int(h * f), int(w * f)), mode="nearest-exact")
+
+
+def ensemble_depth(
+    depth: torch.Tensor,
+    scale_invariant: bool = True,
+    shift_invariant: bool = True,
+    output_uncertainty: bool = False,
+    reduction: str = "median",
+    regularizer_strength: float = 0.02,
+    max_iter: int = 50,
+    tol: float = 1e-6,
+    max_res: int = 1024,
+    engine=None,
+    return_aux: bool = False,
+    param: Optional[np.ndarray] = None,
+) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+    if depth.dim() != 4 or depth.shape[1] != 1:
+        raise ValueError(f"Expecting 4D tensor of shape [B,1,H,W]; got {depth.shape}.")
+    if reduction not in ("mean", "median"):
+        raise ValueError(f"Unrecognized reduction method: {reduction}.")
+    if not scale_invariant and shift_invariant:
+        raise ValueError("Pure shift-invariant ensembling is not supported.")
+    if not scale_invariant:
+        raise ValueError("Unrecognized alignment.")  # reference raises this at ensemble.py:190
+    if not depth.is_cuda:
+        raise _lib.MgbError("marigold_b200.ensemble_depth needs a CUDA tensor (no CPU fallback)")
+    eng = _handle(engine)
+    lib, h = eng.lib, eng._h
+    E = depth.shape[0]
+    H, W = depth.shape[2:]
+    median = 1 if reduction == "median" else 0
+    sc, sh = int(scale_invariant), int(shift_invariant)
+
+    with torch.cuda.device(depth.device):
+        d_full = depth.to(torch.float32).contiguous()
+        d_align = d_full
+        if max_res is not None and max(H, W) > max_res:
+            d_align = _resize_max_res_nearest_exact(d_full, max_res).contiguous()
+        hw_a = d_align.shape[2] * d_align.shape[3]
+
+        # init_param (ensemble.py:91-105)
+        mn = np.zeros(E, dtype=np.float32)
+        mx = np.zeros(E, dtype=np.float32)
+        check(lib.mgb_ens_minmax(h, ptr(d_align), E, hw_a, mn.ctypes.data_as(C.c_void_p),
+                                 mx.ctypes.data_as(C.c_void_p), stream_ptr()), "mgb_ens_minmax")
+        if shift_invariant:
+            init_s = (np.float32(1.0) / np.maximum(mx - mn, np.float32(1e-6))).astype(np.float32)
+            init_t = (-init_s * mn).astype(np.float32)
+            param0 = np.concatenate([init_s, init_t]).astype(np.float64)
+        else:
+            param0 = (np.float32(1.0) / np.maximum(mx, np.float32(1e-6))).astype(np.float64)
+
+        n_eval = [0]
+
+        def cost_fn(param: np.ndarray) -> float:
+            p = np.ascontiguousarray(param, dtype=np.float64)
+            out = C.c_double()
+            check(lib.mgb_ens_depth_cost(h, ptr(d_align), p.ctypes.data_as(C.c_void_p), E, hw_a, sc, sh, median,
+                                         float(regularizer_strength), C.byref(out), stream_ptr()),
+                  "mgb_ens_depth_cost")
+            n_eval[0] += 1
+            return out.value
+
+        nit = 0
+        if param is None:
+            import scipy.optimize
+
+            res = scipy.optimize.minimize(cost_fn, param0, method="BFGS", tol=tol,
+                                          options={"maxiter": max_iter, "disp": False})
+            param, nit = res.x, res.nit
+        param = np.ascontiguousarray(param, dtype=np.float64)   # (tests may inject the alignment)
+
+        pred = torch.empty(1, 1, H, W, dtype=torch.float32, device=depth.device)
+        unc = torch.empty_like(pred) if output_uncertainty else None
+        idx = torch.empty(1, 1, H, W, dtype=torch.int32, device=depth.device) if return_aux else None
+        check(lib.mgb_ens_depth_reduce(h, ptr(d_full), param.ctypes.data_as(C.c_void_p), E, H * W, sc, sh, median,
+                                       ptr(pred), ptr(unc), ptr(idx), stream_ptr()), "mgb_ens_depth_reduce")
+    pred = pred.to(depth.dtype)
+    if unc is not None:
+        unc = unc.to(depth.dtype)
+    if return_aux:
+        return pred, unc, {"param": param, "param0": param0, "member_idx": idx, "nit": nit, "nfev": n_eval[0],
+                            "cost_fn": cost_fn}
+    return pred, unc
+
+
+def ensemble_normals(
+    normals: torch.Tensor,
+    output_uncertainty: bool = False,
+    reduction: str = "closest",
+    engine=None,
+    return_aux: bool = False,
+) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+    if normals.dim() != 4 or normals.shape[1] != 3:
+        raise ValueError(f"Expecting 4D tensor of shape [B,3,H,W]; got {normals.shape}.")
+    if reduction not in ("closest", "mean"):
+        raise ValueError(f"Unrecognized reduction method: {reduction}.")
+    if not normals.is_cuda:
+        raise _lib.MgbError("marigold_b200.ensemble_normals needs a CUDA tensor (no CPU fallback)")
+    eng = _handle(engine)
+    E, _, H, W = normals.shape
+    with torch.cuda.device(normals.device):
+        n32 = normals.to(torch.float32).contiguous()
+        out = torch.empty(1, 3, H, W, dtype=torch.float32, device=normals.device)
+        unc = torch.empty(1, 1, H, W, dtype=torch.float32, device=normals.device) if output_uncertainty else None
+        idx = torch.empty(1, 1, H, W, dtype=torch.int32, device=normals.device) if return_aux else None
+        check(eng.lib.mgb_ens_normals(eng._h, ptr(n32), E, H * W, 1 if reduction == "closest" else 0, ptr(out),
+                                      ptr(unc), ptr(idx), stream_ptr()), "mgb_ens_normals")
+    out = out.to(normals.dtype)
+    if unc is not None:
+        unc = unc.to(normals.dtype)
+    if return_aux:
+        return out, unc, {"member_idx": idx}
+    return out, unc

@@ -1,0 +1,125 @@
+"""CPU tests of the host-side logic: scheduler coefficient tables vs the oracle's op-by-op `step`,
+the C-ABI library (loads, exports every symbol the header declares), pipeline argument handling."""
+import ctypes
+import re
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+from marigold_b200.schedulers import DDIMScheduler, LCMScheduler
+from oracle.schedulers import DDIMSchedulerOracle, LCMSchedulerOracle, SchedulerConfig
+
+ROOT = Path(__file__).resolve().parents[1]
+
+
+@pytest.mark.parametrize("n", [1, 2, 4, 10, 50, 7])
+@pytest.mark.parametrize("pred", ["v_prediction"])
+def test_ddim_coefficients_match_oracle_step(n, pred):
+    s = DDIMScheduler(prediction_type=pred)
+    s.set_timesteps(n)
+    o = DDIMSchedulerOracle(SchedulerConfig(prediction_type=pred))
+    o.set_timesteps(n)
+    assert list(map(int, s.timesteps)) == o.timesteps.tolist()
+    kx, kv, kz = s.coefficients()
+    g = torch.Generator().manual_seed(n)
+    x = torch.randn(2, 4, 8, 8, generator=g)
+    for i, t in enumerate(o.timesteps):
+        v = torch.randn(2, 4, 8, 8, generator=g)
+        ref = o.step(v, t, x)
+        mine = kx[i] * x + kv[i] * v
+        assert (ref - mine).abs().max() < 2e-5 * max(1.0, ref.abs().max().item())
+        x = ref
+    assert (kz == 0).all()
+
+
+def test_ddim_epsilon_prediction_without_zero_snr():
+    s = DDIMScheduler(prediction_type="epsilon", rescale_betas_zero_snr=False, timestep_spacing="leading")
+    s.set_timesteps(10)
+    o = DDIMSchedulerOracle(SchedulerConfig(prediction_type="epsilon", rescale_betas_zero_snr=False,
+                                            timestep_spacing="leading"))
+    o.set_timesteps(10)
+    assert list(map(int, s.timesteps)) == o.timesteps.tolist()
+    kx, kv, _ = s.coefficients()
+    x, v = torch.randn(1, 4, 4, 4), torch.randn(1, 4, 4, 4)
+    for i, t in enumerate(o.timesteps):
+        assert torch.allclose(o.step(v, t, x), kx[i] * x + kv[i] * v, atol=3e-5)
+    with pytest.raises(RuntimeError):
+        z = DDIMScheduler(prediction_type="epsilon")   # zero-SNR + epsilon is undefined at t=999
+        z.set_timesteps(4)
+        z.coefficients()
+
+
+@pytest.mark.parametrize("n", [1, 2, 4, 8])
+def test_lcm_coefficients_match_oracle_step(n):
+    s = LCMScheduler()
+    s.set_timesteps(n)
+    o = LCMSchedulerOracle()
+    o.set_timesteps(n)
+    assert list(map(int, s.timesteps)) == o.timesteps.tolist()
+    kx, kv, kz = s.coefficients()
+    g = torch.Generator().manual_seed(100 + n)
+    x = torch.randn(2, 4, 8, 8, generator=g)
+    for i, t in enumerate(o.timesteps):
+        v = torch.randn(2, 4, 8, 8, generator=g)
+        z = torch.randn(2, 4, 8, 8, generator=g)
+        ref = o.step(v, t, x, noise=z)
+        mine = kx[i] * x + kv[i] * v + kz[i] * z
+        assert (ref - mine).abs().max() < 2e-5 * max(1.0, ref.abs().max().item())
+        x = ref
+    assert kz[-1] == 0 and (kz[:-1] > 0).all()
+
+
+def test_library_exports_every_declared_symbol():
+    from marigold_b200 import _lib
+
+    header = (ROOT / "include" / "marigold_b200.h").read_text()
+    declared = set(re.findall(r"\b(mgb_[a-z0-9_]+)\s*\(", header))
+    declared -= {"mgb_status", "mgb_dtype", "mgb_decode_mode"}
+    assert declared, "no declarations parsed"
+    lib = ctypes.CDLL(str(_lib.lib_path())) if _lib.lib_path().exists() else None
+    if lib is None:
+        _lib.load()          # builds (nvcc cross-compiles without a GPU)
+        lib = ctypes.CDLL(str(_lib.lib_path()))
+    missing = [s for s in sorted(declared) if not hasattr(lib, s)]
+    assert not missing, f"header declares symbols the library does not export: {missing}"
+    assert declared == set(_lib.SIGNATURES), "ctypes SIGNATURES out of sync with include/marigold_b200.h"
+    loaded = _lib.load()
+    assert b"sm_100a" in loaded.mgb_build_info()
+
+
+def test_no_cpu_fallback_on_missing_gpu():
+    """On a box without a GPU the product path must fail loudly, never silently compute on the CPU."""
+    from marigold_b200 import _lib
+    from marigold_b200.engine import Engine
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(_lib.MgbError):
+        Engine()
+    from marigold_b200.ensemble import ensemble_depth, ensemble_normals
+
+    with pytest.raises(_lib.MgbError):
+        ensemble_depth(torch.rand(2, 1, 8, 8))
+    with pytest.raises(_lib.MgbError):
+        ensemble_normals(torch.nn.functional.normalize(torch.randn(2, 3, 8, 8), dim=1))
+
+
+def test_product_never_imports_oracle():
+    for py in (ROOT / "marigold_b200").glob("*.py"):
+        src = py.read_text()
+        assert "import oracle" not in src and "from oracle" not in src, f"{py.name} imports the oracle"
+
+
+def test_colorize_and_resize_helpers():
+    from marigold_b200.pipeline import colorize_depth_maps, get_tv_resample_method, resize_max_res
+
+    c = colorize_depth_maps(np.linspace(0, 1, 12).reshape(3, 4), 0, 1)
+    assert c.shape == (3, 3, 4) and c.min() >= 0 and c.max() <= 1
+    np.testing.assert_allclose(c[:, 0, 0], np.array([158, 1, 66]) / 255.0)
+    np.testing.assert_allclose(c[:, 2, 3], np.array([94, 79, 162]) / 255.0)
+    with pytest.raises(ValueError):
+        get_tv_resample_method("lanczos")
+    img = torch.randint(0, 256, (1, 3, 90, 130), dtype=torch.uint8)
+    assert resize_max_res(img, 64).shape == (1, 3, 44, 64)     # int() truncation: 90 * 64/130 = 44.3

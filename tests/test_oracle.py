@@ -1,0 +1,103 @@
+"""CPU tests that pin the oracle: architecture known-answers (parameter counts, timestep lists,
+zero-terminal-SNR) and the reference-generated golden vectors for the ensembling functions."""
+import numpy as np
+import pytest
+import torch
+
+from oracle.ensemble import ensemble_depth, ensemble_normals
+from oracle.schedulers import DDIMSchedulerOracle, LCMSchedulerOracle
+from oracle.unet import UNet2DConditionOracle, UNetConfig
+from oracle.vae import AutoencoderKLOracle, VAEConfig
+from tests.golden.cases import DEPTH_CASES, NORMALS_CASES, RESIZE_CASES, depth_input, normals_input, resize_input
+
+GOLD = np.load(__file__.rsplit("/", 1)[0] + "/golden/ensemble_golden.npz")
+
+
+def _count(m):
+    return sum(p.numel() for p in m.parameters())
+
+
+def test_sd2_parameter_counts():
+    # the only offline evidence that the restated architecture is structurally right
+    with torch.device("meta"):
+        u = UNet2DConditionOracle(UNetConfig())
+        v = AutoencoderKLOracle(VAEConfig())
+    assert _count(u) == 865_922_244
+    assert _count(v.encoder) + _count(v.quant_conv) == 34_163_664
+    assert _count(v.decoder) + _count(v.post_quant_conv) == 49_490_199
+
+
+def test_unet_shape_walk_tiny():
+    torch.manual_seed(0)
+    u = UNet2DConditionOracle(UNetConfig.tiny()).eval()
+    with torch.no_grad():
+        y = u(torch.randn(2, 8, 16, 24), 999, torch.randn(2, 2, 128))
+    assert y.shape == (2, 4, 16, 24) and torch.isfinite(y).all()
+
+
+def test_ddim_timesteps_and_zero_snr():
+    d = DDIMSchedulerOracle()
+    want = {1: [999], 4: [999, 749, 499, 249], 10: list(range(999, 0, -100))}
+    for n, ts in want.items():
+        d.set_timesteps(n)
+        assert d.timesteps.tolist() == ts
+    d.set_timesteps(50)
+    assert d.timesteps[:3].tolist() == [999, 979, 959] and int(d.timesteps[-1]) == 19
+    assert float(d.alphas_cumprod[999]) == 0.0
+    # t = 999, v-prediction, zero SNR: x0 = -v, no division
+    d.set_timesteps(1)
+    x, v = torch.randn(1, 4, 4, 4), torch.randn(1, 4, 4, 4)
+    a_prev = d.final_alpha_cumprod
+    assert torch.allclose(d.step(v, 999, x), a_prev.sqrt() * (-v) + (1 - a_prev).sqrt() * x, atol=1e-6)
+
+
+def test_lcm_timesteps():
+    l = LCMSchedulerOracle()
+    l.set_timesteps(4)
+    assert l.timesteps.tolist() == [999, 759, 499, 259]
+    l.set_timesteps(1)
+    assert l.timesteps.tolist() == [999]
+
+
+@pytest.mark.parametrize("name", list(DEPTH_CASES))
+def test_ensemble_depth_oracle_matches_reference_golden(name):
+    cfg = DEPTH_CASES[name]
+    pred, unc, param = ensemble_depth(depth_input(cfg), return_param=True, **cfg.get("kwargs", {}))
+    np.testing.assert_array_equal(pred.numpy(), GOLD[f"depth/{name}/pred"])      # bit-exact
+    if f"depth/{name}/unc" in GOLD:
+        np.testing.assert_array_equal(unc.numpy(), GOLD[f"depth/{name}/unc"])
+    np.testing.assert_array_equal(param, GOLD[f"depth/{name}/x"])
+
+
+@pytest.mark.parametrize("name", list(NORMALS_CASES))
+def test_ensemble_normals_oracle_matches_reference_golden(name):
+    cfg = NORMALS_CASES[name]
+    pred, unc = ensemble_normals(normals_input(cfg), **cfg.get("kwargs", {}))
+    np.testing.assert_array_equal(pred.numpy(), GOLD[f"normals/{name}/pred"])
+    if f"normals/{name}/unc" in GOLD:
+        np.testing.assert_array_equal(unc.numpy(), GOLD[f"normals/{name}/unc"])
+
+
+def test_ensemble_error_behaviour():
+    with pytest.raises(ValueError):
+        ensemble_depth(torch.rand(2, 3, 4, 4))
+    with pytest.raises(ValueError):
+        ensemble_depth(torch.rand(2, 1, 4, 4), reduction="mode")
+    with pytest.raises(ValueError):
+        ensemble_depth(torch.rand(2, 1, 4, 4), scale_invariant=False, shift_invariant=True)
+    with pytest.raises(ValueError):
+        ensemble_normals(torch.rand(2, 1, 4, 4))
+    with pytest.raises(ValueError):
+        ensemble_normals(torch.rand(2, 3, 4, 4), reduction="median")
+
+
+@pytest.mark.parametrize("name", [k for k in RESIZE_CASES if f"resize/{k}" in GOLD.files])
+def test_resize_max_res_matches_reference_golden(name):
+    from oracle.pipeline import resize_max_res
+
+    cfg = RESIZE_CASES[name]
+    mode = {"bilinear": "bilinear", "nearest": "nearest-exact"}[cfg["method"]]
+    out = resize_max_res(resize_input(cfg), cfg["max_edge"], mode)
+    g = GOLD[f"resize/{name}"]
+    assert out.shape == g.shape
+    assert np.abs(out.numpy().astype(np.int32) - g.astype(np.int32)).max() <= 1   # uint8 rounding of antialias

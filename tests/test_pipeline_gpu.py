@@ -1,0 +1,107 @@
+"""End-to-end drop-in pipelines (tiny config) against the oracle pipelines on identical weights,
+image and explicit noise; plus the reference's error behaviour at the call surface."""
+import numpy as np
+import pytest
+import torch
+
+from tests.helpers import engine_from_oracle, oracle_models, synthetic_image
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def setup():
+    unet, vae, text = oracle_models("tiny")
+    eng = engine_from_oracle(unet, vae, text)
+    yield unet, vae, text, eng
+    eng.close()
+
+
+def _noise(E, lh, lw, n, seed=2024):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(E, 4, lh, lw, generator=g), torch.randn(max(n - 1, 1), E, 4, lh, lw, generator=g)
+
+
+def test_depth_pipeline_single_member_matches_oracle(setup):
+    from marigold_b200.pipeline import MarigoldDepthPipeline
+    from marigold_b200.schedulers import DDIMScheduler
+    from oracle.pipeline import OracleDepthPipeline
+    from oracle.schedulers import DDIMSchedulerOracle
+
+    unet, vae, text, eng = setup
+    img = synthetic_image(128)
+    z0, _ = _noise(1, 16, 16, 4)
+    pipe = MarigoldDepthPipeline(eng, DDIMScheduler(), text, default_denoising_steps=4,
+                                 default_processing_resolution=128)
+    out = pipe(img, ensemble_size=1, noise=z0, show_progress_bar=False)
+    ora = OracleDepthPipeline(unet, vae, DDIMSchedulerOracle(), text, 4, 128)
+    ref, _, _ = ora(img, ensemble_size=1, noise=z0)
+    assert out.depth_np.shape == (128, 128) and out.uncertainty is None and out.depth_colored is not None
+    # bf16 operand tolerance for a 4-step trajectory + decoder (the map lives in [0,1])
+    assert np.abs(out.depth_np - ref).max() < 3e-2
+    assert np.abs(out.depth_np - ref).mean() < 5e-3
+
+
+def test_depth_pipeline_ensemble_and_resize(setup):
+    from marigold_b200.pipeline import MarigoldDepthPipeline
+    from marigold_b200.schedulers import DDIMScheduler
+    from oracle.pipeline import OracleDepthPipeline
+    from oracle.schedulers import DDIMSchedulerOracle
+
+    unet, vae, text, eng = setup
+    img = synthetic_image(256)[:, :, :128, :]                    # 128 x 256 input -> processed at 64 x 128
+    z0, _ = _noise(3, 8, 16, 2)
+    pipe = MarigoldDepthPipeline(eng, DDIMScheduler(), text, default_denoising_steps=2,
+                                 default_processing_resolution=128)
+    with pytest.raises(Exception):
+        pipe(img, ensemble_size=3, noise=z0, processing_res=100, show_progress_bar=False)  # 50x100: not /64
+    out = pipe(img, ensemble_size=3, noise=z0, batch_size=2, show_progress_bar=False,
+               ensemble_kwargs=dict(output_uncertainty=True))
+    ora = OracleDepthPipeline(unet, vae, DDIMSchedulerOracle(), text, 2, 128)
+    ref, unc, _ = ora(img, ensemble_size=3, noise=z0, batch_size=2, ensemble_kwargs=dict(output_uncertainty=True))
+    assert out.depth_np.shape == (128, 256) and out.uncertainty.shape == (128, 256)
+    assert out.depth_np.min() >= 0 and out.depth_np.max() <= 1
+    assert np.abs(out.depth_np - ref).mean() < 3e-2              # BFGS path is rounding-chaotic (see test_ensemble_gpu)
+
+
+def test_depth_pipeline_lcm(setup):
+    from marigold_b200.pipeline import MarigoldDepthPipeline
+    from marigold_b200.schedulers import LCMScheduler
+    from oracle.pipeline import OracleDepthPipeline
+    from oracle.schedulers import LCMSchedulerOracle
+
+    unet, vae, text, eng = setup
+    img = synthetic_image(128)
+    z0, zs = _noise(2, 16, 16, 4)
+    pipe = MarigoldDepthPipeline(eng, LCMScheduler(), text, default_denoising_steps=4,
+                                 default_processing_resolution=128)
+    out = pipe(img, ensemble_size=1, noise=z0[:1], step_noise=zs[:, :1], show_progress_bar=False)
+    ora = OracleDepthPipeline(unet, vae, LCMSchedulerOracle(), text, 4, 128)
+    ref, _, _ = ora(img, ensemble_size=1, noise=z0[:1], step_noise=zs[:, :1])
+    assert np.abs(out.depth_np - ref).max() < 3e-2
+
+
+def test_normals_pipeline_and_errors(setup):
+    from marigold_b200.pipeline import MarigoldNormalsPipeline
+    from marigold_b200.schedulers import DDIMScheduler, LCMScheduler
+    from oracle.pipeline import OracleNormalsPipeline
+    from oracle.schedulers import DDIMSchedulerOracle
+
+    unet, vae, text, eng = setup
+    img = synthetic_image(128)
+    z0, _ = _noise(4, 16, 16, 2)
+    pipe = MarigoldNormalsPipeline(eng, DDIMScheduler(), text, default_denoising_steps=2,
+                                   default_processing_resolution=128)
+    out = pipe(img, ensemble_size=4, noise=z0, show_progress_bar=False)
+    ora = OracleNormalsPipeline(unet, vae, DDIMSchedulerOracle(), text, 2, 128)
+    ref, _, _ = ora(img, ensemble_size=4, noise=z0)
+    assert out.normals_np.shape == (3, 128, 128)
+    strong = np.linalg.norm(ref, axis=0) > 0.5
+    cos = (out.normals_np * ref).sum(0)[strong]
+    assert np.median(cos) > 0.99
+    with pytest.raises(RuntimeError):
+        MarigoldNormalsPipeline(eng, LCMScheduler(), text, 2, 128)(img, noise=z0[:1])
+    with pytest.raises(TypeError):
+        pipe("not an image")
+    with pytest.raises(AssertionError):
+        pipe(torch.zeros(3, 64, 64))
