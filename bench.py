@@ -284,7 +284,9 @@ def _cpu_baseline(unet, text, steps=1, res=RES):
 
     from oracle.schedulers import DDIMSchedulerOracle
 
-    torch.set_num_threads(os.cpu_count() or 1)
+    from tests.helpers import usable_cores
+
+    torch.set_num_threads(usable_cores())
     lh = res // 8
     g = torch.Generator().manual_seed(1)
     x = torch.randn(1, 4, lh, lh, generator=g)
@@ -312,8 +314,10 @@ def run_reference(args):
     import torch
 
     K, W = args.steps, args.warmup
+    from tests.helpers import usable_cores
+
     unet, vae, text = _build_models("full")
-    torch.set_num_threads(os.cpu_count() or 1)
+    torch.set_num_threads(usable_cores())
     # bounded sample: pick the resolution so that W + K steps fit in ~4 minutes on this host
     probe = _cpu_baseline(unet, text, steps=1, res=384)
     t384 = 1.0 / probe["value"]

@@ -1,6 +1,7 @@
 // C ABI, handle part: weights (load / repack), conditioning, schedule, encode / denoise / decode.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 #include "net.h"
@@ -255,6 +256,12 @@ void mgb_destroy(mgb_handle* h) {
   if (h->splitk_ws) cudaFree(h->splitk_ws);
   if (h->sched_k) cudaFree(h->sched_k);
   if (h->gn_ws) cudaFree(h->gn_ws);
+  if (h->bias_table) cudaFree(h->bias_table);
+  if (h->cur_bias) cudaFree(h->cur_bias);
+  if (h->cur_sched_k) cudaFree(h->cur_sched_k);
+  if (h->step_counter) cudaFree(h->step_counter);
+  if (h->step_graph.exec) cudaGraphExecDestroy(h->step_graph.exec);
+  if (h->capture_stream) cudaStreamDestroy(h->capture_stream);
   if (h->ens_ws) cudaFree(h->ens_ws);
   if (h->ens_pinned) cudaFreeHost(h->ens_pinned);
   delete h;
@@ -440,6 +447,8 @@ int mgb_set_schedule(mgb_handle* h, int32_t n, const int32_t* timesteps, const f
   const int c0 = h->cfg.unet_block_channels[0], temb = U.temb_dim;
   std::vector<float> t(n), k(size_t(n) * 3);
   h->timesteps.assign(timesteps, timesteps + n);
+  h->timesteps_idx_scratch.resize(n);
+  for (int i = 0; i < n; ++i) h->timesteps_idx_scratch[i] = i;
   h->kz_host.assign(kz, kz + n);
   for (int i = 0; i < n; ++i) { t[i] = float(timesteps[i]); k[3 * i] = kx[i]; k[3 * i + 1] = kv[i]; k[3 * i + 2] = kz[i]; }
   if (h->sched_k) { CUDA_TRY(cudaFree(h->sched_k)); h->sched_k = nullptr; }
@@ -455,16 +464,36 @@ int mgb_set_schedule(mgb_handle* h, int32_t n, const int32_t* timesteps, const f
   TRY(launch_linear_small(d_emb, U.te_w1, U.te_b1, d_h1, n, temb, c0, 0, 1, nullptr));
   TRY(launch_linear_small(d_h1, U.te_w2, U.te_b2, d_temb, n, temb, temb, 0, 0, nullptr));
   count_launch(3);
-  for (ResnetW& r : h->unet.resnets) {
-    if (r.step_bias) { CUDA_TRY(cudaFree(r.step_bias)); r.step_bias = nullptr; }
-    CUDA_TRY(cudaMalloc(&r.step_bias, size_t(n) * r.cout * 4));
-    // conv1.bias + time_emb_proj(silu(temb))   (temb_b already holds both biases)
-    TRY(launch_linear_small(d_temb, r.temb_w, r.temb_b, r.step_bias, n, r.cout, temb, 1, 0, nullptr));
-    count_launch(1);
+  // one contiguous table [n, bias_total]: row i = every resnet's (conv1.bias + time_emb_proj(silu(temb_i)))
+  int total = 0;
+  for (ResnetW& r : h->unet.resnets) { r.bias_off = total; total += r.cout; }
+  h->bias_total = total;
+  if (h->bias_table) { CUDA_TRY(cudaFree(h->bias_table)); h->bias_table = nullptr; }
+  CUDA_TRY(cudaMalloc(&h->bias_table, size_t(n) * total * 4));
+  if (!h->cur_bias) {
+    CUDA_TRY(cudaMalloc(&h->cur_bias, size_t(total) * 4));
+    CUDA_TRY(cudaMalloc(&h->cur_sched_k, 3 * 4));
+    CUDA_TRY(cudaMalloc(&h->step_counter, 4));
+    CUDA_TRY(cudaMemset(h->step_counter, 0, 4));
+  }
+  {
+    float* tmp = nullptr;
+    int max_c = 0;
+    for (ResnetW& r : h->unet.resnets) max_c = std::max(max_c, r.cout);
+    CUDA_TRY(cudaMalloc(&tmp, size_t(n) * max_c * 4));
+    for (ResnetW& r : h->unet.resnets) {
+      TRY(launch_linear_small(d_temb, r.temb_w, r.temb_b, tmp, n, r.cout, temb, 1, 0, nullptr));
+      CUDA_TRY(cudaMemcpy2DAsync(h->bias_table + r.bias_off, size_t(total) * 4, tmp, size_t(r.cout) * 4,
+                                 size_t(r.cout) * 4, n, cudaMemcpyDeviceToDevice, nullptr));
+      count_launch(1);
+    }
+    CUDA_TRY(cudaDeviceSynchronize());
+    CUDA_TRY(cudaFree(tmp));
   }
   CUDA_TRY(cudaDeviceSynchronize());
   cudaFree(d_t); cudaFree(d_emb); cudaFree(d_h1); cudaFree(d_temb);
   h->n_steps = n;
+  if (h->step_graph.exec) { cudaGraphExecDestroy(h->step_graph.exec); h->step_graph.exec = nullptr; }
   return MGB_OK;
 }
 
@@ -486,6 +515,7 @@ static int ensure_workspace(mgb_handle* h, int op, int NB, int d0, int d1) {
   const size_t need = dry.peak + (1 << 20);
   if (need > h->arena.cap) {
     CUDA_TRY(cudaDeviceSynchronize());
+    if (h->step_graph.exec) { cudaGraphExecDestroy(h->step_graph.exec); h->step_graph.exec = nullptr; }
     if (h->arena.base) CUDA_TRY(cudaFree(h->arena.base));
     h->arena.base = nullptr; h->arena.cap = 0;
     void* p = nullptr;
@@ -495,6 +525,7 @@ static int ensure_workspace(mgb_handle* h, int op, int NB, int d0, int d1) {
   }
   if (c.splitk_need > h->splitk_cap) {
     CUDA_TRY(cudaDeviceSynchronize());
+    if (h->step_graph.exec) { cudaGraphExecDestroy(h->step_graph.exec); h->step_graph.exec = nullptr; }
     if (h->splitk_ws) CUDA_TRY(cudaFree(h->splitk_ws));
     h->splitk_ws = nullptr; h->splitk_cap = 0;
     void* p = nullptr;
@@ -621,15 +652,54 @@ int mgb_denoise_range(mgb_handle* h, const float* rgb_latent, float* target, con
   TRY(launch_nchw_to_nhwc(rgb_latent, rgb, B, 4, HW, 1.f, c.stream));
   TRY(launch_nchw_to_nhwc(target, tgt, B, 4, HW, 1.f, c.stream));
   count_launch(2);
+  const bool any_noise = step_noise != nullptr;
+  if (!any_noise) CUDA_TRY(cudaMemsetAsync(nz, 0, n * 4, c.stream));   // kz * 0 must stay finite
+  static const bool env_no_graph = getenv("MGB_NO_GRAPH") != nullptr;
+  const bool graphs = h->use_graph && !env_no_graph;
+  mgb_handle::StepGraph& G = h->step_graph;
   for (int i = first_step; i < first_step + num_steps; ++i) {
-    const float* z = nullptr;
     if (h->kz_host[i] != 0.f) {
       TRY(launch_nchw_to_nhwc(step_noise + size_t(i) * n, nz, B, 4, HW, 1.f, c.stream));
       count_launch(1);
-      z = nz;
+    }
+    const bool graph_ok = graphs && G.exec && G.NB == B && G.lh == lh && G.lw == lw &&
+                          G.arena_base == h->arena.base && G.splitk == h->splitk_ws;
+    if (graph_ok) {
+      // arm the device step counter for this replay (pageable 4-byte H2D: staged by the driver, so the
+      // source may be reused immediately)
+      CUDA_TRY(cudaMemcpyAsync(h->step_counter, &h->timesteps_idx_scratch[i], 4, cudaMemcpyHostToDevice, c.stream));
+      CUDA_TRY(cudaGraphLaunch(G.exec, c.stream));
+      count_launch(int(G.launches));
+      continue;
     }
     c.arena->release(base);
-    TRY(unet_forward(h, c, rgb, tgt, z, nullptr, i, B, lh, lw));
+    TRY(unet_forward(h, c, rgb, tgt, nz, nullptr, i, B, lh, lw));      // eager (also warms one-time attributes)
+    if (graphs && !G.exec_failed) {
+      // capture one step (reads the step index from the device counter) for all later steps of this shape
+      if (G.exec) { cudaGraphExecDestroy(G.exec); G.exec = nullptr; }
+      if (!h->capture_stream) CUDA_TRY(cudaStreamCreateWithFlags(&h->capture_stream, cudaStreamNonBlocking));
+      Ctx cc = c;
+      cc.stream = h->capture_stream;
+      const long long l0 = launch_count();
+      cudaGraph_t graph = nullptr;
+      cudaError_t ce = cudaStreamBeginCapture(h->capture_stream, cudaStreamCaptureModeThreadLocal);
+      int rc = MGB_OK;
+      if (ce == cudaSuccess) {
+        c.arena->release(base);
+        rc = unet_forward(h, cc, rgb, tgt, nz, nullptr, -1, B, lh, lw);
+        ce = cudaStreamEndCapture(h->capture_stream, &graph);
+      }
+      const long long nl = launch_count() - l0;
+      count_launch(-int(nl));                                            // capture launched nothing
+      if (rc == MGB_OK && ce == cudaSuccess && graph) ce = cudaGraphInstantiate(&G.exec, graph, 0);
+      if (graph) cudaGraphDestroy(graph);
+      if (rc != MGB_OK || ce != cudaSuccess || !G.exec) {
+        cudaGetLastError();
+        G.exec = nullptr; G.exec_failed = true;                          // stay on the eager path
+      } else {
+        G.NB = B; G.lh = lh; G.lw = lw; G.arena_base = h->arena.base; G.splitk = h->splitk_ws; G.launches = nl;
+      }
+    }
   }
   TRY(launch_nhwc_to_nchw(tgt, target, B, 4, HW, 1.f, c.stream));
   count_launch(1);

@@ -4,6 +4,7 @@
 // cross attention and a row softmax. All use 128-bit accesses where the layout allows.
 #include "common.cuh"
 #include "kernels.h"
+#include "launch.h"
 
 namespace mgb {
 
@@ -24,6 +25,8 @@ static inline int grid_for(size_t n, int threads) {
 
 // x fp32 [NB, H, W, C] -> y bf16 [NB, 4, H/2, W/2, C], plane = (h & 1) * 2 + (w & 1)
 __global__ void s2d_kernel(const float4* __restrict__ x, uint2* __restrict__ y, int NB, int H, int W, int Q) {
+  pdl_launch_dependents();
+  pdl_wait();
   const size_t total = (size_t)NB * H * W * Q;
   const int H2 = H / 2, W2 = W / 2;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -41,13 +44,15 @@ __global__ void s2d_kernel(const float4* __restrict__ x, uint2* __restrict__ y, 
 int launch_space_to_depth(const float* x, bf16* y, int NB, int H, int W, int C, cudaStream_t stream) {
   if ((H | W) & 1 || C % 4) { set_error("space_to_depth: H, W must be even, C %% 4 == 0"); return MGB_ERR_INVALID; }
   const size_t n = (size_t)NB * H * W * (C / 4);
-  s2d_kernel<<<grid_for(n, 256), 256, 0, stream>>>(reinterpret_cast<const float4*>(x), reinterpret_cast<uint2*>(y),
-                                                   NB, H, W, C / 4);
+  launch_k(s2d_kernel, grid_for(n, 256), 256, 0, stream, reinterpret_cast<const float4*>(x), reinterpret_cast<uint2*>(y),
+           NB, H, W, C / 4);
   MGB_LAUNCH_CHECK("space_to_depth");
 }
 
 // nearest x2: x fp32 [NB, H, W, C] -> y bf16 [NB, 2H, 2W, C]   (F.interpolate(scale_factor=2, mode="nearest"))
 __global__ void upsample2x_kernel(const float4* __restrict__ x, uint2* __restrict__ y, int NB, int H, int W, int Q) {
+  pdl_launch_dependents();
+  pdl_wait();
   const size_t total = (size_t)NB * H * W * Q;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     const int q = int(i % Q);
@@ -65,14 +70,16 @@ __global__ void upsample2x_kernel(const float4* __restrict__ x, uint2* __restric
 int launch_upsample2x(const float* x, bf16* y, int NB, int H, int W, int C, cudaStream_t stream) {
   if (C % 4) { set_error("upsample2x: C %% 4 != 0"); return MGB_ERR_INVALID; }
   const size_t n = (size_t)NB * H * W * (C / 4);
-  upsample2x_kernel<<<grid_for(n, 256), 256, 0, stream>>>(reinterpret_cast<const float4*>(x),
-                                                          reinterpret_cast<uint2*>(y), NB, H, W, C / 4);
+  launch_k(upsample2x_kernel, grid_for(n, 256), 256, 0, stream, reinterpret_cast<const float4*>(x),
+           reinterpret_cast<uint2*>(y), NB, H, W, C / 4);
   MGB_LAUNCH_CHECK("upsample2x");
 }
 
 // out[M, Ca + Cb] = [a | b]  (torch.cat(dim=1) in NHWC)
 __global__ void concat_kernel(const float4* __restrict__ a, const float4* __restrict__ b, float4* __restrict__ out,
                               size_t M, int Qa, int Qb) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int Qo = Qa + Qb;
   const size_t total = M * Qo;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -84,9 +91,8 @@ __global__ void concat_kernel(const float4* __restrict__ a, const float4* __rest
 int launch_concat(const float* a, const float* b, float* out, int M, int Ca, int Cb, cudaStream_t stream) {
   if ((Ca | Cb) % 4) { set_error("concat: channels %% 4 != 0"); return MGB_ERR_INVALID; }
   const size_t n = (size_t)M * ((Ca + Cb) / 4);
-  concat_kernel<<<grid_for(n, 256), 256, 0, stream>>>(reinterpret_cast<const float4*>(a),
-                                                      reinterpret_cast<const float4*>(b),
-                                                      reinterpret_cast<float4*>(out), size_t(M), Ca / 4, Cb / 4);
+  launch_k(concat_kernel, grid_for(n, 256), 256, 0, stream, reinterpret_cast<const float4*>(a),
+           reinterpret_cast<const float4*>(b), reinterpret_cast<float4*>(out), size_t(M), Ca / 4, Cb / 4);
   MGB_LAUNCH_CHECK("concat");
 }
 
@@ -107,6 +113,8 @@ int launch_cast_bf16(const float* x, bf16* y, size_t n, cudaStream_t stream) {
 // out bf16 [M, 64] = [rgb(4) | target(4) | 0 x 56]
 __global__ void pack_latents_kernel(const float4* __restrict__ rgb, const float4* __restrict__ tgt,
                                     uint4* __restrict__ out, int M) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int total = M * 8;  // 8 x 16 B per 64-channel row
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int m = i >> 3, part = i & 7;
@@ -119,8 +127,8 @@ __global__ void pack_latents_kernel(const float4* __restrict__ rgb, const float4
   }
 }
 int launch_pack_latents(const float* rgb, const float* tgt, bf16* out, int M, cudaStream_t stream) {
-  pack_latents_kernel<<<grid_for(size_t(M) * 8, 256), 256, 0, stream>>>(
-      reinterpret_cast<const float4*>(rgb), reinterpret_cast<const float4*>(tgt), reinterpret_cast<uint4*>(out), M);
+  launch_k(pack_latents_kernel, grid_for(size_t(M) * 8, 256), 256, 0, stream, reinterpret_cast<const float4*>(rgb),
+           reinterpret_cast<const float4*>(tgt), reinterpret_cast<uint4*>(out), M);
   MGB_LAUNCH_CHECK("pack_latents");
 }
 
@@ -182,6 +190,8 @@ int launch_pack_rgb(const float* rgb_nchw, bf16* out, int NB, int HW, cudaStream
 // q bf16 [M, C]; kv fp32 [2 (k|v), 2 (ctx token), C]; out bf16 [M, C]
 __global__ void __launch_bounds__(256) cross_attn2_kernel(const bf16* __restrict__ q, const float* __restrict__ kv,
                                                           bf16* __restrict__ out, int M, int C, float scale) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int heads = C / 64;
   const long long gw = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
@@ -211,7 +221,7 @@ int launch_cross_attn2(const bf16* q, const float* kv, bf16* out, int M, int C, 
   if (C % 64) { set_error("cross_attn2: C %% 64 != 0"); return MGB_ERR_INVALID; }
   const long long warps = (long long)M * (C / 64);
   const int blocks = int((warps + 7) / 8);
-  cross_attn2_kernel<<<blocks, 256, 0, stream>>>(q, kv, out, M, C, scale);
+  launch_k(cross_attn2_kernel, blocks, 256, 0, stream, q, kv, out, M, C, scale);
   MGB_LAUNCH_CHECK("cross_attn2");
 }
 
@@ -345,6 +355,32 @@ int launch_pack_decoder_latent(const float* latent_nchw, const float* w, const f
   pack_decoder_latent_kernel<<<grid_for((size_t)NB * HW * 8, 256), 256, 0, stream>>>(
       latent_nchw, w, b, inv_scale, reinterpret_cast<uint4*>(out), NB, size_t(HW));
   MGB_LAUNCH_CHECK("pack_decoder_latent");
+}
+
+__global__ void select_step_kernel(const float* __restrict__ table, int total, const float* __restrict__ sched_k,
+                                   float* __restrict__ cur_bias, float* __restrict__ cur_k,
+                                   const int* __restrict__ counter, int step) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int i = step >= 0 ? step : *counter;
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < total; j += gridDim.x * blockDim.x)
+    cur_bias[j] = table[(size_t)i * total + j];
+  if (blockIdx.x == 0 && threadIdx.x < 3) cur_k[threadIdx.x] = sched_k[(size_t)i * 3 + threadIdx.x];
+}
+int launch_select_step(const float* bias_table, int bias_total, const float* sched_k, float* cur_bias, float* cur_k,
+                       const int* counter, int step, cudaStream_t stream) {
+  launch_k(select_step_kernel, grid_for(size_t(bias_total), 256), 256, 0, stream, bias_table, bias_total, sched_k,
+           cur_bias, cur_k, counter, step);
+  MGB_LAUNCH_CHECK("select_step");
+}
+__global__ void advance_counter_kernel(int* counter) {
+  pdl_launch_dependents();
+  pdl_wait();
+  *counter += 1;
+}
+int launch_advance_counter(int* counter, cudaStream_t stream) {
+  launch_k(advance_counter_kernel, 1, 1, 0, stream, counter);
+  MGB_LAUNCH_CHECK("advance_counter");
 }
 
 }  // namespace mgb

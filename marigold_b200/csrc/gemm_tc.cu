@@ -21,6 +21,7 @@
 #include <algorithm>
 #include "common.cuh"
 #include "kernels.h"
+#include "launch.h"
 
 namespace mgb {
 
@@ -136,6 +137,7 @@ __device__ __forceinline__ void epilogue_special(const GemmEpilogue& e, const Ro
 // -------------------------------------------------------------------------------------------------
 template <int BLOCK_N>
 __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_constant__ GemmParams p) {
+  pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B tiles need 1024 B alignment
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -184,6 +186,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  // everything above overlapped the previous kernel's tail; operands / residuals are read below
+  pdl_wait();
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -347,8 +351,42 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
 // One thread per (row, 4 columns).
 // -------------------------------------------------------------------------------------------------
 __global__ void splitk_epilogue_kernel(const GemmParams p, int splits, int geglu_half /* BLOCK_N/2 or 0 */) {
+  pdl_launch_dependents();
+  pdl_wait();
   const GemmEpilogue& e = p.epi;
   const int n_out = geglu_half ? p.N / 2 : p.N;
+  if (!geglu_half && (p.N & 3) == 0 && (e.ldo & 3) == 0) {
+    // 4 columns per thread, 128-bit loads of every partial
+    const int nq = p.N / 4;
+    const long long total4 = (long long)p.M * nq;
+    const size_t slab = (size_t)p.M * p.N;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total4;
+         idx += (long long)gridDim.x * blockDim.x) {
+      const long long m = idx / nq;
+      const int c = int(idx - m * nq) * 4;
+      const float* src = p.partial + (size_t)m * p.N + c;
+      float4 a = __ldg(reinterpret_cast<const float4*>(src));
+      for (int s = 1; s < splits; ++s) {
+        const float4 b = __ldg(reinterpret_cast<const float4*>(src + (size_t)s * slab));
+        a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+      }
+      float v[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        if (e.flags & EPI_SCALE) v[i] *= e.scale;
+        if (e.bias) v[i] += __ldg(e.bias + c + i);
+        if (e.flags & EPI_SILU) v[i] = silu_f(v[i]);
+      }
+      const long long o = m * (long long)e.ldo + c;
+      if (e.residual) {
+        const float4 r = __ldg(reinterpret_cast<const float4*>(e.residual + o));
+        v[0] += r.x; v[1] += r.y; v[2] += r.z; v[3] += r.w;
+      }
+      if (e.out_f32) *reinterpret_cast<float4*>(e.out_f32 + o) = make_float4(v[0], v[1], v[2], v[3]);
+      if (e.out_bf16) *reinterpret_cast<uint2*>(e.out_bf16 + o) = make_uint2(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]));
+    }
+    return;
+  }
   const long long total = (long long)p.M * n_out;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
@@ -400,7 +438,8 @@ static int launch_one(const GemmParams& p, int splits, cudaStream_t stream) {
     m_tiles = (p.M / (p.H * p.W)) * p.tiles_x * p.tiles_y;
   }
   dim3 grid(m_tiles, (p.N + BN - 1) / BN, splits);
-  gemm_tc_kernel<BN><<<grid, kGemmThreads, smem, stream>>>(p);
+  cudaError_t le = launch_k(gemm_tc_kernel<BN>, grid, kGemmThreads, smem, stream, p);
+  if (le != cudaSuccess) return int(le);
   return int(cudaGetLastError());
 }
 
@@ -418,9 +457,9 @@ int launch_gemm_tc(const GemmParams& p, int block_n, int splits, cudaStream_t st
 
 int launch_splitk_epilogue(const GemmParams& p, int block_n, int splits, cudaStream_t stream) {
   const int n_out = (p.epi.flags & EPI_GEGLU) ? p.N / 2 : p.N;
-  const long long total = (long long)p.M * n_out;
+  const long long total = (long long)p.M * n_out / 4;
   int blocks = int(std::min<long long>((total + 255) / 256, 148 * 8));
-  splitk_epilogue_kernel<<<blocks, 256, 0, stream>>>(p, splits, (p.epi.flags & EPI_GEGLU) ? block_n / 2 : 0);
+  launch_k(splitk_epilogue_kernel, blocks, 256, 0, stream, p, splits, (p.epi.flags & EPI_GEGLU) ? block_n / 2 : 0);
   return int(cudaGetLastError());
 }
 

@@ -113,6 +113,10 @@ int launch_pack_rgb(const float* rgb_nchw, bf16* out, int NB, int HW, cudaStream
 // decoder input: post_quant_conv(latent / scale) -> bf16 NHWC-64; latent fp32 NCHW [NB,4,HW]; w fp32 [4,4]
 int launch_pack_decoder_latent(const float* latent_nchw, const float* w, const float* b, float inv_scale, bf16* out,
                                int NB, int HW, cudaStream_t stream);
+// Per-step table selection: cur_bias <- bias_table[i], cur_k <- sched_k[i], with i = step (>= 0) or *counter (< 0).
+int launch_select_step(const float* bias_table, int bias_total, const float* sched_k, float* cur_bias, float* cur_k,
+                       const int* counter, int step, cudaStream_t stream);
+int launch_advance_counter(int* counter, cudaStream_t stream);
 // 2-key cross attention with pre-projected K/V: q bf16 [M, C]; kv fp32 [2(k|v), 2(tokens), C]; out bf16 [M, C]
 int launch_cross_attn2(const bf16* q, const float* kv, bf16* out, int M, int C, float scale, cudaStream_t stream);
 // Tiny dense layer for M <= 16 rows (time MLP, text K/V): y[M,N] = act(x[M,K]) W[N,K]^T + b ; fp32

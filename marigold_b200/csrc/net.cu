@@ -125,8 +125,7 @@ static int groupnorm(Ctx& c, const float* x, bf16* y, bf16* raw, const NormW& n,
 // ResnetBlock2D: GN -> SiLU -> conv3x3 (+temb) -> GN -> SiLU -> conv3x3 ; + (1x1 shortcut | x)
 //   x fp32 [M, cin] -> y fp32 [M, cout] (y preallocated by the caller)
 // ---------------------------------------------------------------------------------------------
-static int resnet_forward(Ctx& c, const ResnetW& R, const float* x, float* y, int NB, int H, int W, int step,
-                          float* gn_ws) {
+static int resnet_forward(Ctx& c, const ResnetW& R, const float* x, float* y, int NB, int H, int W, float* gn_ws) {
   const size_t M = size_t(NB) * H * W;
   const size_t mk = c.arena->mark();
   bf16* t1 = aalloc<bf16>(c, M * R.cin);
@@ -136,7 +135,7 @@ static int resnet_forward(Ctx& c, const ResnetW& R, const float* x, float* y, in
   float* sc = R.has_sc ? aalloc<float>(c, M * R.cout) : nullptr;
   TRY(groupnorm(c, x, t1, raw, R.n1, NB, H * W, R.eps, 1, gn_ws));
   Epi e1;
-  e1.bias = R.step_bias ? R.step_bias + size_t(step) * R.cout : R.c1.b;
+  e1.bias = (R.bias_off >= 0 && c.cur_bias) ? c.cur_bias + R.bias_off : R.c1.b;
   e1.out_f32 = h;
   TRY(conv3x3(c, t1, NB, H, W, R.c1, 0, e1));
   TRY(groupnorm(c, h, t2, nullptr, R.n2, NB, H * W, R.eps, 1, gn_ws));
@@ -238,6 +237,10 @@ int unet_forward(mgb_handle* hd, Ctx& c, const float* rgb, float* tgt, const flo
   std::vector<Skip> skips;
   size_t ri = 0, xi = 0;
 
+  // step < 0: the step index is read from the device counter (CUDA-graph replay)
+  LAUNCH(launch_select_step(hd->bias_table, hd->bias_total, hd->sched_k, hd->cur_bias, hd->cur_sched_k,
+                            hd->step_counter, step, c.stream), 1);
+  c.cur_bias = hd->cur_bias;
   bf16* x0 = aalloc<bf16>(c, M * 64);
   LAUNCH(launch_pack_latents(rgb, tgt, x0, int(M), c.stream), 1);
   float* h = aalloc<float>(c, M * ch[0]);
@@ -249,7 +252,7 @@ int unet_forward(mgb_handle* hd, Ctx& c, const float* rgb, float* tgt, const flo
     const bool last = i == 3;
     for (int j = 0; j < L; ++j) {
       float* y = aalloc<float>(c, M * ch[i]);
-      TRY(resnet_forward(c, U.resnets[ri++], h, y, NB, H, W, step, gn_ws));
+      TRY(resnet_forward(c, U.resnets[ri++], h, y, NB, H, W, gn_ws));
       h = y; cur = ch[i];
       if (!last) {
         float* y2 = aalloc<float>(c, M * cur);
@@ -273,11 +276,11 @@ int unet_forward(mgb_handle* hd, Ctx& c, const float* rgb, float* tgt, const flo
   // mid
   {
     float* y = aalloc<float>(c, M * cur);
-    TRY(resnet_forward(c, U.resnets[ri++], h, y, NB, H, W, step, gn_ws));
+    TRY(resnet_forward(c, U.resnets[ri++], h, y, NB, H, W, gn_ws));
     float* y2 = aalloc<float>(c, M * cur);
     TRY(xfmr_forward(c, U.xfmrs[xi++], y, y2, NB, H * W, gn_ws));
     float* y3 = aalloc<float>(c, M * cur);
-    TRY(resnet_forward(c, U.resnets[ri++], y2, y3, NB, H, W, step, gn_ws));
+    TRY(resnet_forward(c, U.resnets[ri++], y2, y3, NB, H, W, gn_ws));
     h = y3;
   }
   // up path
@@ -289,7 +292,7 @@ int unet_forward(mgb_handle* hd, Ctx& c, const float* rgb, float* tgt, const flo
       float* cat = aalloc<float>(c, M * (cur + s.c));
       LAUNCH(launch_concat(h, s.p, cat, int(M), cur, s.c, c.stream), 1);
       float* y = aalloc<float>(c, M * cout);
-      TRY(resnet_forward(c, U.resnets[ri++], cat, y, NB, H, W, step, gn_ws));
+      TRY(resnet_forward(c, U.resnets[ri++], cat, y, NB, H, W, gn_ws));
       h = y; cur = cout;
       if (i > 0) {
         float* y2 = aalloc<float>(c, M * cur);
@@ -314,9 +317,10 @@ int unet_forward(mgb_handle* hd, Ctx& c, const float* rgb, float* tgt, const flo
     e.bias = U.conv_out.b;
     e.flags = EPI_SCHED;
     e.out_f32 = tgt; e.sched_x = tgt; e.sched_z = noise; e.aux_out = raw_out;
-    e.sched_k = hd->sched_k + size_t(step) * 3;
+    e.sched_k = hd->cur_sched_k;
     TRY(conv3x3(c, t, NB, H, W, U.conv_out, 0, e));
   }
+  if (step < 0) LAUNCH(launch_advance_counter(hd->step_counter, c.stream), 1);
   return MGB_OK;
 }
 
@@ -343,7 +347,7 @@ int vae_encode_forward(mgb_handle* hd, Ctx& c, const float* rgb, float* latent_o
     float* bufB = aalloc<float>(c, M * ch[i]);
     for (int j = 0; j < L; ++j) {
       float* y = (j & 1) ? bufB : bufA;
-      TRY(resnet_forward(c, V.enc_res[ri++], h, y, NB, H, W, 0, gn_ws));
+      TRY(resnet_forward(c, V.enc_res[ri++], h, y, NB, H, W, gn_ws));
       h = y; cur = ch[i];
     }
     if (i < 3) {
@@ -357,11 +361,11 @@ int vae_encode_forward(mgb_handle* hd, Ctx& c, const float* rgb, float* latent_o
   }
   {
     float* y1 = aalloc<float>(c, M * cur);
-    TRY(resnet_forward(c, V.enc_res[ri++], h, y1, NB, H, W, 0, gn_ws));
+    TRY(resnet_forward(c, V.enc_res[ri++], h, y1, NB, H, W, gn_ws));
     float* y2 = aalloc<float>(c, M * cur);
     TRY(vae_attn_forward(c, V.enc_attn, y1, y2, NB, H * W, gn_ws));
     float* y3 = aalloc<float>(c, M * cur);
-    TRY(resnet_forward(c, V.enc_res[ri++], y2, y3, NB, H, W, 0, gn_ws));
+    TRY(resnet_forward(c, V.enc_res[ri++], y2, y3, NB, H, W, gn_ws));
     h = y3;
   }
   bf16* t = aalloc<bf16>(c, M * cur);
@@ -395,11 +399,11 @@ int vae_decode_forward(mgb_handle* hd, Ctx& c, const float* latent, float* out, 
   { Epi e; e.bias = V.dec_in.b; e.out_f32 = h; TRY(conv3x3(c, z, NB, H, W, V.dec_in, 0, e)); }
   {
     float* y1 = aalloc<float>(c, M * cur);
-    TRY(resnet_forward(c, V.dec_res[ri++], h, y1, NB, H, W, 0, gn_ws));
+    TRY(resnet_forward(c, V.dec_res[ri++], h, y1, NB, H, W, gn_ws));
     float* y2 = aalloc<float>(c, M * cur);
     TRY(vae_attn_forward(c, V.dec_attn, y1, y2, NB, H * W, gn_ws));
     float* y3 = aalloc<float>(c, M * cur);
-    TRY(resnet_forward(c, V.dec_res[ri++], y2, y3, NB, H, W, 0, gn_ws));
+    TRY(resnet_forward(c, V.dec_res[ri++], y2, y3, NB, H, W, gn_ws));
     h = y3;
   }
   for (int i = 0; i < 4; ++i) {
@@ -408,7 +412,7 @@ int vae_decode_forward(mgb_handle* hd, Ctx& c, const float* latent, float* out, 
     float* bufB = aalloc<float>(c, M * cout);
     for (int j = 0; j < L + 1; ++j) {
       float* y = (j & 1) ? bufB : bufA;
-      TRY(resnet_forward(c, V.dec_res[ri++], h, y, NB, H, W, 0, gn_ws));
+      TRY(resnet_forward(c, V.dec_res[ri++], h, y, NB, H, W, gn_ws));
       h = y; cur = cout;
     }
     if (i < 3) {

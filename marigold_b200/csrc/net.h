@@ -43,7 +43,7 @@ struct ResnetW {
   // time embedding projection (UNet only): fp32 [cout, temb_dim]; bias already includes conv1.bias
   float* temb_w = nullptr;
   float* temb_b = nullptr;
-  float* step_bias = nullptr;  // device [n_steps, cout]: conv1 bias + time_emb_proj(silu(temb_i))
+  int bias_off = -1;           // offset of this resnet's row in the per-step bias table (UNet only)
   float eps = 1e-5f;
 };
 struct XfmrW {
@@ -78,6 +78,7 @@ struct Ctx {
   size_t splitk_cap = 0;   // bytes available
   size_t splitk_need = 0;  // bytes needed (dry run)
   int groups = 32;
+  const float* cur_bias = nullptr;  // current step's concatenated resnet conv1 biases (device)
 };
 
 struct UNetW {
@@ -125,6 +126,24 @@ struct mgb_handle {
   std::vector<int> timesteps;
   float* sched_k = nullptr;   // device [n_steps, 3]
   std::vector<float> kz_host;
+  // per-step tables selected on the device (so one CUDA graph serves every step)
+  float* bias_table = nullptr;  // device [n_steps, bias_total]
+  int bias_total = 0;
+  float* cur_bias = nullptr;    // device [bias_total]
+  float* cur_sched_k = nullptr; // device [3]
+  int* step_counter = nullptr;  // device
+  // cached CUDA graph of one UNet step
+  struct StepGraph {
+    cudaGraphExec_t exec = nullptr;
+    int NB = 0, lh = 0, lw = 0;
+    const char* arena_base = nullptr;
+    const float* splitk = nullptr;
+    long long launches = 0;
+    bool exec_failed = false;
+  } step_graph;
+  std::vector<int> timesteps_idx_scratch;  // [0, 1, 2, ...]: host source for arming the device step counter
+  cudaStream_t capture_stream = nullptr;
+  bool use_graph = true;
   // small persistent buffers
   float* gn_ws = nullptr;
   size_t gn_ws_bytes = 0;

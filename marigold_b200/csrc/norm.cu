@@ -10,12 +10,13 @@
 // Transformer2DModel / VAE blocks; SURVEY.md App. A.1-A.2.
 #include "common.cuh"
 #include "kernels.h"
+#include "launch.h"
 
 namespace mgb {
 
 constexpr int kGnThreads = 256;
 constexpr int kGnMaxK = 4;      // channel-quads per thread
-constexpr int kGnMaxChunks = 296;
+constexpr int kGnMaxChunks = 148;   // one pixel chunk per SM
 
 struct GnGeom {
   int Q;        // C / 4
@@ -52,6 +53,8 @@ size_t groupnorm_ws_bytes(int NB, int HW, int C, int G) {
 __global__ void __launch_bounds__(kGnThreads) gn_stats_kernel(const float* __restrict__ x, float* __restrict__ ws,
                                                               int HW, int C, int G, GnGeom g) {
   extern __shared__ float s_acc[];  // [2 * C]
+  pdl_launch_dependents();
+  pdl_wait();
   const int img = blockIdx.y, chunk = blockIdx.x;
   for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) s_acc[i] = 0.f;
   __syncthreads();
@@ -103,20 +106,34 @@ __global__ void __launch_bounds__(kGnThreads)
                     const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ ws,
                     int HW, int C, int G, float eps, int silu, GnGeom g) {
   extern __shared__ float s_stat[];  // mean[G], rstd[G]
+  pdl_launch_dependents();
+  pdl_wait();
   const int img = blockIdx.y, chunk = blockIdx.x;
   const int cpg = C / G;
-  for (int gi = threadIdx.x; gi < G; gi += blockDim.x) {
+  // combine the per-chunk partials of this image: (group, slice) per thread, then across slices
+  __shared__ double s_part[2][kGnThreads];
+  {
+    const int slices = kGnThreads / G;                 // G <= 256
+    const int gi = threadIdx.x % G, sl = threadIdx.x / G;
     double s = 0.0, q = 0.0;
-    for (int ch = 0; ch < g.chunks; ++ch) {
-      const float* src = ws + (((size_t)img * kGnMaxChunks + ch) * G + gi) * 2;
-      s += double(src[0]); q += double(src[1]);
+    if (sl < slices) {
+      for (int ch = sl; ch < g.chunks; ch += slices) {
+        const float2 v = __ldg(reinterpret_cast<const float2*>(ws + (((size_t)img * kGnMaxChunks + ch) * G + gi) * 2));
+        s += double(v.x); q += double(v.y);
+      }
     }
-    const double n = double(HW) * cpg;
-    const double mean = s / n;
-    double var = q / n - mean * mean;
-    if (var < 0.0) var = 0.0;
-    s_stat[gi] = float(mean);
-    s_stat[G + gi] = float(1.0 / sqrt(var + double(eps)));
+    s_part[0][threadIdx.x] = s; s_part[1][threadIdx.x] = q;
+    __syncthreads();
+    if (threadIdx.x < G) {
+      s = 0.0; q = 0.0;
+      for (int k = 0; k < slices; ++k) { s += s_part[0][k * G + threadIdx.x]; q += s_part[1][k * G + threadIdx.x]; }
+      const double n = double(HW) * cpg;
+      const double mean = s / n;
+      double var = q / n - mean * mean;
+      if (var < 0.0) var = 0.0;
+      s_stat[threadIdx.x] = float(mean);
+      s_stat[G + threadIdx.x] = float(1.0 / sqrt(var + double(eps)));
+    }
   }
   __syncthreads();
   const int tq = threadIdx.x % g.Tq, tp = threadIdx.x / g.Tq;
@@ -158,14 +175,14 @@ __global__ void __launch_bounds__(kGnThreads)
 int launch_groupnorm(const float* x, bf16* y, bf16* raw_copy, const float* gamma, const float* beta, float* ws,
                      int NB, int HW, int C, int G, float eps, int silu, cudaStream_t stream) {
   GnGeom g;
-  if (C % G != 0 || !gn_geometry(HW, C, &g)) {
+  if (C % G != 0 || G > kGnThreads || kGnThreads % G != 0 || !gn_geometry(HW, C, &g)) {
     set_error("groupnorm: unsupported C=%d G=%d", C, G);
     return MGB_ERR_INVALID;
   }
   dim3 grid(g.chunks, NB);
-  gn_stats_kernel<<<grid, kGnThreads, 2 * C * sizeof(float), stream>>>(x, ws, HW, C, G, g);
-  gn_apply_kernel<<<grid, kGnThreads, 2 * G * sizeof(float), stream>>>(x, y, raw_copy, gamma, beta, ws, HW, C, G, eps,
-                                                                      silu, g);
+  launch_k(gn_stats_kernel, grid, kGnThreads, 2 * C * sizeof(float), stream, x, ws, HW, C, G, g);
+  launch_k(gn_apply_kernel, grid, kGnThreads, 2 * G * sizeof(float), stream, x, y, raw_copy, gamma, beta,
+           static_cast<const float*>(ws), HW, C, G, eps, silu, g);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     set_error("groupnorm launch: %s", cudaGetErrorString(e));
@@ -182,6 +199,8 @@ constexpr int kLnMaxQ = 10;
 __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, bf16* __restrict__ y,
                                                         const float* __restrict__ gamma,
                                                         const float* __restrict__ beta, int M, int C, float eps) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= M) return;
@@ -235,7 +254,7 @@ int launch_layernorm(const float* x, bf16* y, const float* gamma, const float* b
   }
   const int warps_per_block = 8;
   const int blocks = (M + warps_per_block - 1) / warps_per_block;
-  layernorm_kernel<<<blocks, 256, 0, stream>>>(x, y, gamma, beta, M, C, eps);
+  launch_k(layernorm_kernel, blocks, 256, 0, stream, x, y, gamma, beta, M, C, eps);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     set_error("layernorm launch: %s", cudaGetErrorString(e));

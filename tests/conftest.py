@@ -11,6 +11,14 @@ if str(ROOT) not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+    try:
+        import torch
+
+        from tests.helpers import usable_cores
+
+        torch.set_num_threads(min(usable_cores(), 32))
+    except Exception:  # noqa: BLE001
+        pass
 
 
 def pytest_collection_modifyitems(config, items):

@@ -9,6 +9,31 @@ from oracle.unet import UNet2DConditionOracle, UNetConfig
 from oracle.vae import AutoencoderKLOracle, VAEConfig
 
 
+def usable_cores() -> int:
+    """Cores this process may actually use (affinity mask and cgroup CPU quota), not os.cpu_count():
+    on the GPU box the container sees 128 CPUs but is limited, and 128 torch threads thrash."""
+    import os
+
+    n = os.cpu_count() or 1
+    try:
+        n = min(n, len(os.sched_getaffinity(0)))
+    except Exception:  # noqa: BLE001
+        pass
+    try:
+        q, p = open("/sys/fs/cgroup/cpu.max").read().split()
+        if q != "max":
+            n = min(n, max(1, int(float(q) / float(p))))
+    except Exception:  # noqa: BLE001
+        try:
+            q = int(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+            p_ = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if q > 0:
+                n = min(n, max(1, q // p_))
+        except Exception:  # noqa: BLE001
+            pass
+    return max(1, n)
+
+
 def oracle_models(kind: str = "tiny", seed: int = 0):
     torch.manual_seed(seed)
     if kind == "tiny":
