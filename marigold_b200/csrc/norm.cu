@@ -16,7 +16,7 @@ namespace mgb {
 
 constexpr int kGnThreads = 256;
 constexpr int kGnMaxK = 4;      // channel-quads per thread
-constexpr int kGnMaxChunks = 148;   // one pixel chunk per SM
+constexpr int kGnMaxChunks = 592;   // partial-statistics slots per image
 
 struct GnGeom {
   int Q;        // C / 4
@@ -39,7 +39,13 @@ static bool gn_geometry(int HW, int C, GnGeom* g) {
   g->Tq = bestTq;
   g->Tp = 256 / bestTq;
   g->Kq = g->Q / bestTq;
-  g->chunks = HW < kGnMaxChunks ? HW : kGnMaxChunks;
+  // ~16K elements (64 KB fp32) per chunk: enough CTAs to saturate HBM on the big VAE tensors, few enough
+  // partials that combining them stays negligible on the small UNet ones
+  long long want = ((long long)HW * C + 16383) / 16384;
+  if (want < 1) want = 1;
+  if (want > kGnMaxChunks) want = kGnMaxChunks;
+  if (want > HW) want = HW;
+  g->chunks = int(want);
   g->P = (HW + g->chunks - 1) / g->chunks;
   g->chunks = (HW + g->P - 1) / g->P;
   return true;

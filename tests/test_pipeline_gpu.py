@@ -59,7 +59,8 @@ def test_depth_pipeline_ensemble_and_resize(setup):
                ensemble_kwargs=dict(output_uncertainty=True))
     ora = OracleDepthPipeline(unet, vae, DDIMSchedulerOracle(), text, 2, 128)
     ref, unc, _ = ora(img, ensemble_size=3, noise=z0, batch_size=2, ensemble_kwargs=dict(output_uncertainty=True))
-    assert out.depth_np.shape == (128, 256) and out.uncertainty.shape == (128, 256)
+    assert out.depth_np.shape == (128, 256)
+    assert out.uncertainty.shape == (64, 128)      # like the reference, the uncertainty map is NOT resized back (:317-318)
     assert out.depth_np.min() >= 0 and out.depth_np.max() <= 1
     assert np.abs(out.depth_np - ref).mean() < 3e-2              # BFGS path is rounding-chaotic (see test_ensemble_gpu)
 
