@@ -133,6 +133,74 @@ __device__ __forceinline__ void epilogue_special(const GemmEpilogue& e, const Ro
 }
 
 // -------------------------------------------------------------------------------------------------
+// Coalesced chunk store. After tcgen05.ld a lane holds ONE row x 32 columns; stored directly, every warp
+// instruction would touch 32 different 128-byte lines with 16 bytes each (measured: <1 TB/s of output).
+// The 32 x 32 fp32 chunk is transposed through a per-warp smem scratch (pitch 36 floats: conflict-free for
+// 128-bit accesses) so that 8 lanes cover one row's 128 contiguous bytes and a warp instruction writes four
+// full lines. Residual loads use the same mapping.
+// -------------------------------------------------------------------------------------------------
+constexpr int kEpiPitch = 36;
+
+struct TileGeom {
+  int mode;
+  long long m_base;
+  int M;
+  int img, ty, tx, H, W, tile_w, tile_h;
+};
+
+__device__ __forceinline__ bool tile_row_index(const TileGeom& g, int row, long long* m) {
+  if (g.mode == 0) {
+    *m = g.m_base + row;
+    return *m < g.M;
+  }
+  const int hh = row / g.tile_w, ww = row - hh * g.tile_w;
+  const int h = g.ty * g.tile_h + hh, w = g.tx * g.tile_w + ww;
+  *m = ((long long)g.img * g.H + h) * g.W + w;
+  return (h < g.H) && (w < g.W);
+}
+
+__device__ __forceinline__ void store_chunk(const TileGeom& g, float* scratch, int q, int lane, const float (&v)[32],
+                                            float* out_f32, bf16* out_bf16, const float* residual, int ldo, int col0,
+                                            int n_valid) {
+  float4* srow = reinterpret_cast<float4*>(scratch + lane * kEpiPitch);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) srow[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+  __syncwarp();
+  const int sub = lane >> 3, c4 = (lane & 7) * 4;
+  const int nv = n_valid - c4;                     // valid columns starting at this lane's first column
+  const bool vec_ok = ((ldo & 3) == 0) && ((col0 & 3) == 0) && nv >= 4;
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const int R = it * 4 + sub;
+    long long m;
+    const bool valid = tile_row_index(g, q * 32 + R, &m);
+    float4 x = *reinterpret_cast<const float4*>(scratch + R * kEpiPitch + c4);
+    if (!valid || nv <= 0) continue;
+    const long long o = m * (long long)ldo + col0 + c4;
+    if (vec_ok) {
+      if (residual) {
+        const float4 r = __ldg(reinterpret_cast<const float4*>(residual + o));
+        x.x += r.x; x.y += r.y; x.z += r.z; x.w += r.w;
+      }
+      if (out_f32) *reinterpret_cast<float4*>(out_f32 + o) = x;
+      if (out_bf16) *reinterpret_cast<uint2*>(out_bf16 + o) = make_uint2(pack_bf16x2(x.x, x.y), pack_bf16x2(x.z, x.w));
+    } else {
+      const float xs[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (k < nv) {
+          float a = xs[k];
+          if (residual) a += __ldg(residual + o + k);
+          if (out_f32) out_f32[o + k] = a;
+          if (out_bf16) out_bf16[o + k] = __float2bfloat16(a);
+        }
+      }
+    }
+  }
+  __syncwarp();
+}
+
+// -------------------------------------------------------------------------------------------------
 // The kernel
 // -------------------------------------------------------------------------------------------------
 template <int BLOCK_N>
@@ -237,62 +305,56 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
     // ===================== epilogue =====================
     const int q = warp & 3;  // TMEM lane quarter this warp may access
     const int row = q * 32 + lane;
-    RowCtx rc;
-    if (p.mode == 0) {
-      rc.m = (long long)m_tile * BLOCK_M + row;
-      rc.valid = rc.m < p.M;
-    } else {
-      const int hh = row / p.tile_w, ww = row - hh * p.tile_w;
-      const int h = ty * p.tile_h + hh, w = tx * p.tile_w + ww;
-      rc.valid = (h < p.H) && (w < p.W);
-      rc.m = ((long long)img * p.H + h) * p.W + w;
-    }
+    TileGeom tg;
+    tg.mode = p.mode; tg.m_base = (long long)m_tile * BLOCK_M; tg.M = p.M;
+    tg.img = img; tg.ty = ty; tg.tx = tx; tg.H = p.H; tg.W = p.W; tg.tile_w = p.tile_w; tg.tile_h = p.tile_h;
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
+    // the operand pipeline is drained (every issued stage was consumed): its smem is the transpose scratch
+    float* scratch = reinterpret_cast<float*>(smem_a) + (warp - 2) * (32 * kEpiPitch);
     const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16);
     const GemmEpilogue& e = p.epi;
     const int n0 = n_tile * BLOCK_N;
 
-    if (p.partial != nullptr) {
-      // split-K: raw accumulators to the workspace, epilogue deferred
-      float* dst = p.partial + ((long long)split * p.M + rc.m) * p.N + n0;
-      if constexpr (BLOCK_N >= 32) {
-#pragma unroll 1
-        for (int j = 0; j < BLOCK_N / 32; ++j) {
-          uint32_t r[32];
-          tmem_ld32(taddr + j * 32, r);
-          tmem_wait_ld();
-          if (rc.valid) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (n0 + j * 32 + i < p.N) dst[j * 32 + i] = __uint_as_float(r[i]);
-          }
-        }
-      } else {
-        uint32_t r[16];
-        tmem_ld16(taddr, r);
-        tmem_wait_ld();
+    if constexpr (BLOCK_N == 16) {
+      RowCtx rc;
+      rc.valid = tile_row_index(tg, row, &rc.m);
+      uint32_t r[16];
+      tmem_ld16(taddr, r);
+      tmem_wait_ld();
+      if (p.partial != nullptr) {
+        float* dst = p.partial + ((long long)split * p.M + rc.m) * p.N + n0;
         if (rc.valid) {
 #pragma unroll
           for (int i = 0; i < 16; ++i)
             if (n0 + i < p.N) dst[i] = __uint_as_float(r[i]);
         }
-      }
-    } else if constexpr (BLOCK_N == 16) {
-      uint32_t r[16];
-      tmem_ld16(taddr, r);
-      tmem_wait_ld();
-      float v[16];
-#pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        v[i] = __uint_as_float(r[i]);
-        if (e.flags & EPI_SCALE) v[i] *= e.scale;
-        if (e.bias && (n0 + i) < p.N) v[i] += __ldg(e.bias + n0 + i);
-      }
-      if (e.flags & (EPI_SCHED | EPI_DEPTH | EPI_NORMALS | EPI_NCHW)) {
-        epilogue_special(e, rc, v, p.N);
       } else {
-        epilogue_chunk<16>(e, rc, v, n0, p.N - n0);
+        float v[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          v[i] = __uint_as_float(r[i]);
+          if (e.flags & EPI_SCALE) v[i] *= e.scale;
+          if (e.bias && (n0 + i) < p.N) v[i] += __ldg(e.bias + n0 + i);
+        }
+        if (e.flags & (EPI_SCHED | EPI_DEPTH | EPI_NORMALS | EPI_NCHW)) {
+          epilogue_special(e, rc, v, p.N);
+        } else {
+          epilogue_chunk<16>(e, rc, v, n0, p.N - n0);
+        }
+      }
+    } else if (p.partial != nullptr) {
+      // split-K: raw accumulators to the workspace (coalesced), epilogue deferred
+      float* dst = p.partial + (long long)split * p.M * p.N;
+#pragma unroll 1
+      for (int j = 0; j < BLOCK_N / 32; ++j) {
+        uint32_t r[32];
+        tmem_ld32(taddr + j * 32, r);
+        tmem_wait_ld();
+        float v[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+        store_chunk(tg, scratch, q, lane, v, dst, nullptr, nullptr, p.N, n0 + j * 32, p.N - (n0 + j * 32));
       }
     } else if (e.flags & EPI_GEGLU) {
       // tile = [BLOCK_N/2 value columns | BLOCK_N/2 gate columns]
@@ -312,28 +374,26 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
             v[i] = val * gelu_erf_f(gate);
           }
           const int col0 = n_tile * HALF + j * 32;
-          epilogue_chunk<32>(e, rc, v, col0, p.N / 2 - col0);
+          store_chunk(tg, scratch, q, lane, v, e.out_f32, e.out_bf16, e.residual, e.ldo, col0, p.N / 2 - col0);
         }
       }
     } else {
-      if constexpr (BLOCK_N >= 32) {
 #pragma unroll 1
-        for (int j = 0; j < BLOCK_N / 32; ++j) {
-          uint32_t r[32];
-          tmem_ld32(taddr + j * 32, r);
-          tmem_wait_ld();
-          float v[32];
-          const int col0 = n0 + j * 32;
+      for (int j = 0; j < BLOCK_N / 32; ++j) {
+        uint32_t r[32];
+        tmem_ld32(taddr + j * 32, r);
+        tmem_wait_ld();
+        float v[32];
+        const int col0 = n0 + j * 32;
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            float a = __uint_as_float(r[i]);
-            if (e.flags & EPI_SCALE) a *= e.scale;
-            if (e.bias && (col0 + i) < p.N) a += __ldg(e.bias + col0 + i);
-            if (e.flags & EPI_SILU) a = silu_f(a);
-            v[i] = a;
-          }
-          epilogue_chunk<32>(e, rc, v, col0, p.N - col0);
+        for (int i = 0; i < 32; ++i) {
+          float a = __uint_as_float(r[i]);
+          if (e.flags & EPI_SCALE) a *= e.scale;
+          if (e.bias && (col0 + i) < p.N) a += __ldg(e.bias + col0 + i);
+          if (e.flags & EPI_SILU) a = silu_f(a);
+          v[i] = a;
         }
+        store_chunk(tg, scratch, q, lane, v, e.out_f32, e.out_bf16, e.residual, e.ldo, col0, p.N - col0);
       }
     }
     tc_fence_before();
