@@ -67,17 +67,29 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   return ok != 0;
 }
 // Bounded wait: a protocol bug must trap (launch error surfaced to the host) instead of hanging
-// the GPU. ~2^31 cycles ≈ 1 s at 1.9 GHz.
+// the GPU. ~2^31 cycles ~ 1 s at 1.9 GHz. The report is out of line to keep hot code small.
+static __device__ __noinline__ void mbar_timeout_trap(uint32_t bar, uint32_t parity) {
+  printf("mgb: mbarrier timeout block=(%d,%d,%d) thread=%d bar=%u parity=%u\n", blockIdx.x, blockIdx.y, blockIdx.z,
+         threadIdx.x, bar, parity);
+  __trap();
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > (1ll << 31)) {
-      printf("mgb: mbarrier timeout block=(%d,%d,%d) thread=%d bar=%u parity=%u\n", blockIdx.x, blockIdx.y,
-             blockIdx.z, threadIdx.x, smem_u32(bar), parity);
-      __trap();
-    }
+    if (clock64() - t0 > (1ll << 31)) mbar_timeout_trap(smem_u32(bar), parity);
   }
+}
+
+// explicit shared-space 128-bit accesses (pointer arithmetic on the aligned dynamic-smem base decays to
+// generic addressing otherwise)
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+  return v;
 }
 
 // generic-proxy smem writes -> visible to the async proxy (UMMA / TMA reads)

@@ -133,19 +133,21 @@ __device__ __forceinline__ void epilogue_special(const GemmEpilogue& e, const Ro
 }
 
 // -------------------------------------------------------------------------------------------------
-// Coalesced chunk store. After tcgen05.ld a lane holds ONE row x 32 columns; stored directly, every warp
-// instruction would touch 32 different 128-byte lines with 16 bytes each (measured: <1 TB/s of output).
-// The 32 x 32 fp32 chunk is transposed through a per-warp smem scratch (pitch 36 floats: conflict-free for
-// 128-bit accesses) so that 8 lanes cover one row's 128 contiguous bytes and a warp instruction writes four
-// full lines. Residual loads use the same mapping.
+// Coalesced epilogue. After tcgen05.ld a lane holds ONE row x 32 columns. The 32 x 32 fp32 chunk is
+// transposed through a per-warp smem scratch (pitch 36 floats: conflict-free for 128-bit accesses) so that
+// 8 lanes cover one row's 128 contiguous bytes and a warp instruction moves four full lines; bias,
+// activation, residual and the casts are applied AFTER the transpose, where a lane owns 4 fixed columns.
+// The code is deliberately rolled and small: it runs once per CTA, i.e. always from a cold instruction
+// cache (the first, unrolled version was 60 KB of SASS and spent ~20k cycles per CTA fetching itself).
 // -------------------------------------------------------------------------------------------------
 constexpr int kEpiPitch = 36;
+constexpr int kEpiPitchB = kEpiPitch * 4;
 
 struct TileGeom {
   int mode;
   long long m_base;
   int M;
-  int img, ty, tx, H, W, tile_w, tile_h;
+  int img, ty, tx, H, W, tile_w_shift, tile_w_mask, tile_h;
 };
 
 __device__ __forceinline__ bool tile_row_index(const TileGeom& g, int row, long long* m) {
@@ -153,51 +155,28 @@ __device__ __forceinline__ bool tile_row_index(const TileGeom& g, int row, long 
     *m = g.m_base + row;
     return *m < g.M;
   }
-  const int hh = row / g.tile_w, ww = row - hh * g.tile_w;
-  const int h = g.ty * g.tile_h + hh, w = g.tx * g.tile_w + ww;
+  const int hh = row >> g.tile_w_shift, ww = row & g.tile_w_mask;
+  const int h = g.ty * g.tile_h + hh, w = (g.tx << g.tile_w_shift) + ww;
   *m = ((long long)g.img * g.H + h) * g.W + w;
   return (h < g.H) && (w < g.W);
 }
 
-__device__ __forceinline__ void store_chunk(const TileGeom& g, float* scratch, int q, int lane, const float (&v)[32],
-                                            float* out_f32, bf16* out_bf16, const float* residual, int ldo, int col0,
-                                            int n_valid) {
-  float4* srow = reinterpret_cast<float4*>(scratch + lane * kEpiPitch);
-#pragma unroll
-  for (int i = 0; i < 8; ++i) srow[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-  __syncwarp();
-  const int sub = lane >> 3, c4 = (lane & 7) * 4;
-  const int nv = n_valid - c4;                     // valid columns starting at this lane's first column
-  const bool vec_ok = ((ldo & 3) == 0) && ((col0 & 3) == 0) && nv >= 4;
-#pragma unroll
-  for (int it = 0; it < 8; ++it) {
-    const int R = it * 4 + sub;
-    long long m;
-    const bool valid = tile_row_index(g, q * 32 + R, &m);
-    float4 x = *reinterpret_cast<const float4*>(scratch + R * kEpiPitch + c4);
-    if (!valid || nv <= 0) continue;
-    const long long o = m * (long long)ldo + col0 + c4;
-    if (vec_ok) {
-      if (residual) {
-        const float4 r = __ldg(reinterpret_cast<const float4*>(residual + o));
-        x.x += r.x; x.y += r.y; x.z += r.z; x.w += r.w;
-      }
-      if (out_f32) *reinterpret_cast<float4*>(out_f32 + o) = x;
-      if (out_bf16) *reinterpret_cast<uint2*>(out_bf16 + o) = make_uint2(pack_bf16x2(x.x, x.y), pack_bf16x2(x.z, x.w));
-    } else {
-      const float xs[4] = {x.x, x.y, x.z, x.w};
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        if (k < nv) {
-          float a = xs[k];
-          if (residual) a += __ldg(residual + o + k);
-          if (out_f32) out_f32[o + k] = a;
-          if (out_bf16) out_bf16[o + k] = __float2bfloat16(a);
-        }
-      }
-    }
+// Unaligned / ragged tail: rare, kept out of line.
+static __device__ __noinline__ void store_tail(float4 x, int nv, const float* residual, float* out_f32, bf16* out_bf16,
+                                        long long o) {
+  const float xs[4] = {x.x, x.y, x.z, x.w};
+  for (int k = 0; k < 4 && k < nv; ++k) {
+    float a = xs[k];
+    if (residual) a += __ldg(residual + o + k);
+    if (out_f32) out_f32[o + k] = a;
+    if (out_bf16) out_bf16[o + k] = __float2bfloat16(a);
   }
-  __syncwarp();
+}
+
+// Row-owner phase: 32 accumulator columns of this lane's row -> scratch row `lane`.
+__device__ __forceinline__ void scratch_put(uint32_t s_wr, const uint32_t (&r)[32]) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) sts128(s_wr + i * 16, r[4 * i], r[4 * i + 1], r[4 * i + 2], r[4 * i + 3]);
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -206,6 +185,7 @@ __device__ __forceinline__ void store_chunk(const TileGeom& g, float* scratch, i
 template <int BLOCK_N>
 __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_constant__ GemmParams p) {
   pdl_launch_dependents();
+  const long long t_entry = clock64();
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B tiles need 1024 B alignment
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -238,6 +218,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tmap_a);
     tma_prefetch_desc(&p.tmap_b);
+#pragma unroll 1
     for (int s = 0; s < stages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -256,6 +237,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
   const uint32_t tmem_base = *tmem_ptr_smem;
   // everything above overlapped the previous kernel's tail; operands / residuals are read below
   pdl_wait();
+  long long* dbg = p.dbg ? p.dbg + ((size_t(blockIdx.z) * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 8 : nullptr;
+  if (dbg && threadIdx.x == 0) { dbg[0] = t_entry; dbg[1] = clock64(); }
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -287,6 +270,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
     for (int kb = kb0; kb < kb1; ++kb) {
       mbar_wait(&full_bar[stage], phase);
       tc_fence_after();
+      if (dbg && kb == kb0 && lane == 0) dbg[2] = clock64();
       if (elect_one()) {
         const uint64_t da = umma_desc_sw128(smem_u32(smem_a + size_t(stage) * kABytes));
         const uint64_t db = umma_desc_sw128(smem_u32(smem_b + size_t(stage) * kBBytes));
@@ -307,11 +291,11 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
     const int row = q * 32 + lane;
     TileGeom tg;
     tg.mode = p.mode; tg.m_base = (long long)m_tile * BLOCK_M; tg.M = p.M;
-    tg.img = img; tg.ty = ty; tg.tx = tx; tg.H = p.H; tg.W = p.W; tg.tile_w = p.tile_w; tg.tile_h = p.tile_h;
+    tg.img = img; tg.ty = ty; tg.tx = tx; tg.H = p.H; tg.W = p.W;
+    tg.tile_w_shift = p.tile_w_shift; tg.tile_w_mask = p.tile_w - 1; tg.tile_h = p.tile_h;
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
-    // the operand pipeline is drained (every issued stage was consumed): its smem is the transpose scratch
-    float* scratch = reinterpret_cast<float*>(smem_a) + (warp - 2) * (32 * kEpiPitch);
+    if (dbg && threadIdx.x == 64) dbg[3] = clock64();
     const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16);
     const GemmEpilogue& e = p.epi;
     const int n0 = n_tile * BLOCK_N;
@@ -343,59 +327,84 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
           epilogue_chunk<16>(e, rc, v, n0, p.N - n0);
         }
       }
-    } else if (p.partial != nullptr) {
-      // split-K: raw accumulators to the workspace (coalesced), epilogue deferred
-      float* dst = p.partial + (long long)split * p.M * p.N;
-#pragma unroll 1
-      for (int j = 0; j < BLOCK_N / 32; ++j) {
-        uint32_t r[32];
-        tmem_ld32(taddr + j * 32, r);
-        tmem_wait_ld();
-        float v[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-        store_chunk(tg, scratch, q, lane, v, dst, nullptr, nullptr, p.N, n0 + j * 32, p.N - (n0 + j * 32));
-      }
-    } else if (e.flags & EPI_GEGLU) {
-      // tile = [BLOCK_N/2 value columns | BLOCK_N/2 gate columns]
-      if constexpr (BLOCK_N % 64 == 0) {
-        constexpr int HALF = BLOCK_N / 2;
-#pragma unroll 1
-        for (int j = 0; j < HALF / 32; ++j) {
-          uint32_t rv[32], rg[32];
-          tmem_ld32(taddr + j * 32, rv);
-          tmem_ld32(taddr + HALF + j * 32, rg);
-          tmem_wait_ld();
-          float v[32];
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            float val = __uint_as_float(rv[i]) + __ldg(e.bias + n0 + j * 32 + i);
-            float gate = __uint_as_float(rg[i]) + __ldg(e.bias + n0 + HALF + j * 32 + i);
-            v[i] = val * gelu_erf_f(gate);
-          }
-          const int col0 = n_tile * HALF + j * 32;
-          store_chunk(tg, scratch, q, lane, v, e.out_f32, e.out_bf16, e.residual, e.ldo, col0, p.N / 2 - col0);
-        }
-      }
     } else {
+      // the operand pipeline is drained (every issued stage was consumed): its smem is the transpose
+      // scratch, two 32 x 36 fp32 tiles per warp (the second one only for GEGLU's gate chunk)
+      const uint32_t s_base = smem_u32(smem_a) + (warp - 2) * (2 * 32 * kEpiPitchB);
+      const uint32_t s_wr = s_base + lane * kEpiPitchB;
+      const int sub = lane >> 3, c4 = (lane & 7) * 4;
+      const uint32_t s_rd = s_base + sub * kEpiPitchB + c4 * 4;
+      const bool raw = p.partial != nullptr;                 // split-K: raw accumulators, epilogue deferred
+      const bool geglu = !raw && (e.flags & EPI_GEGLU);
+      float* out_f32 = raw ? p.partial + (long long)split * p.M * p.N : e.out_f32;
+      bf16* out_bf16 = raw ? nullptr : e.out_bf16;
+      const float* residual = raw ? nullptr : e.residual;
+      const float* bias = raw ? nullptr : e.bias;
+      const int ldo = raw ? p.N : e.ldo;
+      const int n_out = geglu ? p.N / 2 : p.N;               // output columns
+      const int half = BLOCK_N / 2;
+      const int chunks = geglu ? half / 32 : BLOCK_N / 32;
+      const float scale = (!raw && (e.flags & EPI_SCALE)) ? e.scale : 1.0f;
+      const bool silu = !raw && (e.flags & EPI_SILU);
+      const bool ld_vec = (ldo & 3) == 0;
 #pragma unroll 1
-      for (int j = 0; j < BLOCK_N / 32; ++j) {
-        uint32_t r[32];
-        tmem_ld32(taddr + j * 32, r);
-        tmem_wait_ld();
-        float v[32];
-        const int col0 = n0 + j * 32;
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          float a = __uint_as_float(r[i]);
-          if (e.flags & EPI_SCALE) a *= e.scale;
-          if (e.bias && (col0 + i) < p.N) a += __ldg(e.bias + col0 + i);
-          if (e.flags & EPI_SILU) a = silu_f(a);
-          v[i] = a;
+      for (int j = 0; j < chunks; ++j) {
+        {
+          uint32_t r[32];
+          tmem_ld32(taddr + j * 32, r);
+          tmem_wait_ld();
+          scratch_put(s_wr, r);
+          if (geglu) {
+            tmem_ld32(taddr + half + j * 32, r);
+            tmem_wait_ld();
+            scratch_put(s_wr + 32 * kEpiPitchB, r);
+          }
         }
-        store_chunk(tg, scratch, q, lane, v, e.out_f32, e.out_bf16, e.residual, e.ldo, col0, p.N - col0);
+        __syncwarp();
+        const int acc_col = n0 + j * 32 + c4;                                   // accumulator column (bias index)
+        const int col = geglu ? n_tile * half + j * 32 + c4 : acc_col;          // output column
+        const int nv = n_out - col;
+        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f), g4 = b4;
+        if (bias && nv >= 4) {
+          b4 = __ldg(reinterpret_cast<const float4*>(bias + acc_col));
+          if (geglu) g4 = __ldg(reinterpret_cast<const float4*>(bias + acc_col + half));
+        } else if (bias && nv > 0) {
+          b4.x = __ldg(bias + acc_col);
+          if (nv > 1) b4.y = __ldg(bias + acc_col + 1);
+          if (nv > 2) b4.z = __ldg(bias + acc_col + 2);
+        }
+#pragma unroll 1
+        for (int it = 0; it < 8; ++it) {
+          long long m;
+          const bool valid = tile_row_index(tg, q * 32 + it * 4 + sub, &m);
+          float4 x = lds128(s_rd + it * (4 * kEpiPitchB));
+          if (geglu) {
+            const float4 g = lds128(s_rd + 32 * kEpiPitchB + it * (4 * kEpiPitchB));
+            x.x = (x.x + b4.x) * gelu_erf_f(g.x + g4.x); x.y = (x.y + b4.y) * gelu_erf_f(g.y + g4.y);
+            x.z = (x.z + b4.z) * gelu_erf_f(g.z + g4.z); x.w = (x.w + b4.w) * gelu_erf_f(g.w + g4.w);
+          } else {
+            x.x = fmaf(x.x, scale, b4.x); x.y = fmaf(x.y, scale, b4.y);
+            x.z = fmaf(x.z, scale, b4.z); x.w = fmaf(x.w, scale, b4.w);
+            if (silu) { x.x = silu_f(x.x); x.y = silu_f(x.y); x.z = silu_f(x.z); x.w = silu_f(x.w); }
+          }
+          if (!valid || nv <= 0) continue;
+          const long long o = m * (long long)ldo + col;
+          if (ld_vec && nv >= 4) {
+            if (residual) {
+              const float4 rr = __ldg(reinterpret_cast<const float4*>(residual + o));
+              x.x += rr.x; x.y += rr.y; x.z += rr.z; x.w += rr.w;
+            }
+            if (out_f32) *reinterpret_cast<float4*>(out_f32 + o) = x;
+            if (out_bf16)
+              *reinterpret_cast<uint2*>(out_bf16 + o) = make_uint2(pack_bf16x2(x.x, x.y), pack_bf16x2(x.z, x.w));
+          } else {
+            store_tail(x, nv, residual, out_f32, out_bf16, o);
+          }
+        }
+        __syncwarp();
       }
     }
+    if (dbg && threadIdx.x == 64) dbg[4] = clock64();
     tc_fence_before();
   }
 
@@ -404,6 +413,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
     tc_fence_after();
     tmem_dealloc(tmem_base, kTmemCols);
   }
+  if (dbg && threadIdx.x == 0) dbg[5] = clock64();
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -482,8 +492,13 @@ __global__ void splitk_epilogue_kernel(const GemmParams p, int splits, int geglu
 // -------------------------------------------------------------------------------------------------
 // host side
 // -------------------------------------------------------------------------------------------------
+static long long* g_gemm_dbg = nullptr;
+void set_gemm_debug_buffer(long long* dev_ptr) { g_gemm_dbg = dev_ptr; }
+
 template <int BN>
-static int launch_one(const GemmParams& p, int splits, cudaStream_t stream) {
+static int launch_one(const GemmParams& p_in, int splits, cudaStream_t stream) {
+  GemmParams p = p_in;
+  p.dbg = g_gemm_dbg;
   const size_t smem = gemm_smem_bytes(BN, p.stages);
   static bool attr_set = false;  // per template instantiation
   if (!attr_set) {

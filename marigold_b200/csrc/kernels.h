@@ -55,17 +55,20 @@ struct GemmParams {
   int stages;          // smem pipeline depth
   // conv geometry (mode 1)
   int H, W;            // OUTPUT image size
-  int tile_w, tile_h;  // tile_w * tile_h == 128
+  int tile_w, tile_h;  // tile_w * tile_h == 128, tile_w a power of two
+  int tile_w_shift;    // log2(tile_w)
   int tiles_x, tiles_y;
   int cblocks;         // Cin / 64
   int ntaps;
   int8_t tap_p[12], tap_dy[12], tap_dx[12];
   float* partial;      // split-K: fp32 [splits, M, N] raw accumulators (epilogue deferred)
+  long long* dbg;      // optional per-CTA phase timestamps [ctas][8] (tools/gemm_phases.py), else nullptr
   GemmEpilogue epi;
 };
 
 // Launch. block_n in {16, 32, 64, 128, 160, 256}. Returns cudaError_t as int.
 int launch_gemm_tc(const GemmParams& p, int block_n, int splits, cudaStream_t stream);
+void set_gemm_debug_buffer(long long* dev_ptr);  // debug hook: phase timestamps of subsequent launches
 // Deferred epilogue for split-K: sums `splits` partials and applies p.epi.
 int launch_splitk_epilogue(const GemmParams& p, int block_n, int splits, cudaStream_t stream);
 size_t gemm_smem_bytes(int block_n, int stages);

@@ -57,6 +57,8 @@ int fill_conv_params(GemmParams* p, const bf16* x, const bf16* w, int NB, int Ho
   p->N = Cout;
   p->H = Hout; p->W = Wout;
   conv_tile_shape(Hout, Wout, &p->tile_w, &p->tile_h);
+  p->tile_w_shift = 0;
+  while ((1 << p->tile_w_shift) < p->tile_w) ++p->tile_w_shift;
   p->tiles_x = (Wout + p->tile_w - 1) / p->tile_w;
   p->tiles_y = (Hout + p->tile_h - 1) / p->tile_h;
   p->cblocks = Cin / 64;
