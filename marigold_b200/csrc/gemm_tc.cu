@@ -347,8 +347,20 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
       const float scale = (!raw && (e.flags & EPI_SCALE)) ? e.scale : 1.0f;
       const bool silu = !raw && (e.flags & EPI_SILU);
       const bool ld_vec = (ldo & 3) == 0;
+      // row addressing hoisted out of the chunk loop: after the transpose this lane stores rows
+      // R = it * 4 + (lane >> 3), it = 0..7, of its warp's 32-row slab
+      long long off[8];
+      uint32_t vmask = 0;
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        long long m;
+        const bool ok = tile_row_index(tg, q * 32 + it * 4 + sub, &m);
+        off[it] = m * (long long)ldo;
+        vmask |= uint32_t(ok) << it;
+      }
 #pragma unroll 1
       for (int j = 0; j < chunks; ++j) {
+        const long long c0 = (dbg && j < 2) ? clock64() : 0;
         {
           uint32_t r[32];
           tmem_ld32(taddr + j * 32, r);
@@ -361,6 +373,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
           }
         }
         __syncwarp();
+        const long long c1 = (dbg && j < 2) ? clock64() : 0;
         const int acc_col = n0 + j * 32 + c4;                                   // accumulator column (bias index)
         const int col = geglu ? n_tile * half + j * 32 + c4 : acc_col;          // output column
         const int nv = n_out - col;
@@ -373,35 +386,58 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
           if (nv > 1) b4.y = __ldg(bias + acc_col + 1);
           if (nv > 2) b4.z = __ldg(bias + acc_col + 2);
         }
-#pragma unroll 1
-        for (int it = 0; it < 8; ++it) {
-          long long m;
-          const bool valid = tile_row_index(tg, q * 32 + it * 4 + sub, &m);
-          float4 x = lds128(s_rd + it * (4 * kEpiPitchB));
-          if (geglu) {
-            const float4 g = lds128(s_rd + 32 * kEpiPitchB + it * (4 * kEpiPitchB));
-            x.x = (x.x + b4.x) * gelu_erf_f(g.x + g4.x); x.y = (x.y + b4.y) * gelu_erf_f(g.y + g4.y);
-            x.z = (x.z + b4.z) * gelu_erf_f(g.z + g4.z); x.w = (x.w + b4.w) * gelu_erf_f(g.w + g4.w);
-          } else {
+        const bool vec = ld_vec && nv >= 4;
+        if (!geglu && !silu && vec) {
+          // fast path, tiny body fully unrolled: 8 independent LDS -> FMA -> (residual) -> store chains
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            float4 x = lds128(s_rd + it * (4 * kEpiPitchB));
             x.x = fmaf(x.x, scale, b4.x); x.y = fmaf(x.y, scale, b4.y);
             x.z = fmaf(x.z, scale, b4.z); x.w = fmaf(x.w, scale, b4.w);
-            if (silu) { x.x = silu_f(x.x); x.y = silu_f(x.y); x.z = silu_f(x.z); x.w = silu_f(x.w); }
-          }
-          if (!valid || nv <= 0) continue;
-          const long long o = m * (long long)ldo + col;
-          if (ld_vec && nv >= 4) {
-            if (residual) {
-              const float4 rr = __ldg(reinterpret_cast<const float4*>(residual + o));
-              x.x += rr.x; x.y += rr.y; x.z += rr.z; x.w += rr.w;
+            if ((vmask >> it) & 1u) {
+              const long long o = off[it] + col;
+              if (residual) {
+                const float4 rr = __ldg(reinterpret_cast<const float4*>(residual + o));
+                x.x += rr.x; x.y += rr.y; x.z += rr.z; x.w += rr.w;
+              }
+              if (out_f32) *reinterpret_cast<float4*>(out_f32 + o) = x;
+              if (out_bf16)
+                *reinterpret_cast<uint2*>(out_bf16 + o) = make_uint2(pack_bf16x2(x.x, x.y), pack_bf16x2(x.z, x.w));
             }
-            if (out_f32) *reinterpret_cast<float4*>(out_f32 + o) = x;
-            if (out_bf16)
-              *reinterpret_cast<uint2*>(out_bf16 + o) = make_uint2(pack_bf16x2(x.x, x.y), pack_bf16x2(x.z, x.w));
-          } else {
-            store_tail(x, nv, residual, out_f32, out_bf16, o);
+          }
+        } else {
+          // general path (GEGLU's erf polynomial, SiLU, ragged / unaligned tails): rolled to stay small
+#pragma unroll 1
+          for (int it = 0; it < 8; ++it) {
+            long long m;
+            const bool valid = tile_row_index(tg, q * 32 + it * 4 + sub, &m);
+            float4 x = lds128(s_rd + it * (4 * kEpiPitchB));
+            if (geglu) {
+              const float4 g = lds128(s_rd + 32 * kEpiPitchB + it * (4 * kEpiPitchB));
+              x.x = (x.x + b4.x) * gelu_erf_f(g.x + g4.x); x.y = (x.y + b4.y) * gelu_erf_f(g.y + g4.y);
+              x.z = (x.z + b4.z) * gelu_erf_f(g.z + g4.z); x.w = (x.w + b4.w) * gelu_erf_f(g.w + g4.w);
+            } else {
+              x.x = fmaf(x.x, scale, b4.x); x.y = fmaf(x.y, scale, b4.y);
+              x.z = fmaf(x.z, scale, b4.z); x.w = fmaf(x.w, scale, b4.w);
+              if (silu) { x.x = silu_f(x.x); x.y = silu_f(x.y); x.z = silu_f(x.z); x.w = silu_f(x.w); }
+            }
+            if (!valid || nv <= 0) continue;
+            const long long o = m * (long long)ldo + col;
+            if (vec) {
+              if (residual) {
+                const float4 rr = __ldg(reinterpret_cast<const float4*>(residual + o));
+                x.x += rr.x; x.y += rr.y; x.z += rr.z; x.w += rr.w;
+              }
+              if (out_f32) *reinterpret_cast<float4*>(out_f32 + o) = x;
+              if (out_bf16)
+                *reinterpret_cast<uint2*>(out_bf16 + o) = make_uint2(pack_bf16x2(x.x, x.y), pack_bf16x2(x.z, x.w));
+            } else {
+              store_tail(x, nv, residual, out_f32, out_bf16, o);
+            }
           }
         }
         __syncwarp();
+        if (dbg && j < 2 && threadIdx.x == 64) { dbg[6 + j] = ((c1 - c0) << 32) | (clock64() - c1); }
       }
     }
     if (dbg && threadIdx.x == 64) dbg[4] = clock64();

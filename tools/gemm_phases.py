@@ -38,16 +38,16 @@ def run(M, N, K, bn, stages, out_dtype="f32", flags=0):
     ph = {"prologue": (d[:, 1] - d[:, 0]), "first_stage": (d[:, 2] - d[:, 1]), "mainloop": (d[:, 3] - d[:, 2]),
           "epilogue": (d[:, 4] - d[:, 3]), "teardown": (d[:, 5] - d[:, 4]), "total": (d[:, 5] - d[:, 0])}
     s = " ".join(f"{k}={v.median().item():.0f}/{v.max().item():.0f}" for k, v in ph.items())
-    s += f" chunk1_ld={d[:,6].median().item():.0f} chunk1_store={d[:,7].median().item():.0f}"
+    di = dbg.cpu()
+    for j in (0, 1):
+        v = int(di[:, 6 + j].median().item())
+        s += f" chunk{j}[ld+sts={v >> 32} loop={v & 0xffffffff}]"
     print(f"M{M} N{N} K{K} bn{bn} st{stages} {out_dtype} flags={flags:#x}: event_us={e0.elapsed_time(e1)*1e3:.1f} ctas={ctas} cycles(median/max): {s}", flush=True)
 
 
 if __name__ == "__main__":
     run(128, 160, 64, 160, 2)
-    run(128, 160, 64, 160, 2, flags=1 << 20)
-    run(128, 160, 64, 160, 2, flags=1 << 21)
-    run(128, 160, 64, 160, 2, flags=(1 << 20) | (1 << 21))
     run(9216, 320, 320, 160, 5)
-    run(9216, 320, 320, 160, 5, flags=1 << 20)
-    run(9216, 320, 320, 160, 5, flags=1 << 21)
+    run(9216, 320, 320, 160, 5, "bf16")
     run(9216, 320, 2880, 160, 5)
+    run(9216, 2560, 320, 256, 4, "bf16")
