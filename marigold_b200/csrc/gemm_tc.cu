@@ -174,9 +174,10 @@ static __device__ __noinline__ void store_tail(float4 x, int nv, const float* re
 }
 
 // Row-owner phase: 32 accumulator columns of this lane's row -> scratch row `lane`.
-__device__ __forceinline__ void scratch_put(uint32_t s_wr, const uint32_t (&r)[32]) {
+__device__ __forceinline__ void scratch_put(float* s_wr, const uint32_t (&r)[32]) {
+  uint4* d = reinterpret_cast<uint4*>(s_wr);
 #pragma unroll
-  for (int i = 0; i < 8; ++i) sts128(s_wr + i * 16, r[4 * i], r[4 * i + 1], r[4 * i + 2], r[4 * i + 3]);
+  for (int i = 0; i < 8; ++i) d[i] = make_uint4(r[4 * i], r[4 * i + 1], r[4 * i + 2], r[4 * i + 3]);
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -188,7 +189,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
   const long long t_entry = clock64();
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B tiles need 1024 B alignment
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // pointer + integer keeps the shared address space (a uintptr_t round trip decays to generic ld/st)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int stages = p.stages;
   constexpr int kABytes = a_stage_bytes();
   constexpr int kBBytes = b_stage_bytes(BLOCK_N);
@@ -235,6 +237,15 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  // Weights never depend on a predecessor kernel: start streaming the first B tiles of the pipeline
+  // before waiting on it (the A operand and residuals are read only after pdl_wait()).
+  const int n_pre = min(stages, kb1 - kb0);
+  if (warp == 0 && elect_one()) {
+    for (int i = 0; i < n_pre; ++i) {
+      mbar_arrive_expect_tx(&full_bar[i], kABytes + kBBytes);
+      tma_load_2d(smem_b + size_t(i) * kBBytes, &p.tmap_b, &full_bar[i], (kb0 + i) * BLOCK_K, n_tile * BLOCK_N);
+    }
+  }
   // everything above overlapped the previous kernel's tail; operands / residuals are read below
   pdl_wait();
   long long* dbg = p.dbg ? p.dbg + ((size_t(blockIdx.z) * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 8 : nullptr;
@@ -247,9 +258,12 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
       uint32_t phase = 0;
       for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
-        mbar_arrive_expect_tx(&full_bar[stage], kABytes + kBBytes);
         void* sa = smem_a + size_t(stage) * kABytes;
         void* sb = smem_b + size_t(stage) * kBBytes;
+        if (kb - kb0 >= n_pre) {        // (the first n_pre weight tiles were issued before pdl_wait)
+          mbar_arrive_expect_tx(&full_bar[stage], kABytes + kBBytes);
+          tma_load_2d(sb, &p.tmap_b, &full_bar[stage], kb * BLOCK_K, n_tile * BLOCK_N);
+        }
         if (p.mode == 0) {
           tma_load_2d(sa, &p.tmap_a, &full_bar[stage], kb * BLOCK_K, m_tile * BLOCK_M);
         } else {
@@ -258,7 +272,6 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
           tma_load_5d(sa, &p.tmap_a, &full_bar[stage], cb * BLOCK_K, tx * p.tile_w + p.tap_dx[tap],
                       ty * p.tile_h + p.tap_dy[tap], p.tap_p[tap], img);
         }
-        tma_load_2d(sb, &p.tmap_b, &full_bar[stage], kb * BLOCK_K, n_tile * BLOCK_N);
         if (++stage == stages) { stage = 0; phase ^= 1; }
       }
     }
@@ -330,10 +343,10 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
     } else {
       // the operand pipeline is drained (every issued stage was consumed): its smem is the transpose
       // scratch, two 32 x 36 fp32 tiles per warp (the second one only for GEGLU's gate chunk)
-      const uint32_t s_base = smem_u32(smem_a) + (warp - 2) * (2 * 32 * kEpiPitchB);
-      const uint32_t s_wr = s_base + lane * kEpiPitchB;
+      float* s_base = reinterpret_cast<float*>(smem_a) + (warp - 2) * (2 * 32 * kEpiPitch);
+      float* s_wr = s_base + lane * kEpiPitch;
       const int sub = lane >> 3, c4 = (lane & 7) * 4;
-      const uint32_t s_rd = s_base + sub * kEpiPitchB + c4 * 4;
+      const float* s_rd = s_base + sub * kEpiPitch + c4;
       const bool raw = p.partial != nullptr;                 // split-K: raw accumulators, epilogue deferred
       const bool geglu = !raw && (e.flags & EPI_GEGLU);
       float* out_f32 = raw ? p.partial + (long long)split * p.M * p.N : e.out_f32;
@@ -369,7 +382,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
           if (geglu) {
             tmem_ld32(taddr + half + j * 32, r);
             tmem_wait_ld();
-            scratch_put(s_wr + 32 * kEpiPitchB, r);
+            scratch_put(s_wr + 32 * kEpiPitch, r);
           }
         }
         __syncwarp();
@@ -391,7 +404,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
           // fast path, tiny body fully unrolled: 8 independent LDS -> FMA -> (residual) -> store chains
 #pragma unroll
           for (int it = 0; it < 8; ++it) {
-            float4 x = lds128(s_rd + it * (4 * kEpiPitchB));
+            float4 x = *reinterpret_cast<const float4*>(s_rd + it * (4 * kEpiPitch));
             x.x = fmaf(x.x, scale, b4.x); x.y = fmaf(x.y, scale, b4.y);
             x.z = fmaf(x.z, scale, b4.z); x.w = fmaf(x.w, scale, b4.w);
             if ((vmask >> it) & 1u) {
@@ -411,9 +424,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
           for (int it = 0; it < 8; ++it) {
             long long m;
             const bool valid = tile_row_index(tg, q * 32 + it * 4 + sub, &m);
-            float4 x = lds128(s_rd + it * (4 * kEpiPitchB));
+            float4 x = *reinterpret_cast<const float4*>(s_rd + it * (4 * kEpiPitch));
             if (geglu) {
-              const float4 g = lds128(s_rd + 32 * kEpiPitchB + it * (4 * kEpiPitchB));
+              const float4 g = *reinterpret_cast<const float4*>(s_rd + 32 * kEpiPitch + it * (4 * kEpiPitch));
               x.x = (x.x + b4.x) * gelu_erf_f(g.x + g4.x); x.y = (x.y + b4.y) * gelu_erf_f(g.y + g4.y);
               x.z = (x.z + b4.z) * gelu_erf_f(g.z + g4.z); x.w = (x.w + b4.w) * gelu_erf_f(g.w + g4.w);
             } else {

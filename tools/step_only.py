@@ -1,0 +1,29 @@
+"""Run only UNet denoising steps of the full-size model (for ncu / timing): python tools/step_only.py [steps] [res]"""
+import sys
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parents[1]
+sys.path.insert(0, str(ROOT))
+import torch  # noqa: E402
+
+from marigold_b200.schedulers import DDIMScheduler  # noqa: E402
+from tests.helpers import engine_from_oracle, oracle_models  # noqa: E402
+
+steps = int(sys.argv[1]) if len(sys.argv) > 1 else 3
+res = int(sys.argv[2]) if len(sys.argv) > 2 else 768
+unet, vae, text = oracle_models("full")
+eng = engine_from_oracle(unet, vae, text)
+s = DDIMScheduler()
+s.set_timesteps(max(steps, 1))
+eng.set_schedule(s.timesteps, *s.coefficients())
+lh = res // 8
+rgb = torch.randn(1, 4, lh, lh, device="cuda")
+x = torch.randn(1, 4, lh, lh, device="cuda")
+torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+out = eng.denoise(rgb, x)
+e1.record()
+torch.cuda.synchronize()
+print(f"{steps} steps: {e0.elapsed_time(e1) / steps:.3f} ms/step, finite={bool(torch.isfinite(out).all())}")
+eng.close()
