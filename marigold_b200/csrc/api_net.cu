@@ -539,6 +539,7 @@ static int ensure_workspace(mgb_handle* h, int op, int NB, int d0, int d1) {
     if (h->gn_ws) CUDA_TRY(cudaFree(h->gn_ws));
     void* p = nullptr;
     CUDA_TRY(cudaMalloc(&p, gn_need));
+    CUDA_TRY(cudaMemset(p, 0, gn_need));   // arrival counters start at zero (and reset themselves)
     h->gn_ws = static_cast<float*>(p);
     h->gn_ws_bytes = gn_need;
   }

@@ -163,12 +163,24 @@ __global__ void __launch_bounds__(kAttnThreads, 2) flash_attn64_kernel(const __g
       tmem_ld32(tmem_base + lane_off + b * 64 + 32, r1);
       tmem_wait_ld();
       const int kv_valid = p.T - j * 64;   // >= 64 except possibly in the last block
-      float mx = -INFINITY;
+      if (kv_valid < 64) {                 // ragged tail (T % 64 != 0): mask once, then share the fast path
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        if (i < kv_valid) mx = fmaxf(mx, __uint_as_float(r0[i]));
-        if (32 + i < kv_valid) mx = fmaxf(mx, __uint_as_float(r1[i]));
+        for (int i = 0; i < 32; ++i) {
+          if (i >= kv_valid) r0[i] = 0xff800000u;        // -inf
+          if (32 + i >= kv_valid) r1[i] = 0xff800000u;
+        }
       }
+      // row max with 4 independent chains (one softmax warp per scheduler: dependent chains are the cost)
+      float mxa = __uint_as_float(r0[0]), mxb = __uint_as_float(r0[1]), mxc = __uint_as_float(r1[0]),
+            mxd = __uint_as_float(r1[1]);
+#pragma unroll
+      for (int i = 2; i < 32; i += 2) {
+        mxa = fmaxf(mxa, __uint_as_float(r0[i]));
+        mxb = fmaxf(mxb, __uint_as_float(r0[i + 1]));
+        mxc = fmaxf(mxc, __uint_as_float(r1[i]));
+        mxd = fmaxf(mxd, __uint_as_float(r1[i + 1]));
+      }
+      const float mx = fmaxf(fmaxf(mxa, mxb), fmaxf(mxc, mxd));
       const float m_blk = mx * p.scale_log2;
       if (j == 0) {
         m_ref = m_blk;
@@ -194,24 +206,21 @@ __global__ void __launch_bounds__(kAttnThreads, 2) flash_attn64_kernel(const __g
           tmem_wait_st();
         }
       }
-      // P = exp2(S * c - m_ref), masked; bf16; row sum of what the tensor core will multiply
+      // P = exp2(S * c - m_ref) (exp2(-inf) = 0 masks the tail); bf16 pairs; 4 partial row sums
       uint32_t pk[32];
-      float lsum = 0.f;
+      float ls0 = 0.f, ls1 = 0.f, ls2 = 0.f, ls3 = 0.f;
+      const float nm = -m_ref;
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
-        float a0 = ex2_approx(fmaf(__uint_as_float(r0[2 * i]), p.scale_log2, -m_ref));
-        float a1 = ex2_approx(fmaf(__uint_as_float(r0[2 * i + 1]), p.scale_log2, -m_ref));
-        float b0 = ex2_approx(fmaf(__uint_as_float(r1[2 * i]), p.scale_log2, -m_ref));
-        float b1 = ex2_approx(fmaf(__uint_as_float(r1[2 * i + 1]), p.scale_log2, -m_ref));
-        if (2 * i >= kv_valid) a0 = 0.f;
-        if (2 * i + 1 >= kv_valid) a1 = 0.f;
-        if (32 + 2 * i >= kv_valid) b0 = 0.f;
-        if (32 + 2 * i + 1 >= kv_valid) b1 = 0.f;
-        __nv_bfloat162 pa = __floats2bfloat162_rn(a0, a1), pb = __floats2bfloat162_rn(b0, b1);
-        lsum += (__bfloat162float(pa.x) + __bfloat162float(pa.y)) + (__bfloat162float(pb.x) + __bfloat162float(pb.y));
-        pk[i] = *reinterpret_cast<uint32_t*>(&pa);
-        pk[16 + i] = *reinterpret_cast<uint32_t*>(&pb);
+        const float a0 = ex2_approx(fmaf(__uint_as_float(r0[2 * i]), p.scale_log2, nm));
+        const float a1 = ex2_approx(fmaf(__uint_as_float(r0[2 * i + 1]), p.scale_log2, nm));
+        const float b0 = ex2_approx(fmaf(__uint_as_float(r1[2 * i]), p.scale_log2, nm));
+        const float b1 = ex2_approx(fmaf(__uint_as_float(r1[2 * i + 1]), p.scale_log2, nm));
+        ls0 += a0; ls1 += a1; ls2 += b0; ls3 += b1;
+        pk[i] = pack_bf16x2(a0, a1);
+        pk[16 + i] = pack_bf16x2(b0, b1);
       }
+      const float lsum = (ls0 + ls1) + (ls2 + ls3);
       l_run += lsum;
       // P buffer b was last read by PV(j-2)
       mbar_wait(&p_empty[b], (u & 1) ^ 1);

@@ -39,9 +39,9 @@ static bool gn_geometry(int HW, int C, GnGeom* g) {
   g->Tq = bestTq;
   g->Tp = 256 / bestTq;
   g->Kq = g->Q / bestTq;
-  // ~16K elements (64 KB fp32) per chunk: enough CTAs to saturate HBM on the big VAE tensors, few enough
+  // ~8K elements (32 KB fp32) per chunk: enough CTAs to saturate HBM on the big VAE tensors, few enough
   // partials that combining them stays negligible on the small UNet ones
-  long long want = ((long long)HW * C + 16383) / 16384;
+  long long want = ((long long)HW * C + 8191) / 8192;
   if (want < 1) want = 1;
   if (want > kGnMaxChunks) want = kGnMaxChunks;
   if (want > HW) want = HW;
@@ -53,11 +53,13 @@ static bool gn_geometry(int HW, int C, GnGeom* g) {
 
 size_t groupnorm_ws_bytes(int NB, int HW, int C, int G) {
   (void)HW; (void)C;
-  return size_t(NB) * kGnMaxChunks * G * 2 * sizeof(float);
+  // [partials NB x kGnMaxChunks x G x 2][mean|rstd NB x 2G][arrival counters NB]
+  return (size_t(NB) * kGnMaxChunks * G * 2 + size_t(NB) * 2 * G + size_t(NB)) * sizeof(float);
 }
 
 __global__ void __launch_bounds__(kGnThreads) gn_stats_kernel(const float* __restrict__ x, float* __restrict__ ws,
-                                                              int HW, int C, int G, GnGeom g) {
+                                                              float* __restrict__ stat, unsigned* __restrict__ counters,
+                                                              int HW, int C, int G, float eps, GnGeom g) {
   extern __shared__ float s_acc[];  // [2 * C]
   pdl_launch_dependents();
   pdl_wait();
@@ -73,16 +75,29 @@ __global__ void __launch_bounds__(kGnThreads) gn_stats_kernel(const float* __res
       for (int j = 0; j < 4; ++j) { sum[k][j] = 0.f; sq[k][j] = 0.f; }
     const int p0 = chunk * g.P, p1 = min(HW, p0 + g.P);
     const float4* xi = reinterpret_cast<const float4*>(x + (size_t)img * HW * C);
-    for (int p = p0 + tp; p < p1; p += g.Tp) {
 #pragma unroll
-      for (int k = 0; k < kGnMaxK; ++k) {
-        if (k < g.Kq) {
-          const float4 v = __ldg(xi + (size_t)p * g.Q + tq + k * g.Tq);
-          sum[k][0] += v.x; sq[k][0] += v.x * v.x;
-          sum[k][1] += v.y; sq[k][1] += v.y * v.y;
-          sum[k][2] += v.z; sq[k][2] += v.z * v.z;
-          sum[k][3] += v.w; sq[k][3] += v.w * v.w;
+    for (int k = 0; k < kGnMaxK; ++k) {
+      if (k >= g.Kq) break;
+      const size_t qoff = size_t(tq) + size_t(k) * g.Tq;
+      int p = p0 + tp;
+      for (; p + 3 * g.Tp < p1; p += 4 * g.Tp) {
+        float4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = __ldg(xi + (size_t)(p + u * g.Tp) * g.Q + qoff);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          sum[k][0] += v[u].x; sq[k][0] += v[u].x * v[u].x;
+          sum[k][1] += v[u].y; sq[k][1] += v[u].y * v[u].y;
+          sum[k][2] += v[u].z; sq[k][2] += v[u].z * v[u].z;
+          sum[k][3] += v[u].w; sq[k][3] += v[u].w * v[u].w;
         }
+      }
+      for (; p < p1; p += g.Tp) {
+        const float4 v = __ldg(xi + (size_t)p * g.Q + qoff);
+        sum[k][0] += v.x; sq[k][0] += v.x * v.x;
+        sum[k][1] += v.y; sq[k][1] += v.y * v.y;
+        sum[k][2] += v.z; sq[k][2] += v.z * v.z;
+        sum[k][3] += v.w; sq[k][3] += v.w * v.w;
       }
     }
 #pragma unroll
@@ -105,26 +120,23 @@ __global__ void __launch_bounds__(kGnThreads) gn_stats_kernel(const float* __res
     float* dst = ws + (((size_t)img * kGnMaxChunks + chunk) * G + gi) * 2;
     dst[0] = s; dst[1] = q;
   }
-}
-
-__global__ void __launch_bounds__(kGnThreads)
-    gn_apply_kernel(const float* __restrict__ x, bf16* __restrict__ y, bf16* __restrict__ raw,
-                    const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ ws,
-                    int HW, int C, int G, float eps, int silu, GnGeom g) {
-  extern __shared__ float s_stat[];  // mean[G], rstd[G]
-  pdl_launch_dependents();
-  pdl_wait();
-  const int img = blockIdx.y, chunk = blockIdx.x;
-  const int cpg = C / G;
-  // combine the per-chunk partials of this image: (group, slice) per thread, then across slices
+  // last CTA of this image combines the partials into mean / rstd (so gn_apply starts with 2G floats)
+  __shared__ bool s_last;
   __shared__ double s_part[2][kGnThreads];
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = atomicAdd(counters + img, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
   {
-    const int slices = kGnThreads / G;                 // G <= 256
+    const int slices = kGnThreads / G;
     const int gi = threadIdx.x % G, sl = threadIdx.x / G;
     double s = 0.0, q = 0.0;
     if (sl < slices) {
-      for (int ch = sl; ch < g.chunks; ch += slices) {
-        const float2 v = __ldg(reinterpret_cast<const float2*>(ws + (((size_t)img * kGnMaxChunks + ch) * G + gi) * 2));
+#pragma unroll 4
+      for (int ch = sl; ch < int(gridDim.x); ch += slices) {
+        const float2 v = __ldcg(reinterpret_cast<const float2*>(ws + (((size_t)img * kGnMaxChunks + ch) * G + gi) * 2));
         s += double(v.x); q += double(v.y);
       }
     }
@@ -137,10 +149,23 @@ __global__ void __launch_bounds__(kGnThreads)
       const double mean = s / n;
       double var = q / n - mean * mean;
       if (var < 0.0) var = 0.0;
-      s_stat[threadIdx.x] = float(mean);
-      s_stat[G + threadIdx.x] = float(1.0 / sqrt(var + double(eps)));
+      stat[(size_t)img * 2 * G + threadIdx.x] = float(mean);
+      stat[(size_t)img * 2 * G + G + threadIdx.x] = rsqrtf(float(var) + eps);
     }
+    if (threadIdx.x == 0) counters[img] = 0;   // self-resetting
   }
+}
+
+__global__ void __launch_bounds__(kGnThreads)
+    gn_apply_kernel(const float* __restrict__ x, bf16* __restrict__ y, bf16* __restrict__ raw,
+                    const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ stat,
+                    int HW, int C, int G, int silu, GnGeom g) {
+  extern __shared__ float s_stat[];  // mean[G], rstd[G]
+  pdl_launch_dependents();
+  pdl_wait();
+  const int img = blockIdx.y, chunk = blockIdx.x;
+  const int cpg = C / G;
+  for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) s_stat[i] = __ldcg(stat + (size_t)img * 2 * G + i);
   __syncthreads();
   const int tq = threadIdx.x % g.Tq, tp = threadIdx.x / g.Tq;
   if (tp >= g.Tp) return;
@@ -162,18 +187,34 @@ __global__ void __launch_bounds__(kGnThreads)
       }
     }
   }
-  for (int p = p0 + tp; p < p1; p += g.Tp) {
 #pragma unroll
-    for (int k = 0; k < kGnMaxK; ++k) {
-      if (k < g.Kq) {
-        const size_t idx = (size_t)p * g.Q + tq + k * g.Tq;
-        const float4 v = __ldg(xi + idx);
-        float o0 = v.x * sc[k][0] + sh[k][0], o1 = v.y * sc[k][1] + sh[k][1];
-        float o2 = v.z * sc[k][2] + sh[k][2], o3 = v.w * sc[k][3] + sh[k][3];
+  for (int k = 0; k < kGnMaxK; ++k) {
+    if (k >= g.Kq) break;
+    const float s0 = sc[k][0], s1 = sc[k][1], s2 = sc[k][2], s3 = sc[k][3];
+    const float h0 = sh[k][0], h1 = sh[k][1], h2 = sh[k][2], h3 = sh[k][3];
+    const size_t qoff = size_t(tq) + size_t(k) * g.Tq;
+    int p = p0 + tp;
+    // 4 pixels per trip: the loads are issued back to back, then consumed
+    for (; p + 3 * g.Tp < p1; p += 4 * g.Tp) {
+      float4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = __ldg(xi + (size_t)(p + u * g.Tp) * g.Q + qoff);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const size_t idx = (size_t)(p + u * g.Tp) * g.Q + qoff;
+        float o0 = v[u].x * s0 + h0, o1 = v[u].y * s1 + h1, o2 = v[u].z * s2 + h2, o3 = v[u].w * s3 + h3;
         if (silu) { o0 = silu_f(o0); o1 = silu_f(o1); o2 = silu_f(o2); o3 = silu_f(o3); }
         yo[idx] = make_uint2(pack_bf16x2(o0, o1), pack_bf16x2(o2, o3));
-        if (ro) ro[idx] = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+        if (ro) ro[idx] = make_uint2(pack_bf16x2(v[u].x, v[u].y), pack_bf16x2(v[u].z, v[u].w));
       }
+    }
+    for (; p < p1; p += g.Tp) {
+      const size_t idx = (size_t)p * g.Q + qoff;
+      const float4 v = __ldg(xi + idx);
+      float o0 = v.x * s0 + h0, o1 = v.y * s1 + h1, o2 = v.z * s2 + h2, o3 = v.w * s3 + h3;
+      if (silu) { o0 = silu_f(o0); o1 = silu_f(o1); o2 = silu_f(o2); o3 = silu_f(o3); }
+      yo[idx] = make_uint2(pack_bf16x2(o0, o1), pack_bf16x2(o2, o3));
+      if (ro) ro[idx] = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
     }
   }
 }
@@ -186,9 +227,11 @@ int launch_groupnorm(const float* x, bf16* y, bf16* raw_copy, const float* gamma
     return MGB_ERR_INVALID;
   }
   dim3 grid(g.chunks, NB);
-  launch_k(gn_stats_kernel, grid, kGnThreads, 2 * C * sizeof(float), stream, x, ws, HW, C, G, g);
+  float* stat = ws + size_t(NB) * kGnMaxChunks * G * 2;
+  unsigned* counters = reinterpret_cast<unsigned*>(stat + size_t(NB) * 2 * G);
+  launch_k(gn_stats_kernel, grid, kGnThreads, 2 * C * sizeof(float), stream, x, ws, stat, counters, HW, C, G, eps, g);
   launch_k(gn_apply_kernel, grid, kGnThreads, 2 * G * sizeof(float), stream, x, y, raw_copy, gamma, beta,
-           static_cast<const float*>(ws), HW, C, G, eps, silu, g);
+           static_cast<const float*>(stat), HW, C, G, silu, g);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     set_error("groupnorm launch: %s", cudaGetErrorString(e));
