@@ -73,8 +73,7 @@ static int linear(Ctx& c, const bf16* a, int M, const LinW& W, const Epi& e) {
   int bn, sp, st;
   const bool geglu = (e.flags & EPI_GEGLU) != 0;
   choose_tile((M + 127) / 128, W.n, W.k / 64, geglu, true, &bn, &sp, &st);
-  if (geglu) bn = 256;
-  if (geglu) { sp = 1; st = 4; }
+  if (geglu) { bn = 256; sp = 1; st = (W.k / 64 <= 12) ? 2 : 4; }
   if (sp > 1) c.splitk_need = std::max(c.splitk_need, size_t(sp) * M * W.n * sizeof(float));
   if (c.dry) return MGB_OK;
   GemmParams p;

@@ -181,8 +181,15 @@ void choose_tile(int m_tiles, int N, int num_kb, bool geglu, bool allow_split, i
   *block_n = bbn;
   *splits = bsp;
   const int stage_bytes = 16384 + bbn * 128;
-  int st = int((200 * 1024) / stage_bytes);
+  const int kb = (num_kb + bsp - 1) / bsp;
+  // Deep pipelines (the whole 200 KB) only pay off for long K loops. Short-K GEMMs are dominated by
+  // prologue / first-load / epilogue latency: cap them near 110 KB so that the NEXT kernel's CTA (launched
+  // early through PDL) can become resident on the same SM and overlap its prologue and first operand loads
+  // with this kernel's epilogue.
+  const int budget = kb <= 12 ? 110 * 1024 : 200 * 1024;
+  int st = int((budget - 2048) / stage_bytes);
   st = std::max(2, std::min(st, 8));
+  st = std::min(st, std::max(2, kb));
   *stages = st;
 }
 
