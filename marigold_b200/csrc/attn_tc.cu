@@ -32,6 +32,9 @@ constexpr int kKvBytes = 64 * 128;       // 64 rows x 64 bf16
 constexpr int kPBytes = 128 * 128;       // 128 rows x 64 bf16
 constexpr int kKvStages = 3;
 constexpr float kRescaleThreshold = 8.0f;  // log2 units
+// P (bf16) goes back to tensor memory and feeds the PV MMA as a TMEM A-operand: no smem round trip and no
+// generic->async proxy fence in the softmax loop.
+constexpr bool kPInTmem = true;
 
 struct AttnParams {
   CUtensorMap tmap_q;   // 3D {3C, T, NB}, box {64, 128, 1}
@@ -139,9 +142,16 @@ __global__ void __launch_bounds__(kAttnThreads, 2) flash_attn64_kernel(const __g
         const uint32_t pbase = smem_u32(sP + b * kPBytes), vbase = smem_u32(sV + s * kKvBytes);
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          // A: P rows K-major, 32 B per K=16 step; B: V [kv, d] d-contiguous (MN-major): 16 kv rows = 2048 B
-          umma_bf16(tmem_o, umma_desc_sw128(pbase + k * 32), umma_desc_sw128(vbase + k * 2048), idesc_pv,
-                    (j > 0 || k > 0) ? 1u : 0u);
+          // B: V [kv, d] d-contiguous (MN-major): 16 kv rows = 2048 B per K=16 step
+          if constexpr (kPInTmem) {
+            // A: P in TMEM, 16 bf16 = 8 columns per K=16 step
+            umma_bf16_ts(tmem_o, tmem_base + 192 + b * 32 + k * 8, umma_desc_sw128(vbase + k * 2048), idesc_pv,
+                         (j > 0 || k > 0) ? 1u : 0u);
+          } else {
+            // A: P rows K-major in smem, 32 B per K=16 step
+            umma_bf16(tmem_o, umma_desc_sw128(pbase + k * 32), umma_desc_sw128(vbase + k * 2048), idesc_pv,
+                      (j > 0 || k > 0) ? 1u : 0u);
+          }
         }
         umma_commit(&v_empty[s]);
         umma_commit(&p_empty[b]);
@@ -224,13 +234,18 @@ __global__ void __launch_bounds__(kAttnThreads, 2) flash_attn64_kernel(const __g
       l_run += lsum;
       // P buffer b was last read by PV(j-2)
       mbar_wait(&p_empty[b], (u & 1) ^ 1);
-      uint8_t* prow = sP + b * kPBytes + row * 128;
+      if constexpr (kPInTmem) {
+        tmem_st32(tmem_base + 192 + b * 32 + lane_off, pk);
+        tmem_wait_st();
+      } else {
+        uint8_t* prow = sP + b * kPBytes + row * 128;
 #pragma unroll
-      for (int ch = 0; ch < 8; ++ch) {
-        uint4* dst = reinterpret_cast<uint4*>(prow + ((ch ^ (row & 7)) << 4));
-        *dst = make_uint4(pk[4 * ch], pk[4 * ch + 1], pk[4 * ch + 2], pk[4 * ch + 3]);
+        for (int ch = 0; ch < 8; ++ch) {
+          uint4* dst = reinterpret_cast<uint4*>(prow + ((ch ^ (row & 7)) << 4));
+          *dst = make_uint4(pk[4 * ch], pk[4 * ch + 1], pk[4 * ch + 2], pk[4 * ch + 3]);
+        }
+        fence_proxy_async_smem();
       }
-      fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(&p_full[b]);
     }
