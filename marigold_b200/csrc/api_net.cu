@@ -536,6 +536,7 @@ static int ensure_workspace(mgb_handle* h, int op, int NB, int d0, int d1) {
   const size_t gn_need = groupnorm_ws_bytes(NB, 0, 0, h->cfg.norm_groups);
   if (gn_need > h->gn_ws_bytes) {
     CUDA_TRY(cudaDeviceSynchronize());
+    if (h->step_graph.exec) { cudaGraphExecDestroy(h->step_graph.exec); h->step_graph.exec = nullptr; }
     if (h->gn_ws) CUDA_TRY(cudaFree(h->gn_ws));
     void* p = nullptr;
     CUDA_TRY(cudaMalloc(&p, gn_need));

@@ -17,6 +17,7 @@ namespace mgb {
 constexpr int kGnThreads = 256;
 constexpr int kGnMaxK = 4;      // channel-quads per thread
 constexpr int kGnMaxChunks = 592;   // partial-statistics slots per image
+constexpr int kGnMaxImages = 256;   // arrival counters
 
 struct GnGeom {
   int Q;        // C / 4
@@ -53,8 +54,9 @@ static bool gn_geometry(int HW, int C, GnGeom* g) {
 
 size_t groupnorm_ws_bytes(int NB, int HW, int C, int G) {
   (void)HW; (void)C;
-  // [partials NB x kGnMaxChunks x G x 2][mean|rstd NB x 2G][arrival counters NB]
-  return (size_t(NB) * kGnMaxChunks * G * 2 + size_t(NB) * 2 * G + size_t(NB)) * sizeof(float);
+  // [arrival counters: kGnMaxImages, FIXED offset 0 so that they stay valid (zero) across calls with
+  //  different NB][mean|rstd NB x 2G][partials NB x kGnMaxChunks x G x 2]
+  return (size_t(kGnMaxImages) + size_t(NB) * 2 * G + size_t(NB) * kGnMaxChunks * G * 2) * sizeof(float);
 }
 
 __global__ void __launch_bounds__(kGnThreads) gn_stats_kernel(const float* __restrict__ x, float* __restrict__ ws,
@@ -222,14 +224,15 @@ __global__ void __launch_bounds__(kGnThreads)
 int launch_groupnorm(const float* x, bf16* y, bf16* raw_copy, const float* gamma, const float* beta, float* ws,
                      int NB, int HW, int C, int G, float eps, int silu, cudaStream_t stream) {
   GnGeom g;
-  if (C % G != 0 || G > kGnThreads || kGnThreads % G != 0 || !gn_geometry(HW, C, &g)) {
+  if (C % G != 0 || G > kGnThreads || kGnThreads % G != 0 || NB > kGnMaxImages || !gn_geometry(HW, C, &g)) {
     set_error("groupnorm: unsupported C=%d G=%d", C, G);
     return MGB_ERR_INVALID;
   }
   dim3 grid(g.chunks, NB);
-  float* stat = ws + size_t(NB) * kGnMaxChunks * G * 2;
-  unsigned* counters = reinterpret_cast<unsigned*>(stat + size_t(NB) * 2 * G);
-  launch_k(gn_stats_kernel, grid, kGnThreads, 2 * C * sizeof(float), stream, x, ws, stat, counters, HW, C, G, eps, g);
+  unsigned* counters = reinterpret_cast<unsigned*>(ws);
+  float* stat = ws + kGnMaxImages;
+  float* partials = stat + size_t(NB) * 2 * G;
+  launch_k(gn_stats_kernel, grid, kGnThreads, 2 * C * sizeof(float), stream, x, partials, stat, counters, HW, C, G, eps, g);
   launch_k(gn_apply_kernel, grid, kGnThreads, 2 * G * sizeof(float), stream, x, y, raw_copy, gamma, beta,
            static_cast<const float*>(stat), HW, C, G, silu, g);
   cudaError_t e = cudaGetLastError();
