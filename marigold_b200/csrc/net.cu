@@ -7,6 +7,7 @@
 // Numerics: bf16 tensor-core operands, fp32 accumulation, fp32 residual trunk and latent state;
 // GroupNorm/LayerNorm/softmax statistics in fp32.
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 #include "net.h"
@@ -57,6 +58,7 @@ static void set_epi(GemmParams& p, const Epi& e, int ldo) {
 }
 
 static int gemm_common(Ctx& c, GemmParams& p, int bn, int splits, const Epi& e, int ldo) {
+  if (skip_family("gemm")) return MGB_OK;
   set_epi(p, e, ldo);
   if (splits > 1) {
     const size_t need = size_t(splits) * p.M * p.N * sizeof(float);
@@ -106,6 +108,13 @@ static int conv3x3(Ctx& c, const bf16* x, int NB, int Hout, int Wout, const Conv
   return gemm_common(c, p, bn, effective_splits(p), e2, W.cout);
 }
 
+// Debug only (tools/marginal_cost.py): MGB_SKIP=gn,ln,attn,xattn,concat,gemm drops a kernel family from the graph so
+// that its marginal in-graph cost can be read from the step time. Results are garbage when set.
+static bool skip_family(const char* name) {
+  static const char* env = getenv("MGB_SKIP");
+  return env && strstr(env, name) != nullptr;
+}
+
 #define LAUNCH(call, n)            \
   do {                             \
     if (!c.dry) {                  \
@@ -116,6 +125,7 @@ static int conv3x3(Ctx& c, const bf16* x, int NB, int Hout, int Wout, const Conv
 
 static int groupnorm(Ctx& c, const float* x, bf16* y, bf16* raw, const NormW& n, int NB, int HW, float eps, int silu,
                      float* gn_ws) {
+  if (skip_family("gn")) return MGB_OK;
   LAUNCH(launch_groupnorm(x, y, raw, n.g, n.b, gn_ws, NB, HW, n.c, c.groups, eps, silu, c.stream), 2);
   return MGB_OK;
 }
@@ -168,17 +178,18 @@ static int xfmr_forward(Ctx& c, const XfmrW& X, const float* x, float* y, int NB
   TRY(groupnorm(c, x, a, nullptr, X.gn, NB, T, 1e-6f, 0, gn_ws));
   { Epi e; e.bias = X.proj_in.b; e.out_f32 = hs0; TRY(linear(c, a, int(M), X.proj_in, e)); }
   // self attention
-  LAUNCH(launch_layernorm(hs0, a, X.ln1.g, X.ln1.b, int(M), C, 1e-5f, c.stream), 1);
+  const bool no_ln = skip_family("ln"), no_attn = skip_family("attn"), no_x = skip_family("xattn");
+  if (!no_ln) LAUNCH(launch_layernorm(hs0, a, X.ln1.g, X.ln1.b, int(M), C, 1e-5f, c.stream), 1);
   { Epi e; e.out_bf16 = qkv; TRY(linear(c, a, int(M), X.qkv, e)); }
-  LAUNCH(launch_flash_attn64(qkv, o, NB, T, C, 0.125f, c.stream), 1);
+  if (!no_attn) LAUNCH(launch_flash_attn64(qkv, o, NB, T, C, 0.125f, c.stream), 1);
   { Epi e; e.bias = X.o1.b; e.residual = hs0; e.out_f32 = hs1; TRY(linear(c, o, int(M), X.o1, e)); }
   // cross attention against the folded empty-prompt K/V
-  LAUNCH(launch_layernorm(hs1, a, X.ln2.g, X.ln2.b, int(M), C, 1e-5f, c.stream), 1);
+  if (!no_ln) LAUNCH(launch_layernorm(hs1, a, X.ln2.g, X.ln2.b, int(M), C, 1e-5f, c.stream), 1);
   { Epi e; e.out_bf16 = qkv; TRY(linear(c, a, int(M), X.q2, e)); }  // q in the first M*C elements of qkv
-  LAUNCH(launch_cross_attn2(qkv, X.kv, o, int(M), C, 0.125f, c.stream), 1);
+  if (!no_x) LAUNCH(launch_cross_attn2(qkv, X.kv, o, int(M), C, 0.125f, c.stream), 1);
   { Epi e; e.bias = X.o2.b; e.residual = hs1; e.out_f32 = hs0; TRY(linear(c, o, int(M), X.o2, e)); }
   // GEGLU feed-forward
-  LAUNCH(launch_layernorm(hs0, a, X.ln3.g, X.ln3.b, int(M), C, 1e-5f, c.stream), 1);
+  if (!no_ln) LAUNCH(launch_layernorm(hs0, a, X.ln3.g, X.ln3.b, int(M), C, 1e-5f, c.stream), 1);
   { Epi e; e.bias = X.ff1.b; e.out_bf16 = ffm; e.flags = EPI_GEGLU; TRY(linear(c, a, int(M), X.ff1, e)); }
   { Epi e; e.bias = X.ff2.b; e.residual = hs0; e.out_bf16 = hsb; TRY(linear(c, ffm, int(M), X.ff2, e)); }
   { Epi e; e.bias = X.proj_out.b; e.residual = x; e.out_f32 = y; TRY(linear(c, hsb, int(M), X.proj_out, e)); }
@@ -289,7 +300,7 @@ int unet_forward(mgb_handle* hd, Ctx& c, const float* rgb, float* tgt, const flo
       Skip s = skips.back();
       skips.pop_back();
       float* cat = aalloc<float>(c, M * (cur + s.c));
-      LAUNCH(launch_concat(h, s.p, cat, int(M), cur, s.c, c.stream), 1);
+      if (!skip_family("concat")) LAUNCH(launch_concat(h, s.p, cat, int(M), cur, s.c, c.stream), 1);
       float* y = aalloc<float>(c, M * cout);
       TRY(resnet_forward(c, U.resnets[ri++], cat, y, NB, H, W, gn_ws));
       h = y; cur = cout;
