@@ -51,6 +51,13 @@ struct Epi {
   float* aux_out = nullptr;
 };
 
+// Debug only (tools/marginal_cost.py): MGB_SKIP=gn,ln,attn,xattn,concat,gemm drops a kernel family from the graph so
+// that its marginal in-graph cost can be read from the step time. Results are garbage when set.
+static bool skip_family(const char* name) {
+  static const char* env = getenv("MGB_SKIP");
+  return env && strstr(env, name) != nullptr;
+}
+
 static void set_epi(GemmParams& p, const Epi& e, int ldo) {
   p.epi.bias = e.bias; p.epi.residual = e.residual; p.epi.out_f32 = e.out_f32; p.epi.out_bf16 = e.out_bf16;
   p.epi.ldo = ldo; p.epi.flags = e.flags; p.epi.hw = e.hw; p.epi.scale = e.scale;
@@ -106,13 +113,6 @@ static int conv3x3(Ctx& c, const bf16* x, int NB, int Hout, int Wout, const Conv
   Epi e2 = e;
   e2.hw = Hout * Wout;
   return gemm_common(c, p, bn, effective_splits(p), e2, W.cout);
-}
-
-// Debug only (tools/marginal_cost.py): MGB_SKIP=gn,ln,attn,xattn,concat,gemm drops a kernel family from the graph so
-// that its marginal in-graph cost can be read from the step time. Results are garbage when set.
-static bool skip_family(const char* name) {
-  static const char* env = getenv("MGB_SKIP");
-  return env && strstr(env, name) != nullptr;
 }
 
 #define LAUNCH(call, n)            \
