@@ -151,8 +151,7 @@ int mgb_op_conv2d(const void* x_bf16_dev, const void* w_bf16_dev, const float* b
                   float* splitk_ws_dev, void* stream);
 int mgb_op_flash_attn64(const void* qkv_bf16_dev, void* out_bf16_dev, int32_t NB, int32_t T, int32_t C, float scale,
                         void* stream);
-/* ws_dev: (256 + NB*2*G + NB*592*G*2) floats whose first 256 words are ZERO before the first call
- * (arrival counters; they reset themselves). */
+/* ws_dev: NB*C*2 floats of scratch (per-channel sums). */
 int mgb_op_groupnorm(const float* x_dev, void* y_bf16_dev, const float* gamma_dev, const float* beta_dev,
                      float* ws_dev, int32_t NB, int32_t HW, int32_t C, int32_t G, float eps, int32_t silu,
                      void* stream);

@@ -256,6 +256,7 @@ void mgb_destroy(mgb_handle* h) {
   if (h->splitk_ws) cudaFree(h->splitk_ws);
   if (h->sched_k) cudaFree(h->sched_k);
   if (h->gn_ws) cudaFree(h->gn_ws);
+  if (h->stat_slab) cudaFree(h->stat_slab);
   if (h->bias_table) cudaFree(h->bias_table);
   if (h->cur_bias) cudaFree(h->cur_bias);
   if (h->cur_sched_k) cudaFree(h->cur_sched_k);
@@ -533,16 +534,16 @@ static int ensure_workspace(mgb_handle* h, int op, int NB, int d0, int d1) {
     h->splitk_ws = static_cast<float*>(p);
     h->splitk_cap = c.splitk_need;
   }
-  const size_t gn_need = groupnorm_ws_bytes(NB, 0, 0, h->cfg.norm_groups);
-  if (gn_need > h->gn_ws_bytes) {
+  const size_t stat_need = c.stat_need * sizeof(float);
+  if (stat_need > h->stat_slab_bytes) {
     CUDA_TRY(cudaDeviceSynchronize());
     if (h->step_graph.exec) { cudaGraphExecDestroy(h->step_graph.exec); h->step_graph.exec = nullptr; }
-    if (h->gn_ws) CUDA_TRY(cudaFree(h->gn_ws));
+    if (h->stat_slab) CUDA_TRY(cudaFree(h->stat_slab));
+    h->stat_slab = nullptr; h->stat_slab_bytes = 0;
     void* p = nullptr;
-    CUDA_TRY(cudaMalloc(&p, gn_need));
-    CUDA_TRY(cudaMemset(p, 0, gn_need));   // arrival counters start at zero (and reset themselves)
-    h->gn_ws = static_cast<float*>(p);
-    h->gn_ws_bytes = gn_need;
+    CUDA_TRY(cudaMalloc(&p, stat_need));
+    h->stat_slab = static_cast<float*>(p);
+    h->stat_slab_bytes = stat_need;
   }
   return MGB_OK;
 }
@@ -596,6 +597,8 @@ static Ctx make_ctx(mgb_handle* h, void* stream) {
   c.dry = false;
   c.splitk_ws = h->splitk_ws; c.splitk_cap = h->splitk_cap;
   c.groups = h->cfg.norm_groups;
+  c.stat_base = h->stat_slab;
+  c.stat_cap = h->stat_slab_bytes / sizeof(float);
   return c;
 }
 

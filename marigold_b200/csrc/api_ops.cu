@@ -44,7 +44,8 @@ int mgb_op_linear(const void* a, const void* w, const float* bias, const float* 
   if (!a || !w || (!out_f32 && !out_bf16)) { set_error("op_linear: null pointer"); return MGB_ERR_INVALID; }
   if (block_n <= 0) {
     int bn, sp, st;
-    choose_tile((M + 127) / 128, N, K / 64, (flags & EPI_GEGLU) != 0, splitk_ws != nullptr, &bn, &sp, &st);
+    choose_tile((M + 127) / 128, N, K / 64, (flags & EPI_GEGLU) != 0, splitk_ws != nullptr && !(flags & EPI_GEGLU), &bn, &sp,
+                &st);
     block_n = bn; if (splits <= 0) splits = sp; if (stages <= 0) stages = st;
   }
   if (splits <= 0) splits = 1;

@@ -360,6 +360,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
       const float scale = (!raw && (e.flags & EPI_SCALE)) ? e.scale : 1.0f;
       const bool silu = !raw && (e.flags & EPI_SILU);
       const bool ld_vec = (ldo & 3) == 0;
+      float* cstat = raw ? nullptr : e.cstat;
+      const int stat_img = p.mode == 1 ? img : int(((long long)m_tile * BLOCK_M) / (e.hw > 0 ? e.hw : 1));
       // row addressing hoisted out of the chunk loop: after the transpose this lane stores rows
       // R = it * 4 + (lane >> 3), it = 0..7, of its warp's 32-row slab
       long long off[8];
@@ -412,6 +414,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
               rr[it] = ((vmask >> it) & 1u) ? __ldg(reinterpret_cast<const float4*>(residual + off[it] + col))
                                            : make_float4(0.f, 0.f, 0.f, 0.f);
           }
+          float cs[4] = {0.f, 0.f, 0.f, 0.f}, cq[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
           for (int it = 0; it < 8; ++it) {
             float4 v = x[it];
@@ -423,6 +426,28 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
               if (out_f32) *reinterpret_cast<float4*>(out_f32 + o) = v;
               if (out_bf16)
                 *reinterpret_cast<uint2*>(out_bf16 + o) = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+              cs[0] += v.x; cs[1] += v.y; cs[2] += v.z; cs[3] += v.w;
+              cq[0] = fmaf(v.x, v.x, cq[0]); cq[1] = fmaf(v.y, v.y, cq[1]);
+              cq[2] = fmaf(v.z, v.z, cq[2]); cq[3] = fmaf(v.w, v.w, cq[3]);
+            }
+          }
+          if (cstat) {
+            // GroupNorm statistics for the consumer: column sums over this warp's 32 rows (the 4 row
+            // sub-groups sit in lane bits 3..4), then one RED per column and moment from lanes 0..7
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              cs[k] += __shfl_xor_sync(0xffffffffu, cs[k], 8);
+              cq[k] += __shfl_xor_sync(0xffffffffu, cq[k], 8);
+              cs[k] += __shfl_xor_sync(0xffffffffu, cs[k], 16);
+              cq[k] += __shfl_xor_sync(0xffffffffu, cq[k], 16);
+            }
+            if (sub == 0) {
+              float* dst = cstat + ((long long)stat_img * ldo + col) * 2;
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                atomicAdd(dst + 2 * k, cs[k]);
+                atomicAdd(dst + 2 * k + 1, cq[k]);
+              }
             }
           }
         } else {
@@ -473,23 +498,32 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
 }
 
 // -------------------------------------------------------------------------------------------------
-// Split-K deferred epilogue: sum partials, then the same fused epilogue on CUDA cores.
-// One thread per (row, 4 columns).
+// Split-K deferred epilogue: sum the partials, then the same fused epilogue on CUDA cores.
+// Column-owner mapping: a thread owns up to kSkQuads column quads and walks a block of rows of ONE image,
+// so the per-channel GroupNorm statistics stay in registers and cost 8 REDs per quad per block.
 // -------------------------------------------------------------------------------------------------
-__global__ void splitk_epilogue_kernel(const GemmParams p, int splits, int geglu_half /* BLOCK_N/2 or 0 */) {
+constexpr int kSkThreads = 256;
+constexpr int kSkQuads = 3;      // N <= 3072
+
+__global__ void __launch_bounds__(kSkThreads) splitk_epilogue_kernel(const GemmParams p, int splits, int rows_per_block,
+                                                                     int blocks_per_img, int rows_per_img) {
   pdl_launch_dependents();
   pdl_wait();
   const GemmEpilogue& e = p.epi;
-  const int n_out = geglu_half ? p.N / 2 : p.N;
-  if (!geglu_half && (p.N & 3) == 0 && (e.ldo & 3) == 0) {
-    // 4 columns per thread, 128-bit loads of every partial
-    const int nq = p.N / 4;
-    const long long total4 = (long long)p.M * nq;
-    const size_t slab = (size_t)p.M * p.N;
-    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total4;
-         idx += (long long)gridDim.x * blockDim.x) {
-      const long long m = idx / nq;
-      const int c = int(idx - m * nq) * 4;
+  const int nq = p.N / 4;
+  const int img = blockIdx.x / blocks_per_img;
+  const int r0 = img * rows_per_img + (blockIdx.x % blocks_per_img) * rows_per_block;
+  const int r1 = min(r0 + rows_per_block, (img + 1) * rows_per_img);
+  const size_t slab = (size_t)p.M * p.N;
+#pragma unroll
+  for (int k = 0; k < kSkQuads; ++k) {
+    const int q = threadIdx.x + k * kSkThreads;
+    if (q >= nq) break;
+    const int c = q * 4;
+    float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (e.bias) b4 = __ldg(reinterpret_cast<const float4*>(e.bias + c));
+    float cs[4] = {0.f, 0.f, 0.f, 0.f}, cq[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int m = r0; m < r1; ++m) {
       const float* src = p.partial + (size_t)m * p.N + c;
       float4 a = __ldg(reinterpret_cast<const float4*>(src));
       for (int s = 1; s < splits; ++s) {
@@ -497,51 +531,24 @@ __global__ void splitk_epilogue_kernel(const GemmParams p, int splits, int geglu
         a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
       }
       float v[4] = {a.x, a.y, a.z, a.w};
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        if (e.flags & EPI_SCALE) v[i] *= e.scale;
-        if (e.bias) v[i] += __ldg(e.bias + c + i);
-        if (e.flags & EPI_SILU) v[i] = silu_f(v[i]);
-      }
-      const long long o = m * (long long)e.ldo + c;
+      if (e.flags & EPI_SCALE) { v[0] *= e.scale; v[1] *= e.scale; v[2] *= e.scale; v[3] *= e.scale; }
+      v[0] += b4.x; v[1] += b4.y; v[2] += b4.z; v[3] += b4.w;
+      if (e.flags & EPI_SILU) { v[0] = silu_f(v[0]); v[1] = silu_f(v[1]); v[2] = silu_f(v[2]); v[3] = silu_f(v[3]); }
+      const long long o = (long long)m * e.ldo + c;
       if (e.residual) {
         const float4 r = __ldg(reinterpret_cast<const float4*>(e.residual + o));
         v[0] += r.x; v[1] += r.y; v[2] += r.z; v[3] += r.w;
       }
       if (e.out_f32) *reinterpret_cast<float4*>(e.out_f32 + o) = make_float4(v[0], v[1], v[2], v[3]);
       if (e.out_bf16) *reinterpret_cast<uint2*>(e.out_bf16 + o) = make_uint2(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]));
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { cs[j] += v[j]; cq[j] = fmaf(v[j], v[j], cq[j]); }
     }
-    return;
-  }
-  const long long total = (long long)p.M * n_out;
-  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-       idx += (long long)gridDim.x * blockDim.x) {
-    const long long m = idx / n_out;
-    const int c = int(idx - m * n_out);
-    float out;
-    if (geglu_half) {
-      const int tile = c / geglu_half, within = c - tile * geglu_half;
-      const int cv = tile * 2 * geglu_half + within, cg = cv + geglu_half;
-      float v = 0.f, g = 0.f;
-      for (int s = 0; s < splits; ++s) {
-        v += p.partial[((long long)s * p.M + m) * p.N + cv];
-        g += p.partial[((long long)s * p.M + m) * p.N + cg];
-      }
-      v += __ldg(e.bias + cv);
-      g += __ldg(e.bias + cg);
-      out = v * gelu_erf_f(g);
-    } else {
-      float a = 0.f;
-      for (int s = 0; s < splits; ++s) a += p.partial[((long long)s * p.M + m) * p.N + c];
-      if (e.flags & EPI_SCALE) a *= e.scale;
-      if (e.bias) a += __ldg(e.bias + c);
-      if (e.flags & EPI_SILU) a = silu_f(a);
-      out = a;
+    if (e.cstat) {
+      float* dst = e.cstat + ((long long)img * e.ldo + c) * 2;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { atomicAdd(dst + 2 * j, cs[j]); atomicAdd(dst + 2 * j + 1, cq[j]); }
     }
-    const long long o = m * (long long)e.ldo + c;
-    if (e.residual) out += __ldg(e.residual + o);
-    if (e.out_f32) e.out_f32[o] = out;
-    if (e.out_bf16) e.out_bf16[o] = __float2bfloat16(out);
   }
 }
 
@@ -587,10 +594,20 @@ int launch_gemm_tc(const GemmParams& p, int block_n, int splits, cudaStream_t st
 }
 
 int launch_splitk_epilogue(const GemmParams& p, int block_n, int splits, cudaStream_t stream) {
-  const int n_out = (p.epi.flags & EPI_GEGLU) ? p.N / 2 : p.N;
-  const long long total = (long long)p.M * n_out / 4;
-  int blocks = int(std::min<long long>((total + 255) / 256, 148 * 8));
-  launch_k(splitk_epilogue_kernel, blocks, 256, 0, stream, p, splits, (p.epi.flags & EPI_GEGLU) ? block_n / 2 : 0);
+  (void)block_n;
+  if ((p.epi.flags & EPI_GEGLU) || (p.N & 3) || (p.epi.ldo & 3) || p.N / 4 > kSkThreads * kSkQuads) {
+    set_error("split-K epilogue: unsupported shape/flags (N=%d ldo=%d flags=%d)", p.N, p.epi.ldo, p.epi.flags);
+    return int(cudaErrorInvalidValue);
+  }
+  // blocks never straddle images (rows_per_img = hw when known, else the whole M)
+  const int rows_per_img = (p.epi.hw > 0 && p.M % p.epi.hw == 0) ? p.epi.hw : p.M;
+  const int imgs = p.M / rows_per_img;
+  int blocks_per_img = std::max(1, std::min(rows_per_img, (148 * 2) / imgs));
+  const int rows_per_block = (rows_per_img + blocks_per_img - 1) / blocks_per_img;
+  blocks_per_img = (rows_per_img + rows_per_block - 1) / rows_per_block;
+  cudaError_t e = launch_k(splitk_epilogue_kernel, imgs * blocks_per_img, kSkThreads, 0, stream, p, splits,
+                           rows_per_block, blocks_per_img, rows_per_img);
+  if (e != cudaSuccess) return int(e);
   return int(cudaGetLastError());
 }
 

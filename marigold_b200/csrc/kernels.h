@@ -43,6 +43,8 @@ struct GemmEpilogue {
   const float* sched_z;   // EPI_SCHED: fresh noise     [M, ldo] or nullptr
   const float* sched_k;   // EPI_SCHED: device pointer to {kx, kv, kz}
   float* aux_out;         // EPI_SCHED: optional raw model output (acc + bias) [M, ldo], or nullptr
+  float* cstat;           // optional per-channel (sum, sum^2) of the stored fp32 output: [img, ldo, 2] += ... (GroupNorm
+                          // statistics for the consumer); needs hw (rows per image), fast path only
 };
 
 struct GemmParams {
@@ -95,6 +97,13 @@ int launch_flash_attn64(const bf16* qkv, bf16* out, int NB, int T, int C, float 
 int launch_groupnorm(const float* x, bf16* y, bf16* raw_copy, const float* gamma, const float* beta, float* ws,
                      int NB, int HW, int C, int G, float eps, int silu, cudaStream_t stream);
 size_t groupnorm_ws_bytes(int NB, int HW, int C, int G);
+// per-channel (sum, sum of squares) of x [NB, HW, C] accumulated into cs [NB, C, 2] (must be zero on entry)
+int launch_chan_stats(const float* x, float* cs, int NB, int HW, int C, cudaStream_t stream);
+// GroupNorm(+SiLU) over the channel concat [a | b] (b optional) with group statistics derived from the
+// per-channel sums csa / csb; y bf16 [NB, HW, Ca + Cb]; optional raw bf16 copy of the concat
+int launch_gn_apply2(const float* xa, const float* csa, int Ca, const float* xb, const float* csb, int Cb, bf16* y,
+                     bf16* raw_copy, const float* gamma, const float* beta, int NB, int HW, int G, float eps, int silu,
+                     cudaStream_t stream);
 // LayerNorm over the channel dim: x_f32 [M, C] -> y_bf16 [M, C]
 int launch_layernorm(const float* x, bf16* y, const float* gamma, const float* beta, int M, int C, float eps,
                      cudaStream_t stream);

@@ -49,6 +49,7 @@ struct Epi {
   const float* sched_z = nullptr;
   const float* sched_k = nullptr;
   float* aux_out = nullptr;
+  float* cstat = nullptr;   // per-channel (sum, sum^2) of the fp32 output for the consuming GroupNorm
 };
 
 // Debug only (tools/marginal_cost.py): MGB_SKIP=gn,ln,attn,xattn,concat,gemm drops a kernel family from the graph so
@@ -62,6 +63,7 @@ static void set_epi(GemmParams& p, const Epi& e, int ldo) {
   p.epi.bias = e.bias; p.epi.residual = e.residual; p.epi.out_f32 = e.out_f32; p.epi.out_bf16 = e.out_bf16;
   p.epi.ldo = ldo; p.epi.flags = e.flags; p.epi.hw = e.hw; p.epi.scale = e.scale;
   p.epi.sched_x = e.sched_x; p.epi.sched_z = e.sched_z; p.epi.sched_k = e.sched_k; p.epi.aux_out = e.aux_out;
+  p.epi.cstat = e.cstat;
 }
 
 static int gemm_common(Ctx& c, GemmParams& p, int bn, int splits, const Epi& e, int ldo) {
@@ -123,10 +125,46 @@ static int conv3x3(Ctx& c, const bf16* x, int NB, int Hout, int Wout, const Conv
     }                              \
   } while (0)
 
-static int groupnorm(Ctx& c, const float* x, bf16* y, bf16* raw, const NormW& n, int NB, int HW, float eps, int silu,
-                     float* gn_ws) {
+// fp32 trunk tensor [M, C] with its slot in the GroupNorm statistics slab
+static Act act_alloc(Ctx& c, size_t M, int C, int NB) {
+  Act a;
+  a.p = aalloc<float>(c, M * C);
+  a.C = C;
+  const size_t n = size_t(NB) * C * 2;
+  const size_t off = c.stat_off;
+  c.stat_off += n;
+  if (c.stat_off > c.stat_need) c.stat_need = c.stat_off;
+  a.cs = c.dry ? nullptr : (c.stat_off <= c.stat_cap ? c.stat_base + off : nullptr);
+  a.cs_valid = false;
+  return a;
+}
+
+// Ask the producer GEMM to accumulate y's channel statistics in its epilogue. Possible when every 128-row
+// tile lies inside one image (conv tiles always do; token tiles need hw % 128 == 0 or a single image).
+static void emit_stats(Ctx& c, Epi& e, Act& y, int NB, int hw, bool conv_mode) {
+  if (!c.fuse_stats || c.dry || !y.cs) return;
+  if (!conv_mode && NB > 1 && (hw % 128) != 0) return;
+  e.cstat = y.cs;
+  e.hw = hw;
+  y.cs_valid = true;
+}
+
+// GroupNorm (+SiLU) over [a | b] (b.p == nullptr: single source) -> bf16 operand; stats come from the
+// producers' epilogues, or from a stats kernel when a producer could not emit them.
+static int groupnorm(Ctx& c, Act& a, Act* b, bf16* y, bf16* raw, const NormW& n, int NB, int HW, float eps, int silu) {
   if (skip_family("gn")) return MGB_OK;
-  LAUNCH(launch_groupnorm(x, y, raw, n.g, n.b, gn_ws, NB, HW, n.c, c.groups, eps, silu, c.stream), 2);
+  if (c.dry) return MGB_OK;
+  Act* srcs[2] = {&a, b};
+  for (Act* t : srcs) {
+    if (!t || !t->p || t->cs_valid) continue;
+    if (!t->cs) { set_error("groupnorm: statistics slab exhausted"); return MGB_ERR_STATE; }
+    TRY(launch_chan_stats(t->p, t->cs, NB, HW, t->C, c.stream));
+    count_launch(1);
+    t->cs_valid = true;
+  }
+  TRY(launch_gn_apply2(a.p, a.cs, a.C, b ? b->p : nullptr, b ? b->cs : nullptr, b ? b->C : 0, y, raw, n.g, n.b, NB, HW,
+                       c.groups, eps, silu, c.stream));
+  count_launch(1);
   return MGB_OK;
 }
 
@@ -134,36 +172,42 @@ static int groupnorm(Ctx& c, const float* x, bf16* y, bf16* raw, const NormW& n,
 // ResnetBlock2D: GN -> SiLU -> conv3x3 (+temb) -> GN -> SiLU -> conv3x3 ; + (1x1 shortcut | x)
 //   x fp32 [M, cin] -> y fp32 [M, cout] (y preallocated by the caller)
 // ---------------------------------------------------------------------------------------------
-static int resnet_forward(Ctx& c, const ResnetW& R, const float* x, float* y, int NB, int H, int W, float* gn_ws) {
+static int resnet_forward(Ctx& c, const ResnetW& R, Act& x, Act* skip, Act& y, int NB, int H, int W) {
+  // input = x, or the channel concat [x | skip] of an up block (never materialised in fp32: GroupNorm reads both
+  // sources, and the 1x1 shortcut reads the bf16 copy GroupNorm emits)
   const size_t M = size_t(NB) * H * W;
   const size_t mk = c.arena->mark();
+  const size_t smk = c.stat_off;
   bf16* t1 = aalloc<bf16>(c, M * R.cin);
   bf16* raw = R.has_sc ? aalloc<bf16>(c, M * R.cin) : nullptr;
-  float* h = aalloc<float>(c, M * R.cout);
+  Act h = act_alloc(c, M, R.cout, NB);
   bf16* t2 = aalloc<bf16>(c, M * R.cout);
   float* sc = R.has_sc ? aalloc<float>(c, M * R.cout) : nullptr;
-  TRY(groupnorm(c, x, t1, raw, R.n1, NB, H * W, R.eps, 1, gn_ws));
+  TRY(groupnorm(c, x, skip, t1, raw, R.n1, NB, H * W, R.eps, 1));
   Epi e1;
   e1.bias = (R.bias_off >= 0 && c.cur_bias) ? c.cur_bias + R.bias_off : R.c1.b;
-  e1.out_f32 = h;
+  e1.out_f32 = h.p;
+  emit_stats(c, e1, h, NB, H * W, true);
   TRY(conv3x3(c, t1, NB, H, W, R.c1, 0, e1));
-  TRY(groupnorm(c, h, t2, nullptr, R.n2, NB, H * W, R.eps, 1, gn_ws));
-  const float* residual = x;
+  TRY(groupnorm(c, h, nullptr, t2, nullptr, R.n2, NB, H * W, R.eps, 1));
+  const float* residual = x.p;
   if (R.has_sc) {
     Epi es; es.bias = R.sc.b; es.out_f32 = sc;
     TRY(linear(c, raw, int(M), R.sc, es));
     residual = sc;
   }
-  Epi e2; e2.bias = R.c2.b; e2.residual = residual; e2.out_f32 = y;
+  Epi e2; e2.bias = R.c2.b; e2.residual = residual; e2.out_f32 = y.p;
+  emit_stats(c, e2, y, NB, H * W, true);
   TRY(conv3x3(c, t2, NB, H, W, R.c2, 0, e2));
   c.arena->release(mk);
+  (void)smk;   // h's statistics slot stays reserved for this graph execution (the slab is zeroed once per graph)
   return MGB_OK;
 }
 
 // ---------------------------------------------------------------------------------------------
 // Transformer2DModel (1 BasicTransformerBlock, linear projections). x fp32 [M, C] -> y fp32 [M, C]
 // ---------------------------------------------------------------------------------------------
-static int xfmr_forward(Ctx& c, const XfmrW& X, const float* x, float* y, int NB, int T, float* gn_ws) {
+static int xfmr_forward(Ctx& c, const XfmrW& X, Act& x, Act& y, int NB, int T) {
   const int C = X.C;
   const size_t M = size_t(NB) * T;
   const size_t mk = c.arena->mark();
@@ -175,7 +219,7 @@ static int xfmr_forward(Ctx& c, const XfmrW& X, const float* x, float* y, int NB
   bf16* ffm = aalloc<bf16>(c, M * 4 * C);
   bf16* hsb = aalloc<bf16>(c, M * C);
 
-  TRY(groupnorm(c, x, a, nullptr, X.gn, NB, T, 1e-6f, 0, gn_ws));
+  TRY(groupnorm(c, x, nullptr, a, nullptr, X.gn, NB, T, 1e-6f, 0));
   { Epi e; e.bias = X.proj_in.b; e.out_f32 = hs0; TRY(linear(c, a, int(M), X.proj_in, e)); }
   // self attention
   const bool no_ln = skip_family("ln"), no_attn = skip_family("attn"), no_x = skip_family("xattn");
@@ -192,7 +236,11 @@ static int xfmr_forward(Ctx& c, const XfmrW& X, const float* x, float* y, int NB
   if (!no_ln) LAUNCH(launch_layernorm(hs0, a, X.ln3.g, X.ln3.b, int(M), C, 1e-5f, c.stream), 1);
   { Epi e; e.bias = X.ff1.b; e.out_bf16 = ffm; e.flags = EPI_GEGLU; TRY(linear(c, a, int(M), X.ff1, e)); }
   { Epi e; e.bias = X.ff2.b; e.residual = hs0; e.out_bf16 = hsb; TRY(linear(c, ffm, int(M), X.ff2, e)); }
-  { Epi e; e.bias = X.proj_out.b; e.residual = x; e.out_f32 = y; TRY(linear(c, hsb, int(M), X.proj_out, e)); }
+  {
+    Epi e; e.bias = X.proj_out.b; e.residual = x.p; e.out_f32 = y.p;
+    emit_stats(c, e, y, NB, T, false);
+    TRY(linear(c, hsb, int(M), X.proj_out, e));
+  }
   c.arena->release(mk);
   return MGB_OK;
 }
@@ -201,7 +249,7 @@ static int xfmr_forward(Ctx& c, const XfmrW& X, const float* x, float* y, int NB
 // VAE mid-block attention: single head, dim C (512), over T = h*w tokens. x, y fp32 [NB*T, C].
 // Scores are materialised per image in bf16 (T x T), softmaxed in place, then P V via V^T.
 // ---------------------------------------------------------------------------------------------
-static int vae_attn_forward(Ctx& c, const VaeAttnW& A, const float* x, float* y, int NB, int T, float* gn_ws) {
+static int vae_attn_forward(Ctx& c, const VaeAttnW& A, Act& x, Act& y, int NB, int T) {
   const int C = A.C;
   const size_t M = size_t(NB) * T;
   const size_t mk = c.arena->mark();
@@ -212,7 +260,7 @@ static int vae_attn_forward(Ctx& c, const VaeAttnW& A, const float* x, float* y,
   bf16* vt = aalloc<bf16>(c, size_t(T) * C);
   bf16* s = aalloc<bf16>(c, size_t(T) * T);
   bf16* o = aalloc<bf16>(c, M * C);
-  TRY(groupnorm(c, x, a, nullptr, A.gn, NB, T, 1e-6f, 0, gn_ws));
+  TRY(groupnorm(c, x, nullptr, a, nullptr, A.gn, NB, T, 1e-6f, 0));
   { Epi e; e.bias = A.q.b; e.out_bf16 = q; TRY(linear(c, a, int(M), A.q, e)); }
   { Epi e; e.bias = A.k.b; e.out_bf16 = k; TRY(linear(c, a, int(M), A.k, e)); }
   { Epi e; e.bias = A.v.b; e.out_bf16 = v; TRY(linear(c, a, int(M), A.v, e)); }
@@ -224,7 +272,7 @@ static int vae_attn_forward(Ctx& c, const VaeAttnW& A, const float* x, float* y,
     LAUNCH(launch_transpose_bf16(v + off, vt, T, C, c.stream), 1);
     { Epi e; e.out_bf16 = o + off; TRY(matmul_nt(c, s, vt, T, C, T, e)); }
   }
-  { Epi e; e.bias = A.o.b; e.residual = x; e.out_f32 = y; TRY(linear(c, o, int(M), A.o, e)); }
+  { Epi e; e.bias = A.o.b; e.residual = x.p; e.out_f32 = y.p; TRY(linear(c, o, int(M), A.o, e)); }
   c.arena->release(mk);
   return MGB_OK;
 }
@@ -233,18 +281,29 @@ static int vae_attn_forward(Ctx& c, const VaeAttnW& A, const float* x, float* y,
 // UNet step. rgb / tgt: fp32 NHWC [NB, lh, lw, 4]. tgt is updated in place by the fused
 // conv_out + scheduler epilogue. raw_out (or null): fp32 NHWC [NB, lh, lw, 4] model output.
 // ---------------------------------------------------------------------------------------------
+static int zero_stats(Ctx& c) {
+  // one memset (a memset node under capture) for every GroupNorm statistic of this graph execution
+  if (c.dry || !c.stat_base || c.stat_cap == 0) return MGB_OK;
+  if (cudaMemsetAsync(c.stat_base, 0, c.stat_cap * sizeof(float), c.stream) != cudaSuccess) {
+    set_error("statistics slab memset failed");
+    return MGB_ERR_CUDA;
+  }
+  return MGB_OK;
+}
+
 int unet_forward(mgb_handle* hd, Ctx& c, const float* rgb, float* tgt, const float* noise, float* raw_out, int step,
                  int NB, int lh, int lw) {
   const UNetW& U = hd->unet;
   const mgb_config& cfg = hd->cfg;
   const int L = cfg.unet_layers_per_block;
   const int* ch = cfg.unet_block_channels;
-  float* gn_ws = hd->gn_ws;
   int H = lh, W = lw;
   size_t M = size_t(NB) * H * W;
+  c.stat_off = 0;
+  c.fuse_stats = true;
+  TRY(zero_stats(c));
 
-  struct Skip { float* p; int c; };
-  std::vector<Skip> skips;
+  std::vector<Act> skips;
   size_t ri = 0, xi = 0;
 
   // step < 0: the step index is read from the device counter (CUDA-graph replay)
@@ -253,75 +312,83 @@ int unet_forward(mgb_handle* hd, Ctx& c, const float* rgb, float* tgt, const flo
   c.cur_bias = hd->cur_bias;
   bf16* x0 = aalloc<bf16>(c, M * 64);
   LAUNCH(launch_pack_latents(rgb, tgt, x0, int(M), c.stream), 1);
-  float* h = aalloc<float>(c, M * ch[0]);
-  { Epi e; e.bias = U.conv_in.b; e.out_f32 = h; TRY(conv3x3(c, x0, NB, H, W, U.conv_in, 0, e)); }
-  skips.push_back({h, ch[0]});
+  Act h = act_alloc(c, M, ch[0], NB);
+  {
+    Epi e; e.bias = U.conv_in.b; e.out_f32 = h.p;
+    emit_stats(c, e, h, NB, H * W, true);
+    TRY(conv3x3(c, x0, NB, H, W, U.conv_in, 0, e));
+  }
+  skips.push_back(h);
   int cur = ch[0];
   // down path
   for (int i = 0; i < 4; ++i) {
     const bool last = i == 3;
     for (int j = 0; j < L; ++j) {
-      float* y = aalloc<float>(c, M * ch[i]);
-      TRY(resnet_forward(c, U.resnets[ri++], h, y, NB, H, W, gn_ws));
+      Act y = act_alloc(c, M, ch[i], NB);
+      TRY(resnet_forward(c, U.resnets[ri++], h, nullptr, y, NB, H, W));
       h = y; cur = ch[i];
       if (!last) {
-        float* y2 = aalloc<float>(c, M * cur);
-        TRY(xfmr_forward(c, U.xfmrs[xi++], h, y2, NB, H * W, gn_ws));
+        Act y2 = act_alloc(c, M, cur, NB);
+        TRY(xfmr_forward(c, U.xfmrs[xi++], h, y2, NB, H * W));
         h = y2;
       }
-      skips.push_back({h, cur});
+      skips.push_back(h);
     }
     if (!last) {
-      const size_t mk = c.arena->mark();
-      (void)mk;
       bf16* planes = aalloc<bf16>(c, M * cur);
-      LAUNCH(launch_space_to_depth(h, planes, NB, H, W, cur, c.stream), 1);
+      LAUNCH(launch_space_to_depth(h.p, planes, NB, H, W, cur, c.stream), 1);
       H /= 2; W /= 2; M = size_t(NB) * H * W;
-      float* y = aalloc<float>(c, M * cur);
-      { Epi e; e.bias = U.downs[i].b; e.out_f32 = y; TRY(conv3x3(c, planes, NB, H, W, U.downs[i], 2, e)); }
+      Act y = act_alloc(c, M, cur, NB);
+      {
+        Epi e; e.bias = U.downs[i].b; e.out_f32 = y.p;
+        emit_stats(c, e, y, NB, H * W, true);
+        TRY(conv3x3(c, planes, NB, H, W, U.downs[i], 2, e));
+      }
       h = y;
-      skips.push_back({h, cur});
+      skips.push_back(h);
     }
   }
   // mid
   {
-    float* y = aalloc<float>(c, M * cur);
-    TRY(resnet_forward(c, U.resnets[ri++], h, y, NB, H, W, gn_ws));
-    float* y2 = aalloc<float>(c, M * cur);
-    TRY(xfmr_forward(c, U.xfmrs[xi++], y, y2, NB, H * W, gn_ws));
-    float* y3 = aalloc<float>(c, M * cur);
-    TRY(resnet_forward(c, U.resnets[ri++], y2, y3, NB, H, W, gn_ws));
+    Act y = act_alloc(c, M, cur, NB);
+    TRY(resnet_forward(c, U.resnets[ri++], h, nullptr, y, NB, H, W));
+    Act y2 = act_alloc(c, M, cur, NB);
+    TRY(xfmr_forward(c, U.xfmrs[xi++], y, y2, NB, H * W));
+    Act y3 = act_alloc(c, M, cur, NB);
+    TRY(resnet_forward(c, U.resnets[ri++], y2, nullptr, y3, NB, H, W));
     h = y3;
   }
-  // up path
+  // up path: the concat [h | skip] is consumed directly by the resnet's GroupNorm
   for (int i = 0; i < 4; ++i) {
     const int cout = ch[3 - i];
     for (int j = 0; j < L + 1; ++j) {
-      Skip s = skips.back();
+      Act sk = skips.back();
       skips.pop_back();
-      float* cat = aalloc<float>(c, M * (cur + s.c));
-      if (!skip_family("concat")) LAUNCH(launch_concat(h, s.p, cat, int(M), cur, s.c, c.stream), 1);
-      float* y = aalloc<float>(c, M * cout);
-      TRY(resnet_forward(c, U.resnets[ri++], cat, y, NB, H, W, gn_ws));
+      Act y = act_alloc(c, M, cout, NB);
+      TRY(resnet_forward(c, U.resnets[ri++], h, &sk, y, NB, H, W));
       h = y; cur = cout;
       if (i > 0) {
-        float* y2 = aalloc<float>(c, M * cur);
-        TRY(xfmr_forward(c, U.xfmrs[xi++], h, y2, NB, H * W, gn_ws));
+        Act y2 = act_alloc(c, M, cur, NB);
+        TRY(xfmr_forward(c, U.xfmrs[xi++], h, y2, NB, H * W));
         h = y2;
       }
     }
     if (i < 3) {
       bf16* up = aalloc<bf16>(c, M * 4 * cur);
-      LAUNCH(launch_upsample2x(h, up, NB, H, W, cur, c.stream), 1);
+      LAUNCH(launch_upsample2x(h.p, up, NB, H, W, cur, c.stream), 1);
       H *= 2; W *= 2; M = size_t(NB) * H * W;
-      float* y = aalloc<float>(c, M * cur);
-      { Epi e; e.bias = U.ups[i].b; e.out_f32 = y; TRY(conv3x3(c, up, NB, H, W, U.ups[i], 0, e)); }
+      Act y = act_alloc(c, M, cur, NB);
+      {
+        Epi e; e.bias = U.ups[i].b; e.out_f32 = y.p;
+        emit_stats(c, e, y, NB, H * W, true);
+        TRY(conv3x3(c, up, NB, H, W, U.ups[i], 0, e));
+      }
       h = y;
     }
   }
   // out: GN -> SiLU -> conv_out fused with the scheduler step
   bf16* t = aalloc<bf16>(c, M * cur);
-  TRY(groupnorm(c, h, t, nullptr, U.norm_out, NB, H * W, 1e-5f, 1, gn_ws));
+  TRY(groupnorm(c, h, nullptr, t, nullptr, U.norm_out, NB, H * W, 1e-5f, 1));
   {
     Epi e;
     e.bias = U.conv_out.b;
@@ -336,50 +403,56 @@ int unet_forward(mgb_handle* hd, Ctx& c, const float* rgb, float* tgt, const flo
 
 // ---------------------------------------------------------------------------------------------
 // VAE encoder: rgb fp32 NCHW [NB,3,H,W] -> latent fp32 NCHW [NB,4,H/8,W/8] (mean * latent_scale)
+// The VAE tensors are HBM-sized (up to 590k pixels): their GroupNorm statistics come from the streaming
+// chan_stats kernel rather than from epilogue atomics (which would contend on 128-512 addresses).
 // ---------------------------------------------------------------------------------------------
 int vae_encode_forward(mgb_handle* hd, Ctx& c, const float* rgb, float* latent_out, int NB, int H, int W) {
   const VaeW& V = hd->vae;
   const mgb_config& cfg = hd->cfg;
   const int* ch = cfg.vae_block_channels;
   const int L = cfg.vae_layers_per_block;
-  float* gn_ws = hd->gn_ws;
   size_t M = size_t(NB) * H * W;
   size_t ri = 0;
+  c.stat_off = 0;
+  c.fuse_stats = false;
+  TRY(zero_stats(c));
   const size_t mk0 = c.arena->mark();
   bf16* x0 = aalloc<bf16>(c, M * 64);
   LAUNCH(launch_pack_rgb(rgb, x0, NB, H * W, c.stream), 1);
-  float* h = aalloc<float>(c, M * ch[0]);
-  { Epi e; e.bias = V.enc_in.b; e.out_f32 = h; TRY(conv3x3(c, x0, NB, H, W, V.enc_in, 0, e)); }
+  Act h = act_alloc(c, M, ch[0], NB);
+  { Epi e; e.bias = V.enc_in.b; e.out_f32 = h.p; TRY(conv3x3(c, x0, NB, H, W, V.enc_in, 0, e)); }
   int cur = ch[0];
   for (int i = 0; i < 4; ++i) {
     // ping-pong trunk buffers for this resolution
-    float* bufA = aalloc<float>(c, M * ch[i]);
-    float* bufB = aalloc<float>(c, M * ch[i]);
+    Act buf[2] = {act_alloc(c, M, ch[i], NB), act_alloc(c, M, ch[i], NB)};
     for (int j = 0; j < L; ++j) {
-      float* y = (j & 1) ? bufB : bufA;
-      TRY(resnet_forward(c, V.enc_res[ri++], h, y, NB, H, W, gn_ws));
+      Act y = buf[j & 1];
+      // a ping-pong buffer is reused: its statistics slot must be a fresh (zeroed) one
+      if (j >= 2) { Act fresh = act_alloc(c, 0, ch[i], NB); y.cs = fresh.cs; }
+      y.cs_valid = false;
+      TRY(resnet_forward(c, V.enc_res[ri++], h, nullptr, y, NB, H, W));
       h = y; cur = ch[i];
     }
     if (i < 3) {
       bf16* planes = aalloc<bf16>(c, M * cur);
-      LAUNCH(launch_space_to_depth(h, planes, NB, H, W, cur, c.stream), 1);
+      LAUNCH(launch_space_to_depth(h.p, planes, NB, H, W, cur, c.stream), 1);
       H /= 2; W /= 2; M = size_t(NB) * H * W;
-      float* y = aalloc<float>(c, M * cur);
-      { Epi e; e.bias = V.enc_down[i].b; e.out_f32 = y; TRY(conv3x3(c, planes, NB, H, W, V.enc_down[i], 3, e)); }
+      Act y = act_alloc(c, M, cur, NB);
+      { Epi e; e.bias = V.enc_down[i].b; e.out_f32 = y.p; TRY(conv3x3(c, planes, NB, H, W, V.enc_down[i], 3, e)); }
       h = y;
     }
   }
   {
-    float* y1 = aalloc<float>(c, M * cur);
-    TRY(resnet_forward(c, V.enc_res[ri++], h, y1, NB, H, W, gn_ws));
-    float* y2 = aalloc<float>(c, M * cur);
-    TRY(vae_attn_forward(c, V.enc_attn, y1, y2, NB, H * W, gn_ws));
-    float* y3 = aalloc<float>(c, M * cur);
-    TRY(resnet_forward(c, V.enc_res[ri++], y2, y3, NB, H, W, gn_ws));
+    Act y1 = act_alloc(c, M, cur, NB);
+    TRY(resnet_forward(c, V.enc_res[ri++], h, nullptr, y1, NB, H, W));
+    Act y2 = act_alloc(c, M, cur, NB);
+    TRY(vae_attn_forward(c, V.enc_attn, y1, y2, NB, H * W));
+    Act y3 = act_alloc(c, M, cur, NB);
+    TRY(resnet_forward(c, V.enc_res[ri++], y2, nullptr, y3, NB, H, W));
     h = y3;
   }
   bf16* t = aalloc<bf16>(c, M * cur);
-  TRY(groupnorm(c, h, t, nullptr, V.enc_norm_out, NB, H * W, 1e-6f, 1, gn_ws));
+  TRY(groupnorm(c, h, nullptr, t, nullptr, V.enc_norm_out, NB, H * W, 1e-6f, 1));
   {
     // conv_out with quant_conv folded in; mean half only; * latent_scale; NCHW output
     Epi e; e.bias = V.enc_out.b; e.out_f32 = latent_out; e.flags = EPI_NCHW | EPI_SCALE; e.scale = cfg.latent_scale;
@@ -397,45 +470,48 @@ int vae_decode_forward(mgb_handle* hd, Ctx& c, const float* latent, float* out, 
   const mgb_config& cfg = hd->cfg;
   const int* ch = cfg.vae_block_channels;
   const int L = cfg.vae_layers_per_block;
-  float* gn_ws = hd->gn_ws;
   int H = lh, W = lw;
   size_t M = size_t(NB) * H * W;
   size_t ri = 0;
+  c.stat_off = 0;
+  c.fuse_stats = false;
+  TRY(zero_stats(c));
   const size_t mk0 = c.arena->mark();
   bf16* z = aalloc<bf16>(c, M * 64);
   LAUNCH(launch_pack_decoder_latent(latent, V.pq_w, V.pq_b, 1.0f / cfg.latent_scale, z, NB, H * W, c.stream), 1);
   int cur = ch[3];
-  float* h = aalloc<float>(c, M * cur);
-  { Epi e; e.bias = V.dec_in.b; e.out_f32 = h; TRY(conv3x3(c, z, NB, H, W, V.dec_in, 0, e)); }
+  Act h = act_alloc(c, M, cur, NB);
+  { Epi e; e.bias = V.dec_in.b; e.out_f32 = h.p; TRY(conv3x3(c, z, NB, H, W, V.dec_in, 0, e)); }
   {
-    float* y1 = aalloc<float>(c, M * cur);
-    TRY(resnet_forward(c, V.dec_res[ri++], h, y1, NB, H, W, gn_ws));
-    float* y2 = aalloc<float>(c, M * cur);
-    TRY(vae_attn_forward(c, V.dec_attn, y1, y2, NB, H * W, gn_ws));
-    float* y3 = aalloc<float>(c, M * cur);
-    TRY(resnet_forward(c, V.dec_res[ri++], y2, y3, NB, H, W, gn_ws));
+    Act y1 = act_alloc(c, M, cur, NB);
+    TRY(resnet_forward(c, V.dec_res[ri++], h, nullptr, y1, NB, H, W));
+    Act y2 = act_alloc(c, M, cur, NB);
+    TRY(vae_attn_forward(c, V.dec_attn, y1, y2, NB, H * W));
+    Act y3 = act_alloc(c, M, cur, NB);
+    TRY(resnet_forward(c, V.dec_res[ri++], y2, nullptr, y3, NB, H, W));
     h = y3;
   }
   for (int i = 0; i < 4; ++i) {
     const int cout = ch[3 - i];
-    float* bufA = aalloc<float>(c, M * cout);
-    float* bufB = aalloc<float>(c, M * cout);
+    Act buf[2] = {act_alloc(c, M, cout, NB), act_alloc(c, M, cout, NB)};
     for (int j = 0; j < L + 1; ++j) {
-      float* y = (j & 1) ? bufB : bufA;
-      TRY(resnet_forward(c, V.dec_res[ri++], h, y, NB, H, W, gn_ws));
+      Act y = buf[j & 1];
+      if (j >= 2) { Act fresh = act_alloc(c, 0, cout, NB); y.cs = fresh.cs; }
+      y.cs_valid = false;
+      TRY(resnet_forward(c, V.dec_res[ri++], h, nullptr, y, NB, H, W));
       h = y; cur = cout;
     }
     if (i < 3) {
       bf16* up = aalloc<bf16>(c, M * 4 * cur);
-      LAUNCH(launch_upsample2x(h, up, NB, H, W, cur, c.stream), 1);
+      LAUNCH(launch_upsample2x(h.p, up, NB, H, W, cur, c.stream), 1);
       H *= 2; W *= 2; M = size_t(NB) * H * W;
-      float* y = aalloc<float>(c, M * cur);
-      { Epi e; e.bias = V.dec_up[i].b; e.out_f32 = y; TRY(conv3x3(c, up, NB, H, W, V.dec_up[i], 0, e)); }
+      Act y = act_alloc(c, M, cur, NB);
+      { Epi e; e.bias = V.dec_up[i].b; e.out_f32 = y.p; TRY(conv3x3(c, up, NB, H, W, V.dec_up[i], 0, e)); }
       h = y;
     }
   }
   bf16* t = aalloc<bf16>(c, M * cur);
-  TRY(groupnorm(c, h, t, nullptr, V.dec_norm_out, NB, H * W, 1e-6f, 1, gn_ws));
+  TRY(groupnorm(c, h, nullptr, t, nullptr, V.dec_norm_out, NB, H * W, 1e-6f, 1));
   {
     Epi e; e.bias = V.dec_out.b; e.out_f32 = out;
     e.flags = mode == MGB_DECODE_DEPTH ? EPI_DEPTH : mode == MGB_DECODE_NORMALS ? EPI_NORMALS : EPI_NCHW;

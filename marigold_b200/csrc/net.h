@@ -70,6 +70,15 @@ struct Arena {
   void release(size_t m) { off = m; }
 };
 
+// A trunk activation: fp32 [M, C] plus (optionally) the per-channel (sum, sum^2) its producer accumulated for
+// the GroupNorm that consumes it (cs: [NB, C, 2]; cs_valid says whether the producer filled it).
+struct Act {
+  float* p = nullptr;
+  int C = 0;
+  float* cs = nullptr;
+  bool cs_valid = false;
+};
+
 struct Ctx {
   cudaStream_t stream = nullptr;
   Arena* arena = nullptr;
@@ -79,6 +88,10 @@ struct Ctx {
   size_t splitk_need = 0;  // bytes needed (dry run)
   int groups = 32;
   const float* cur_bias = nullptr;  // current step's concatenated resnet conv1 biases (device)
+  // per-graph slab of GroupNorm channel statistics (zeroed once at the start of the graph)
+  float* stat_base = nullptr;
+  size_t stat_off = 0, stat_cap = 0, stat_need = 0;
+  bool fuse_stats = true;           // producers emit statistics from their epilogues (UNet); else a stats kernel
 };
 
 struct UNetW {
@@ -147,6 +160,8 @@ struct mgb_handle {
   // small persistent buffers
   float* gn_ws = nullptr;
   size_t gn_ws_bytes = 0;
+  float* stat_slab = nullptr;   // GroupNorm channel statistics of one graph execution
+  size_t stat_slab_bytes = 0;
   // ensemble scratch
   void* ens_ws = nullptr;
   double* ens_pinned = nullptr;  // pinned host, 64 doubles

@@ -16,8 +16,7 @@ namespace mgb {
 
 constexpr int kGnThreads = 256;
 constexpr int kGnMaxK = 4;      // channel-quads per thread
-constexpr int kGnMaxChunks = 592;   // partial-statistics slots per image
-constexpr int kGnMaxImages = 256;   // arrival counters
+constexpr int kGnMaxChunks = 592;   // CTAs per image
 
 struct GnGeom {
   int Q;        // C / 4
@@ -53,15 +52,17 @@ static bool gn_geometry(int HW, int C, GnGeom* g) {
 }
 
 size_t groupnorm_ws_bytes(int NB, int HW, int C, int G) {
-  (void)HW; (void)C;
-  // [arrival counters: kGnMaxImages, FIXED offset 0 so that they stay valid (zero) across calls with
-  //  different NB][mean|rstd NB x 2G][partials NB x kGnMaxChunks x G x 2]
-  return (size_t(kGnMaxImages) + size_t(NB) * 2 * G + size_t(NB) * kGnMaxChunks * G * 2) * sizeof(float);
+  (void)HW; (void)G;
+  return size_t(NB) * C * 2 * sizeof(float);   // per-channel (sum, sum of squares)
 }
 
-__global__ void __launch_bounds__(kGnThreads) gn_stats_kernel(const float* __restrict__ x, float* __restrict__ ws,
-                                                              float* __restrict__ stat, unsigned* __restrict__ counters,
-                                                              int HW, int C, int G, float eps, GnGeom g) {
+// -------------------------------------------------------------------------------------------------
+// Per-channel statistics of x [NB, HW, C]: cs[(img * C + c) * 2 + {0,1}] += (sum, sum of squares).
+// Only used where the producer could not emit them from its epilogue (VAE-sized tensors, ragged token
+// tiles); cs must be zero on entry.
+// -------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kGnThreads) chan_stats_kernel(const float* __restrict__ x, float* __restrict__ cs,
+                                                                int HW, int C, GnGeom g) {
   extern __shared__ float s_acc[];  // [2 * C]
   pdl_launch_dependents();
   pdl_wait();
@@ -115,105 +116,97 @@ __global__ void __launch_bounds__(kGnThreads) gn_stats_kernel(const float* __res
     }
   }
   __syncthreads();
-  const int cpg = C / G;
-  for (int gi = threadIdx.x; gi < G; gi += blockDim.x) {
-    float s = 0.f, q = 0.f;
-    for (int c = gi * cpg; c < (gi + 1) * cpg; ++c) { s += s_acc[c]; q += s_acc[C + c]; }
-    float* dst = ws + (((size_t)img * kGnMaxChunks + chunk) * G + gi) * 2;
-    dst[0] = s; dst[1] = q;
-  }
-  // last CTA of this image combines the partials into mean / rstd (so gn_apply starts with 2G floats)
-  __shared__ bool s_last;
-  __shared__ double s_part[2][kGnThreads];
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) s_last = atomicAdd(counters + img, 1u) == gridDim.x - 1;
-  __syncthreads();
-  if (!s_last) return;
-  __threadfence();
-  {
-    const int slices = kGnThreads / G;
-    const int gi = threadIdx.x % G, sl = threadIdx.x / G;
-    double s = 0.0, q = 0.0;
-    if (sl < slices) {
-#pragma unroll 4
-      for (int ch = sl; ch < int(gridDim.x); ch += slices) {
-        const float2 v = __ldcg(reinterpret_cast<const float2*>(ws + (((size_t)img * kGnMaxChunks + ch) * G + gi) * 2));
-        s += double(v.x); q += double(v.y);
-      }
-    }
-    s_part[0][threadIdx.x] = s; s_part[1][threadIdx.x] = q;
-    __syncthreads();
-    if (threadIdx.x < G) {
-      s = 0.0; q = 0.0;
-      for (int k = 0; k < slices; ++k) { s += s_part[0][k * G + threadIdx.x]; q += s_part[1][k * G + threadIdx.x]; }
-      const double n = double(HW) * cpg;
-      const double mean = s / n;
-      double var = q / n - mean * mean;
-      if (var < 0.0) var = 0.0;
-      stat[(size_t)img * 2 * G + threadIdx.x] = float(mean);
-      stat[(size_t)img * 2 * G + G + threadIdx.x] = rsqrtf(float(var) + eps);
-    }
-    if (threadIdx.x == 0) counters[img] = 0;   // self-resetting
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    atomicAdd(cs + ((size_t)img * C + c) * 2, s_acc[c]);
+    atomicAdd(cs + ((size_t)img * C + c) * 2 + 1, s_acc[C + c]);
   }
 }
 
+// -------------------------------------------------------------------------------------------------
+// GroupNorm apply over the channel concatenation [a | b] (b optional): group statistics come from the
+// per-channel sums of each source; y = act((x - mean) * rstd * gamma + beta) as bf16 [NB, HW, Ca + Cb];
+// optionally also the raw bf16 copy of [a | b] (operand of a ResnetBlock's 1x1 shortcut conv).
+// This is torch.cat(dim=1) + GroupNorm (+SiLU) of diffusers' up-block resnets in one pass.
+// -------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kGnThreads)
-    gn_apply_kernel(const float* __restrict__ x, bf16* __restrict__ y, bf16* __restrict__ raw,
-                    const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ stat,
-                    int HW, int C, int G, int silu, GnGeom g) {
+    gn_apply2_kernel(const float* __restrict__ xa, const float* __restrict__ csa, int Ca, const float* __restrict__ xb,
+                     const float* __restrict__ csb, int Cb, bf16* __restrict__ y, bf16* __restrict__ raw,
+                     const float* __restrict__ gamma, const float* __restrict__ beta, int HW, int G, float eps, int silu,
+                     GnGeom g) {
   extern __shared__ float s_stat[];  // mean[G], rstd[G]
   pdl_launch_dependents();
   pdl_wait();
   const int img = blockIdx.y, chunk = blockIdx.x;
-  const int cpg = C / G;
-  for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) s_stat[i] = __ldcg(stat + (size_t)img * 2 * G + i);
+  const int C = Ca + Cb, cpg = C / G;
+  {
+    // 8 lanes per group, then a shuffle reduction (G * 8 <= 256 threads)
+    const int gi = threadIdx.x >> 3, part = threadIdx.x & 7;
+    double s = 0.0, q = 0.0;
+    if (gi < G) {
+      for (int j = part; j < cpg; j += 8) {
+        const int c = gi * cpg + j;
+        const float2 v = c < Ca ? __ldcg(reinterpret_cast<const float2*>(csa + ((size_t)img * Ca + c) * 2))
+                                : __ldcg(reinterpret_cast<const float2*>(csb + ((size_t)img * Cb + (c - Ca)) * 2));
+        s += double(v.x); q += double(v.y);
+      }
+    }
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) {
+      s += __shfl_xor_sync(0xffffffffu, s, o);
+      q += __shfl_xor_sync(0xffffffffu, q, o);
+    }
+    if (gi < G && part == 0) {
+      const double n = double(HW) * cpg;
+      const double mean = s / n;
+      double var = q / n - mean * mean;
+      if (var < 0.0) var = 0.0;
+      s_stat[gi] = float(mean);
+      s_stat[G + gi] = rsqrtf(float(var) + eps);
+    }
+  }
   __syncthreads();
   const int tq = threadIdx.x % g.Tq, tp = threadIdx.x / g.Tq;
   if (tp >= g.Tp) return;
   const int p0 = chunk * g.P, p1 = min(HW, p0 + g.P);
-  const float4* xi = reinterpret_cast<const float4*>(x + (size_t)img * HW * C);
+  const int Qa = Ca / 4, Qb = Cb / 4;
+  const float4* xai = reinterpret_cast<const float4*>(xa + (size_t)img * HW * Ca);
+  const float4* xbi = xb ? reinterpret_cast<const float4*>(xb + (size_t)img * HW * Cb) : nullptr;
   uint2* yo = reinterpret_cast<uint2*>(y + (size_t)img * HW * C);
   uint2* ro = raw ? reinterpret_cast<uint2*>(raw + (size_t)img * HW * C) : nullptr;
-  float sc[kGnMaxK][4], sh[kGnMaxK][4];
-#pragma unroll
-  for (int k = 0; k < kGnMaxK; ++k) {
-    if (k < g.Kq) {
-      const int c0 = 4 * (tq + k * g.Tq);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int c = c0 + j, gi = c / cpg;
-        const float ga = gamma ? __ldg(gamma + c) : 1.f, be = beta ? __ldg(beta + c) : 0.f;
-        sc[k][j] = s_stat[G + gi] * ga;
-        sh[k][j] = be - s_stat[gi] * s_stat[G + gi] * ga;
-      }
-    }
-  }
 #pragma unroll
   for (int k = 0; k < kGnMaxK; ++k) {
     if (k >= g.Kq) break;
-    const float s0 = sc[k][0], s1 = sc[k][1], s2 = sc[k][2], s3 = sc[k][3];
-    const float h0 = sh[k][0], h1 = sh[k][1], h2 = sh[k][2], h3 = sh[k][3];
-    const size_t qoff = size_t(tq) + size_t(k) * g.Tq;
+    const int qd = tq + k * g.Tq;                 // quad index in the concatenated channel space
+    float sc[4], sh[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int c = 4 * qd + j, gi = c / cpg;
+      const float ga = gamma ? __ldg(gamma + c) : 1.f, be = beta ? __ldg(beta + c) : 0.f;
+      sc[j] = s_stat[G + gi] * ga;
+      sh[j] = be - s_stat[gi] * s_stat[G + gi] * ga;
+    }
+    const bool from_a = qd < Qa;
+    const float4* src = from_a ? xai + qd : xbi + (qd - Qa);
+    const size_t sstride = from_a ? size_t(Qa) : size_t(Qb);
     int p = p0 + tp;
-    // 4 pixels per trip: the loads are issued back to back, then consumed
     for (; p + 3 * g.Tp < p1; p += 4 * g.Tp) {
       float4 v[4];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) v[u] = __ldg(xi + (size_t)(p + u * g.Tp) * g.Q + qoff);
+      for (int u = 0; u < 4; ++u) v[u] = __ldg(src + (size_t)(p + u * g.Tp) * sstride);
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        const size_t idx = (size_t)(p + u * g.Tp) * g.Q + qoff;
-        float o0 = v[u].x * s0 + h0, o1 = v[u].y * s1 + h1, o2 = v[u].z * s2 + h2, o3 = v[u].w * s3 + h3;
+        const size_t idx = (size_t)(p + u * g.Tp) * g.Q + qd;
+        float o0 = v[u].x * sc[0] + sh[0], o1 = v[u].y * sc[1] + sh[1], o2 = v[u].z * sc[2] + sh[2],
+              o3 = v[u].w * sc[3] + sh[3];
         if (silu) { o0 = silu_f(o0); o1 = silu_f(o1); o2 = silu_f(o2); o3 = silu_f(o3); }
         yo[idx] = make_uint2(pack_bf16x2(o0, o1), pack_bf16x2(o2, o3));
         if (ro) ro[idx] = make_uint2(pack_bf16x2(v[u].x, v[u].y), pack_bf16x2(v[u].z, v[u].w));
       }
     }
     for (; p < p1; p += g.Tp) {
-      const size_t idx = (size_t)p * g.Q + qoff;
-      const float4 v = __ldg(xi + idx);
-      float o0 = v.x * s0 + h0, o1 = v.y * s1 + h1, o2 = v.z * s2 + h2, o3 = v.w * s3 + h3;
+      const size_t idx = (size_t)p * g.Q + qd;
+      const float4 v = __ldg(src + (size_t)p * sstride);
+      float o0 = v.x * sc[0] + sh[0], o1 = v.y * sc[1] + sh[1], o2 = v.z * sc[2] + sh[2], o3 = v.w * sc[3] + sh[3];
       if (silu) { o0 = silu_f(o0); o1 = silu_f(o1); o2 = silu_f(o2); o3 = silu_f(o3); }
       yo[idx] = make_uint2(pack_bf16x2(o0, o1), pack_bf16x2(o2, o3));
       if (ro) ro[idx] = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
@@ -221,26 +214,41 @@ __global__ void __launch_bounds__(kGnThreads)
   }
 }
 
-int launch_groupnorm(const float* x, bf16* y, bf16* raw_copy, const float* gamma, const float* beta, float* ws,
-                     int NB, int HW, int C, int G, float eps, int silu, cudaStream_t stream) {
+int launch_chan_stats(const float* x, float* cs, int NB, int HW, int C, cudaStream_t stream) {
   GnGeom g;
-  if (C % G != 0 || G > kGnThreads || kGnThreads % G != 0 || NB > kGnMaxImages || !gn_geometry(HW, C, &g)) {
-    set_error("groupnorm: unsupported C=%d G=%d", C, G);
+  if (!gn_geometry(HW, C, &g)) { set_error("chan_stats: unsupported C=%d", C); return MGB_ERR_INVALID; }
+  dim3 grid(g.chunks, NB);
+  cudaError_t e = launch_k(chan_stats_kernel, grid, kGnThreads, 2 * C * sizeof(float), stream, x, cs, HW, C, g);
+  if (e == cudaSuccess) e = cudaGetLastError();
+  if (e != cudaSuccess) { set_error("chan_stats launch: %s", cudaGetErrorString(e)); return MGB_ERR_CUDA; }
+  return MGB_OK;
+}
+
+int launch_gn_apply2(const float* xa, const float* csa, int Ca, const float* xb, const float* csb, int Cb, bf16* y,
+                     bf16* raw_copy, const float* gamma, const float* beta, int NB, int HW, int G, float eps, int silu,
+                     cudaStream_t stream) {
+  GnGeom g;
+  const int C = Ca + Cb;
+  if (C % G != 0 || G * 8 > kGnThreads || (Ca & 3) || (Cb & 3) || !gn_geometry(HW, C, &g)) {
+    set_error("groupnorm: unsupported C=%d+%d G=%d", Ca, Cb, G);
     return MGB_ERR_INVALID;
   }
   dim3 grid(g.chunks, NB);
-  unsigned* counters = reinterpret_cast<unsigned*>(ws);
-  float* stat = ws + kGnMaxImages;
-  float* partials = stat + size_t(NB) * 2 * G;
-  launch_k(gn_stats_kernel, grid, kGnThreads, 2 * C * sizeof(float), stream, x, partials, stat, counters, HW, C, G, eps, g);
-  launch_k(gn_apply_kernel, grid, kGnThreads, 2 * G * sizeof(float), stream, x, y, raw_copy, gamma, beta,
-           static_cast<const float*>(stat), HW, C, G, silu, g);
-  cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) {
-    set_error("groupnorm launch: %s", cudaGetErrorString(e));
-    return MGB_ERR_CUDA;
-  }
+  cudaError_t e = launch_k(gn_apply2_kernel, grid, kGnThreads, 2 * G * sizeof(float), stream, xa, csa, Ca, xb, csb, Cb, y,
+                           raw_copy, gamma, beta, HW, G, eps, silu, g);
+  if (e == cudaSuccess) e = cudaGetLastError();
+  if (e != cudaSuccess) { set_error("groupnorm launch: %s", cudaGetErrorString(e)); return MGB_ERR_CUDA; }
   return MGB_OK;
+}
+
+// Stand-alone GroupNorm (operator-level ABI): ws = per-channel stats scratch [NB, C, 2] (zeroed here).
+int launch_groupnorm(const float* x, bf16* y, bf16* raw_copy, const float* gamma, const float* beta, float* ws,
+                     int NB, int HW, int C, int G, float eps, int silu, cudaStream_t stream) {
+  cudaError_t e = cudaMemsetAsync(ws, 0, size_t(NB) * C * 2 * sizeof(float), stream);
+  if (e != cudaSuccess) { set_error("groupnorm memset: %s", cudaGetErrorString(e)); return MGB_ERR_CUDA; }
+  int rc = launch_chan_stats(x, ws, NB, HW, C, stream);
+  if (rc) return rc;
+  return launch_gn_apply2(x, ws, C, nullptr, nullptr, 0, y, raw_copy, gamma, beta, NB, HW, G, eps, silu, stream);
 }
 
 // -------------------------------------------------------------------------------------------------

@@ -126,8 +126,8 @@ int run_gemm(GemmParams& p, int block_n, float* splitk_ws, cudaStream_t stream) 
       set_error("split-K requested without a workspace");
       return MGB_ERR_INVALID;
     }
-    if (p.epi.flags & (EPI_SCHED | EPI_DEPTH | EPI_NORMALS | EPI_NCHW)) {
-      set_error("split-K is not supported with small-N special epilogues");
+    if (p.epi.flags & (EPI_SCHED | EPI_DEPTH | EPI_NORMALS | EPI_NCHW | EPI_GEGLU)) {
+      set_error("split-K is not supported with GEGLU or the small-N special epilogues");
       return MGB_ERR_INVALID;
     }
     p.partial = splitk_ws;

@@ -36,7 +36,6 @@ def _cases():
     add("linear_geglu", case_linear, M=2304, N=5120, K=640, block_n=256, bias=True, geglu=True, bf16out=True)
     add("linear_geglu_bn128", case_linear, M=300, N=512, K=128, block_n=128, bias=True, geglu=True)
     add("linear_splitk4", case_linear, M=144, N=1280, K=5120, block_n=128, splits=4, bias=True, residual=True)
-    add("linear_splitk_geglu", case_linear, M=144, N=2560, K=1280, block_n=128, splits=3, bias=True, geglu=True)
     add("linear_stages2", case_linear, M=512, N=256, K=1024, block_n=128, stages=2)
     add("linear_silu_scale", case_linear, M=256, N=128, K=256, block_n=128, bias=True, silu=True)
     add("linear_n_ragged", case_linear, M=256, N=200, K=128, block_n=128, bias=True)
