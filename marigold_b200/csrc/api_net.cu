@@ -732,6 +732,10 @@ int mgb_decode(mgb_handle* h, const float* latent, int32_t B, int32_t lh, int32_
   return MGB_OK;
 }
 
+/* debug hooks (not in the public header) */
+void mgb_debug_set_fuse_stats(mgb_handle* h, int on) { if (h) h->dbg_fuse_stats = on != 0; }
+void* mgb_debug_stat_slab(mgb_handle* h, size_t* nfloats) { if (nfloats) *nfloats = h->stat_slab_bytes / 4; return h->stat_slab; }
+
 size_t mgb_workspace_bytes(mgb_handle* h, int32_t B, int32_t H, int32_t W) {
   if (!h || !h->finalized || B <= 0 || H % 64 || W % 64) return 0;
   size_t peak = 0;

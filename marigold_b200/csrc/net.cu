@@ -300,7 +300,7 @@ int unet_forward(mgb_handle* hd, Ctx& c, const float* rgb, float* tgt, const flo
   int H = lh, W = lw;
   size_t M = size_t(NB) * H * W;
   c.stat_off = 0;
-  c.fuse_stats = true;
+  c.fuse_stats = hd->dbg_fuse_stats;
   TRY(zero_stats(c));
 
   std::vector<Act> skips;

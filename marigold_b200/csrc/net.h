@@ -160,6 +160,7 @@ struct mgb_handle {
   // small persistent buffers
   float* gn_ws = nullptr;
   size_t gn_ws_bytes = 0;
+  bool dbg_fuse_stats = true;   // debug: false -> every GroupNorm input goes through the stats kernel
   float* stat_slab = nullptr;   // GroupNorm channel statistics of one graph execution
   size_t stat_slab_bytes = 0;
   // ensemble scratch
