@@ -28,6 +28,7 @@ const char* mgb_build_info(void) {
 }
 int64_t mgb_launch_count(void) { return launch_count(); }
 /* debug hook (not in the public header): per-CTA clock64 phase stamps of subsequent GEMM launches */
+void mgb_debug_gemm_cstat(void* dev_buffer, int hw) { set_gemm_debug_cstat(reinterpret_cast<float*>(dev_buffer), hw); }
 void mgb_debug_gemm_timing(void* dev_buffer) { set_gemm_debug_buffer(reinterpret_cast<long long*>(dev_buffer)); }
 
 static void fill_epi(GemmEpilogue* e, const float* bias, const float* residual, float* out_f32, void* out_bf16,

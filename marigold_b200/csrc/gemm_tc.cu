@@ -558,10 +558,16 @@ __global__ void __launch_bounds__(kSkThreads) splitk_epilogue_kernel(const GemmP
 static long long* g_gemm_dbg = nullptr;
 void set_gemm_debug_buffer(long long* dev_ptr) { g_gemm_dbg = dev_ptr; }
 
+
+static float* g_dbg_cstat = nullptr;
+static int g_dbg_cstat_hw = 0;
+void set_gemm_debug_cstat(float* p, int hw) { g_dbg_cstat = p; g_dbg_cstat_hw = hw; }
+
 template <int BN>
 static int launch_one(const GemmParams& p_in, int splits, cudaStream_t stream) {
   GemmParams p = p_in;
   p.dbg = g_gemm_dbg;
+  if (g_dbg_cstat) { p.epi.cstat = g_dbg_cstat; p.epi.hw = g_dbg_cstat_hw; }
   const size_t smem = gemm_smem_bytes(BN, p.stages);
   static bool attr_set = false;  // per template instantiation
   if (!attr_set) {
@@ -593,8 +599,10 @@ int launch_gemm_tc(const GemmParams& p, int block_n, int splits, cudaStream_t st
   }
 }
 
-int launch_splitk_epilogue(const GemmParams& p, int block_n, int splits, cudaStream_t stream) {
+int launch_splitk_epilogue(const GemmParams& p_in, int block_n, int splits, cudaStream_t stream) {
   (void)block_n;
+  GemmParams p = p_in;
+  if (g_dbg_cstat) { p.epi.cstat = g_dbg_cstat; p.epi.hw = g_dbg_cstat_hw; }
   if ((p.epi.flags & EPI_GEGLU) || (p.N & 3) || (p.epi.ldo & 3) || p.N / 4 > kSkThreads * kSkQuads) {
     set_error("split-K epilogue: unsupported shape/flags (N=%d ldo=%d flags=%d)", p.N, p.epi.ldo, p.epi.flags);
     return int(cudaErrorInvalidValue);

@@ -71,6 +71,7 @@ struct GemmParams {
 // Launch. block_n in {16, 32, 64, 128, 160, 256}. Returns cudaError_t as int.
 int launch_gemm_tc(const GemmParams& p, int block_n, int splits, cudaStream_t stream);
 void set_gemm_debug_buffer(long long* dev_ptr);  // debug hook: phase timestamps of subsequent launches
+void set_gemm_debug_cstat(float* p, int hw);     // debug hook: force channel statistics output
 // Deferred epilogue for split-K: sums `splits` partials and applies p.epi.
 int launch_splitk_epilogue(const GemmParams& p, int block_n, int splits, cudaStream_t stream);
 size_t gemm_smem_bytes(int block_n, int stages);

@@ -50,5 +50,10 @@ print("first mismatching slab indices:", bad[:20].tolist(), "count", bad.numel()
 if bad.numel():
     i = int(bad[0])
     print("around first mismatch (kernel-path vs fused):", a[i:i + 8].tolist(), b[i:i + 8].tolist())
-# walk the slab in (channels*2*B)-sized records of the tiny config to name the tensor index
+nz = (b != 0)
+chg = (nz[1:] != nz[:-1]).nonzero().flatten().tolist()
+print('fused slab: nonzero fraction', nz.float().mean().item(), 'segment boundaries', chg[:40])
+nz0 = (a != 0)
+chg0 = (nz0[1:] != nz0[:-1]).nonzero().flatten().tolist()
+print('kernel-path slab: nonzero fraction', nz0.float().mean().item(), 'segment boundaries', chg0[:40])
 eng.close()
