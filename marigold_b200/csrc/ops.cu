@@ -117,6 +117,12 @@ int run_gemm(GemmParams& p, int block_n, float* splitk_ws, cudaStream_t stream) 
     set_error("GEGLU epilogue needs block_n %% 64 == 0 (got %d)", block_n);
     return MGB_ERR_INVALID;
   }
+  if (p.epi.cstat && (block_n < 32 || (p.epi.flags & (EPI_GEGLU | EPI_SILU)) || (p.N & 31) || (p.epi.ldo & 3) ||
+                      p.epi.hw <= 0)) {
+    set_error("gemm: channel statistics need block_n >= 32, N %% 32 == 0 and a plain epilogue (block_n=%d N=%d)", block_n,
+              p.N);
+    return MGB_ERR_INVALID;
+  }
   if (p.stages < 2 || gemm_smem_bytes(block_n, p.stages) > 227 * 1024) {
     set_error("gemm: stages=%d does not fit shared memory for block_n=%d", p.stages, block_n);
     return MGB_ERR_INVALID;
@@ -161,6 +167,7 @@ void choose_tile(int m_tiles, int N, int num_kb, bool geglu, bool allow_split, i
   for (int bn : cands) {
     if (geglu && (bn % 64 != 0)) continue;
     if (bn > 64 && N < bn / 2 + 1) continue;  // mostly padding
+    if (bn < 64 && N >= 64) continue;         // 16 / 32 wide tiles are for the tiny heads only (N <= 32)
     const int n_tiles = (N + bn - 1) / bn;
     const double waste = double(n_tiles) * bn / N;  // MMA work on padded columns is still paid
     (void)waste;
