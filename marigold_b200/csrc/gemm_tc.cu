@@ -361,6 +361,13 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
       const bool silu = !raw && (e.flags & EPI_SILU);
       const bool ld_vec = (ldo & 3) == 0;
       float* cstat = raw ? nullptr : e.cstat;
+      // per-CTA column (sum, sum^2) in the drained B pipeline memory; one RED per column and moment per CTA
+      float* colsum = reinterpret_cast<float*>(smem_b + size_t(stages) * kBBytes) - 2 * BLOCK_N;   // tail of the B ring
+      const int etid = threadIdx.x - 64;
+      if (cstat) {
+        for (int i = etid; i < 2 * BLOCK_N; i += 128) colsum[i] = 0.f;
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+      }
       const int stat_img = p.mode == 1 ? img : int(((long long)m_tile * BLOCK_M) / (e.hw > 0 ? e.hw : 1));
       // row addressing hoisted out of the chunk loop: after the transpose this lane stores rows
       // R = it * 4 + (lane >> 3), it = 0..7, of its warp's 32-row slab
@@ -401,8 +408,11 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
           if (nv > 1) b4.y = __ldg(bias + acc_col + 1);
           if (nv > 2) b4.z = __ldg(bias + acc_col + 2);
         }
+        // warp-uniform: the whole 32-column chunk is inside the matrix (the fast path uses full-mask shuffles)
+        const int chunk_nv = n_out - (col - c4);
+        if (chunk_nv <= 0) { __syncwarp(); continue; }
         const bool vec = ld_vec && nv >= 4;
-        if (!geglu && !silu && vec) {
+        if (!geglu && !silu && ld_vec && chunk_nv >= 32) {
           // fast path. All 8 scratch loads and all 8 residual loads are issued BEFORE anything is consumed:
           // with one epilogue warp per scheduler nothing else hides a ~600-cycle LDG per row.
           float4 x[8], rr[8];
@@ -442,7 +452,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
               cq[k] += __shfl_xor_sync(0xffffffffu, cq[k], 16);
             }
             if (sub == 0) {
-              float* dst = cstat + ((long long)stat_img * ldo + col) * 2;
+              float* dst = colsum + (j * 32 + c4) * 2;      // per-CTA column sums (4 warps -> 1)
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
                 atomicAdd(dst + 2 * k, cs[k]);
@@ -483,6 +493,13 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
         }
         __syncwarp();
         if (dbg && j < 2 && threadIdx.x == 64) { dbg[6 + j] = ((c1 - c0) << 32) | (clock64() - c1); }
+      }
+      if (cstat) {
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        for (int i = etid; i < 2 * BLOCK_N; i += 128) {
+          const int cidx = n0 + (i >> 1);
+          if (cidx < n_out) atomicAdd(cstat + ((long long)stat_img * ldo + cidx) * 2 + (i & 1), colsum[i]);
+        }
       }
     }
     if (dbg && threadIdx.x == 64) dbg[4] = clock64();
