@@ -20,7 +20,8 @@ eng = engine_from_oracle(unet, vae, text)
 s = DDIMScheduler(); s.set_timesteps(2)
 eng.set_schedule(s.timesteps, *s.coefficients())
 g = torch.Generator().manual_seed(0)
-B, lh, lw = int(sys.argv[1]) if len(sys.argv) > 1 else 1, 16, 16
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 1
+lh, lw = (int(sys.argv[2]), int(sys.argv[3])) if len(sys.argv) > 3 else (16, 16)
 rgb = torch.randn(B, 4, lh, lw, generator=g).cuda(); x = torch.randn(B, 4, lh, lw, generator=g).cuda()
 slabs = {}
 outs = {}
@@ -44,16 +45,38 @@ for mode in (0, 1):
     outs[mode] = mo.cpu()
     print("mode", mode, "nan in model out:", torch.isnan(mo).sum().item(), "slab floats", n.value)
 a, b = slabs[0], slabs[1]
-d = (a - b).abs() / (a.abs() + 1e-3)
-bad = (d > 1e-3).nonzero().flatten()
-print("first mismatching slab indices:", bad[:20].tolist(), "count", bad.numel(), "of", a.numel())
-if bad.numel():
-    i = int(bad[0])
-    print("around first mismatch (kernel-path vs fused):", a[i:i + 8].tolist(), b[i:i + 8].tolist())
-nz = (b != 0)
-chg = (nz[1:] != nz[:-1]).nonzero().flatten().tolist()
-print('fused slab: nonzero fraction', nz.float().mean().item(), 'segment boundaries', chg[:40])
-nz0 = (a != 0)
-chg0 = (nz0[1:] != nz0[:-1]).nonzero().flatten().tolist()
-print('kernel-path slab: nonzero fraction', nz0.float().mean().item(), 'segment boundaries', chg0[:40])
+# allocation order of unet_forward (tiny config: ch = [64,128,256,256], L = 2)
+ch, L = [64, 128, 256, 256], 2
+recs = [("conv_in", ch[0])]
+for i in range(4):
+    for j in range(L):
+        recs.append((f"down{i}.res{j}.y", ch[i])); recs.append((f"down{i}.res{j}.h", ch[i]))
+        if i < 3:
+            recs.append((f"down{i}.xf{j}.y", ch[i]))
+    if i < 3:
+        recs.append((f"down{i}.ds", ch[i]))
+recs += [("mid.res0.y", ch[3]), ("mid.res0.h", ch[3]), ("mid.xf.y", ch[3]), ("mid.res1.y", ch[3]), ("mid.res1.h", ch[3])]
+for i in range(4):
+    co = ch[3 - i]
+    for j in range(L + 1):
+        recs.append((f"up{i}.res{j}.y", co)); recs.append((f"up{i}.res{j}.h", co))
+        if i > 0:
+            recs.append((f"up{i}.xf{j}.y", co))
+    if i < 3:
+        recs.append((f"up{i}.us", co))
+off = 0
+for name, C_ in recs:
+    n = B * C_ * 2
+    ra, rb = a[off:off + n], b[off:off + n]
+    rel = ((ra - rb).abs() / (ra.abs() + 1e-2)).max().item() if n else 0
+    flag = "" if rel < 1e-3 else "   <-- MISMATCH"
+    if flag or ra.abs().max() == 0:
+        print(f"{name:16s} C={C_:4d} off={off:6d} max_rel={rel:.3e} ref_absmax={ra.abs().max().item():.3g} fused_absmax={rb.abs().max().item():.3g}{flag}")
+    off += n
+print("slab used", off, "of", a.numel())
+# timing of both modes
+import time
+for mode in (0, 1):
+    raw.mgb_debug_set_fuse_stats(eng._h, mode)
+    t = x.clone(); eng.unet_step(rgb, t, 0); torch.cuda.synchronize()
 eng.close()
