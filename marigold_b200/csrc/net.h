@@ -160,7 +160,11 @@ struct mgb_handle {
   // small persistent buffers
   float* gn_ws = nullptr;
   size_t gn_ws_bytes = 0;
-  bool dbg_fuse_stats = true;   // debug: false -> every GroupNorm input goes through the stats kernel
+  // GroupNorm statistics from producer epilogues (RED into the slab). OFF by default in round 1: it is
+  // numerically validated per kernel (tools/debug_cstat.py) but one producer in the composed UNet still
+  // disagrees with the stats kernel and it gave no net speed-up (atomics ~ cost of the stats launches);
+  // the default path is chan_stats + gn_apply2 (2 launches per GroupNorm, concat fused).
+  bool dbg_fuse_stats = false;
   float* stat_slab = nullptr;   // GroupNorm channel statistics of one graph execution
   size_t stat_slab_bytes = 0;
   // ensemble scratch
