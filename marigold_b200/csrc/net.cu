@@ -135,7 +135,6 @@ static Act act_alloc(Ctx& c, size_t M, int C, int NB) {
   c.stat_off += n;
   if (c.stat_off > c.stat_need) c.stat_need = c.stat_off;
   a.cs = c.dry ? nullptr : (c.stat_off <= c.stat_cap ? c.stat_base + off : nullptr);
-  a.cs_valid = false;
   return a;
 }
 
@@ -146,7 +145,7 @@ static void emit_stats(Ctx& c, Epi& e, Act& y, int NB, int hw, bool conv_mode) {
   if (!conv_mode && NB > 1 && (hw % 128) != 0) return;
   e.cstat = y.cs;
   e.hw = hw;
-  y.cs_valid = true;
+  c.stat_filled.insert(y.cs);
 }
 
 // GroupNorm (+SiLU) over [a | b] (b.p == nullptr: single source) -> bf16 operand; stats come from the
@@ -156,11 +155,12 @@ static int groupnorm(Ctx& c, Act& a, Act* b, bf16* y, bf16* raw, const NormW& n,
   if (c.dry) return MGB_OK;
   Act* srcs[2] = {&a, b};
   for (Act* t : srcs) {
-    if (!t || !t->p || t->cs_valid) continue;
+    if (!t || !t->p) continue;
     if (!t->cs) { set_error("groupnorm: statistics slab exhausted"); return MGB_ERR_STATE; }
+    if (c.stat_filled.count(t->cs)) continue;
     TRY(launch_chan_stats(t->p, t->cs, NB, HW, t->C, c.stream));
     count_launch(1);
-    t->cs_valid = true;
+    c.stat_filled.insert(t->cs);
   }
   TRY(launch_gn_apply2(a.p, a.cs, a.C, b ? b->p : nullptr, b ? b->cs : nullptr, b ? b->C : 0, y, raw, n.g, n.b, NB, HW,
                        c.groups, eps, silu, c.stream));
@@ -282,6 +282,7 @@ static int vae_attn_forward(Ctx& c, const VaeAttnW& A, Act& x, Act& y, int NB, i
 // conv_out + scheduler epilogue. raw_out (or null): fp32 NHWC [NB, lh, lw, 4] model output.
 // ---------------------------------------------------------------------------------------------
 static int zero_stats(Ctx& c) {
+  c.stat_filled.clear();
   // one memset (a memset node under capture) for every GroupNorm statistic of this graph execution
   if (c.dry || !c.stat_base || c.stat_cap == 0) return MGB_OK;
   if (cudaMemsetAsync(c.stat_base, 0, c.stat_cap * sizeof(float), c.stream) != cudaSuccess) {
@@ -429,7 +430,6 @@ int vae_encode_forward(mgb_handle* hd, Ctx& c, const float* rgb, float* latent_o
       Act y = buf[j & 1];
       // a ping-pong buffer is reused: its statistics slot must be a fresh (zeroed) one
       if (j >= 2) { Act fresh = act_alloc(c, 0, ch[i], NB); y.cs = fresh.cs; }
-      y.cs_valid = false;
       TRY(resnet_forward(c, V.enc_res[ri++], h, nullptr, y, NB, H, W));
       h = y; cur = ch[i];
     }
@@ -497,7 +497,6 @@ int vae_decode_forward(mgb_handle* hd, Ctx& c, const float* latent, float* out, 
     for (int j = 0; j < L + 1; ++j) {
       Act y = buf[j & 1];
       if (j >= 2) { Act fresh = act_alloc(c, 0, cout, NB); y.cs = fresh.cs; }
-      y.cs_valid = false;
       TRY(resnet_forward(c, V.dec_res[ri++], h, nullptr, y, NB, H, W));
       h = y; cur = cout;
     }

@@ -4,6 +4,7 @@
 #pragma once
 #include <map>
 #include <string>
+#include <unordered_set>
 #include <vector>
 
 #include "kernels.h"
@@ -71,12 +72,12 @@ struct Arena {
 };
 
 // A trunk activation: fp32 [M, C] plus (optionally) the per-channel (sum, sum^2) its producer accumulated for
-// the GroupNorm that consumes it (cs: [NB, C, 2]; cs_valid says whether the producer filled it).
+// the GroupNorm that consumes it (cs: [NB, C, 2]). Whether the slot has been filled is tracked per slot in
+// Ctx::stat_filled, NOT in the Act: Acts are copied around (skip connections) and have two consumers.
 struct Act {
   float* p = nullptr;
   int C = 0;
   float* cs = nullptr;
-  bool cs_valid = false;
 };
 
 struct Ctx {
@@ -91,6 +92,7 @@ struct Ctx {
   // per-graph slab of GroupNorm channel statistics (zeroed once at the start of the graph)
   float* stat_base = nullptr;
   size_t stat_off = 0, stat_cap = 0, stat_need = 0;
+  std::unordered_set<const float*> stat_filled;   // slots whose sums are (being) produced in this forward
   bool fuse_stats = true;           // producers emit statistics from their epilogues (UNet); else a stats kernel
 };
 
