@@ -16,6 +16,12 @@
 //           stride-1). A CTA's 128 rows are a tile_h x tile_w pixel rectangle; K block kb maps to
 //           (tap, channel block); the tap shifts the box by (dy, dx) and TMA zero-fills the halo, so
 //           padding costs nothing and no im2col buffer exists.
+//   mode 2  3x3 stride-1 conv with operand reuse: per channel block the producer loads the tile's HALO
+//           ((tile_h+2) x (tile_w+2) pixels x 64 channels, one 128 B swizzle row per pixel) ONCE, and the 9 taps
+//           are 9 UMMA descriptors into it: tile_w == 8, so an 8-row core-matrix group is one image row of the
+//           tile and the stride between groups (SBO) is the halo row pitch. A traffic per channel block drops
+//           from 9 x 16 KB to 23 KB; the B (weight) tiles keep their own ring, one tile per tap. K order is
+//           (channel block, tap). The kernel is L2->SM bandwidth bound, so this is a direct speed-up.
 // Replaces (behaviourally) the cuDNN/cuBLAS calls under torch.nn.Conv2d / Linear reached from
 // reference marigold/marigold_depth_pipeline.py:461-463,491-492,512-513.
 #include <algorithm>
@@ -34,9 +40,10 @@ __host__ __device__ constexpr int a_stage_bytes() { return BLOCK_M * BLOCK_K * 2
 __host__ __device__ constexpr int b_stage_bytes(int block_n) { return block_n * BLOCK_K * 2; }
 __host__ __device__ constexpr int tmem_cols_for(int n) { return n <= 32 ? 32 : n <= 64 ? 64 : n <= 128 ? 128 : 256; }
 
-size_t gemm_smem_bytes(int block_n, int stages) {
-  // 1024 B alignment slack + stages * (A + B) + barriers
-  return 1024 + size_t(stages) * (a_stage_bytes() + b_stage_bytes(block_n)) + 256;
+size_t gemm_smem_bytes(int block_n, int stages, int a_ring_bytes) {
+  // 1024 B alignment slack + A ring + B ring + barriers
+  const size_t a = a_ring_bytes >= 0 ? size_t(a_ring_bytes) : size_t(stages) * a_stage_bytes();
+  return 1024 + a + size_t(stages) * b_stage_bytes(block_n) + 256;
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -194,12 +201,15 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
   const int stages = p.stages;
   constexpr int kABytes = a_stage_bytes();
   constexpr int kBBytes = b_stage_bytes(BLOCK_N);
+  const bool halo = p.mode == 2;
   uint8_t* smem_a = smem;
-  uint8_t* smem_b = smem + size_t(stages) * kABytes;
+  uint8_t* smem_b = smem + (halo ? size_t(p.halo_slots) * p.halo_slot_bytes : size_t(stages) * kABytes);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_b + size_t(stages) * kBBytes);
   uint64_t* empty_bar = full_bar + stages;
   uint64_t* tmem_full_bar = empty_bar + stages;
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  uint64_t* a_full = tmem_full_bar + 1;     // mode 2: halo ring barriers (up to 4 slots)
+  uint64_t* a_empty = a_full + 4;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(a_empty + 4);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -209,7 +219,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
 
   // conv tile decomposition
   int img = 0, ty = 0, tx = 0;
-  if (p.mode == 1) {
+  if (p.mode != 0) {
     const int per_img = p.tiles_x * p.tiles_y;
     img = m_tile / per_img;
     const int r = m_tile - img * per_img;
@@ -226,6 +236,11 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
       mbar_init(&empty_bar[s], 1);
     }
     mbar_init(tmem_full_bar, 1);
+#pragma unroll 1
+    for (int s = 0; s < 4; ++s) {
+      mbar_init(&a_full[s], 1);
+      mbar_init(&a_empty[s], 1);
+    }
     fence_mbar_init();
   }
   constexpr uint32_t kTmemCols = tmem_cols_for(BLOCK_N);
@@ -240,10 +255,12 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
   // Weights never depend on a predecessor kernel: start streaming the first B tiles of the pipeline
   // before waiting on it (the A operand and residuals are read only after pdl_wait()).
   const int n_pre = min(stages, kb1 - kb0);
-  if (warp == 0 && elect_one()) {
+  if (warp == 0 && !((p.epi.flags >> 22) & 1) && elect_one()) {
     for (int i = 0; i < n_pre; ++i) {
-      mbar_arrive_expect_tx(&full_bar[i], kABytes + kBBytes);
-      tma_load_2d(smem_b + size_t(i) * kBBytes, &p.tmap_b, &full_bar[i], (kb0 + i) * BLOCK_K, n_tile * BLOCK_N);
+      mbar_arrive_expect_tx(&full_bar[i], halo ? kBBytes : kABytes + kBBytes);
+      int kc = kb0 + i;
+      if (halo) { const int cb = kc / 9; kc = (kc - cb * 9) * p.cblocks + cb; }   // K order (cb, tap) -> weight column block
+      tma_load_2d(smem_b + size_t(i) * kBBytes, &p.tmap_b, &full_bar[i], kc * BLOCK_K, n_tile * BLOCK_N);
     }
   }
   // everything above overlapped the previous kernel's tail; operands / residuals are read below
@@ -251,53 +268,152 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
   long long* dbg = p.dbg ? p.dbg + ((size_t(blockIdx.z) * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 8 : nullptr;
   if (dbg && threadIdx.x == 0) { dbg[0] = t_entry; dbg[1] = clock64(); }
 
+  // The producer and the MMA issuer are each ONE thread running a latency chain per K block; measured
+  // (tools/conv_phases.py, profiles/r01_gemm_issue_loop.txt): the tensor core retires a 128 x 160 x 16 MMA in 78
+  // cycles when fed back to back, but the first version of these loops took ~650 cycles per K block (elect + warp
+  // sync + generic->shared conversions + 64-bit descriptor arithmetic + integer divisions), i.e. the tensor pipe
+  // idled half of the time. Hence: whole loop inside one elected thread, shared-window addresses and descriptor
+  // words precomputed, counters instead of divisions.
+#ifdef MGB_GEMM_DEBUG_LOOPS
+  const bool dbg_no_tma = (p.epi.flags >> 22) & 1, dbg_no_mma = (p.epi.flags >> 23) & 1;
+#else
+  constexpr bool dbg_no_tma = false, dbg_no_mma = false;
+#endif
+  const uint32_t full_a = smem_u32(full_bar), empty_a = smem_u32(empty_bar);
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (elect_one()) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int kb = kb0; kb < kb1; ++kb) {
-        mbar_wait(&empty_bar[stage], phase ^ 1);
-        void* sa = smem_a + size_t(stage) * kABytes;
-        void* sb = smem_b + size_t(stage) * kBBytes;
-        if (kb - kb0 >= n_pre) {        // (the first n_pre weight tiles were issued before pdl_wait)
-          mbar_arrive_expect_tx(&full_bar[stage], kABytes + kBBytes);
-          tma_load_2d(sb, &p.tmap_b, &full_bar[stage], kb * BLOCK_K, n_tile * BLOCK_N);
+    if (!dbg_no_tma && elect_one()) {
+      uint32_t stage = 0, phase = 0;
+      const uint32_t sa0 = smem_u32(smem_a), sb0 = smem_u32(smem_b);
+      const int ncol = n_tile * BLOCK_N;
+      const uint32_t ustages = uint32_t(stages);
+      if (p.mode == 0) {
+        const int mrow = m_tile * BLOCK_M;
+        int kc = kb0 * BLOCK_K;
+        for (int kb = kb0; kb < kb1; ++kb, kc += BLOCK_K) {
+          mbar_wait_a(empty_a + stage * 8, phase ^ 1);
+          const uint32_t fb = full_a + stage * 8;
+          if (kb - kb0 >= n_pre) {        // (the first n_pre weight tiles were issued before pdl_wait)
+            mbar_expect_tx_a(fb, kABytes + kBBytes);
+            tma_load_2d_a(sb0 + stage * kBBytes, &p.tmap_b, fb, kc, ncol);
+          }
+          tma_load_2d_a(sa0 + stage * kABytes, &p.tmap_a, fb, kc, mrow);
+          if (++stage == ustages) { stage = 0; phase ^= 1; }
         }
-        if (p.mode == 0) {
-          tma_load_2d(sa, &p.tmap_a, &full_bar[stage], kb * BLOCK_K, m_tile * BLOCK_M);
-        } else {
-          const int tap = kb / p.cblocks;
-          const int cb = kb - tap * p.cblocks;
-          tma_load_5d(sa, &p.tmap_a, &full_bar[stage], cb * BLOCK_K, tx * p.tile_w + p.tap_dx[tap],
-                      ty * p.tile_h + p.tap_dy[tap], p.tap_p[tap], img);
+      } else if (p.mode == 1) {
+        const int cblocks = p.cblocks, x0 = tx * p.tile_w, y0 = ty * p.tile_h;
+        int tap = kb0 / cblocks, cb = kb0 - tap * cblocks;
+        int kc = kb0 * BLOCK_K;
+        for (int kb = kb0; kb < kb1; ++kb, kc += BLOCK_K) {
+          mbar_wait_a(empty_a + stage * 8, phase ^ 1);
+          const uint32_t fb = full_a + stage * 8;
+          if (kb - kb0 >= n_pre) {
+            mbar_expect_tx_a(fb, kABytes + kBBytes);
+            tma_load_2d_a(sb0 + stage * kBBytes, &p.tmap_b, fb, kc, ncol);
+          }
+          tma_load_5d_a(sa0 + stage * kABytes, &p.tmap_a, fb, cb * BLOCK_K, x0 + p.tap_dx[tap], y0 + p.tap_dy[tap],
+                        p.tap_p[tap], img);
+          if (++cb == cblocks) { cb = 0; ++tap; }
+          if (++stage == ustages) { stage = 0; phase ^= 1; }
         }
-        if (++stage == stages) { stage = 0; phase ^= 1; }
+      } else {
+        // halo conv: K order (channel block, tap); splits are whole channel blocks
+        const uint32_t afull_a = smem_u32(a_full), aempty_a = smem_u32(a_empty);
+        const uint32_t copy_tx = uint32_t(p.halo_w) * uint32_t(p.tile_h + 2) * 128u;
+        const uint32_t slots = uint32_t(p.halo_slots), slot_bytes = uint32_t(p.halo_slot_bytes);
+        const int copies = p.halo_copies, cstep = p.cblocks * BLOCK_K;
+        const int x0 = tx * p.tile_w - 1, y0 = ty * p.tile_h - 1;
+        uint32_t aslot = 0, aphase = 0;
+        int cb = kb0 / 9, tap = 0, bk = cb * BLOCK_K;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          if (tap == 0) {
+            mbar_wait_a(aempty_a + aslot * 8, aphase ^ 1);
+            const uint32_t fa = afull_a + aslot * 8, sa = sa0 + aslot * slot_bytes;
+            mbar_expect_tx_a(fa, copy_tx * uint32_t(copies));
+            if (copies == 1) {
+              tma_load_5d_a(sa, &p.tmap_a, fa, cb * BLOCK_K, x0, y0, 0, img);
+            } else {
+              for (int d = 0; d < 3; ++d)
+                tma_load_5d_a(sa + uint32_t(d) * uint32_t(p.halo_copy_bytes), &p.tmap_a, fa, cb * BLOCK_K, x0 + d,
+                              y0, 0, img);
+            }
+            if (++aslot == slots) { aslot = 0; aphase ^= 1; }
+          }
+          // The first n_pre B tiles were issued before pdl_wait and need no slot wait. (They MUST NOT wait: the MMA
+          // thread may already have consumed and released such a stage, and a first-pass parity wait on a barrier
+          // that has completed a phase blocks forever.)
+          if (kb - kb0 >= n_pre) {
+            mbar_wait_a(empty_a + stage * 8, phase ^ 1);
+            const uint32_t fb = full_a + stage * 8;
+            mbar_expect_tx_a(fb, kBBytes);
+            tma_load_2d_a(sb0 + stage * kBBytes, &p.tmap_b, fb, bk, ncol);
+          }
+          bk += cstep;
+          if (++tap == 9) { tap = 0; ++cb; bk = cb * BLOCK_K; }
+          if (++stage == ustages) { stage = 0; phase ^= 1; }
+        }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    constexpr uint32_t idesc = umma_idesc_bf16(BLOCK_M, BLOCK_N);
-    int stage = 0;
-    uint32_t phase = 0;
-    for (int kb = kb0; kb < kb1; ++kb) {
-      mbar_wait(&full_bar[stage], phase);
-      tc_fence_after();
-      if (dbg && kb == kb0 && lane == 0) dbg[2] = clock64();
-      if (elect_one()) {
-        const uint64_t da = umma_desc_sw128(smem_u32(smem_a + size_t(stage) * kABytes));
-        const uint64_t db = umma_desc_sw128(smem_u32(smem_b + size_t(stage) * kBBytes));
-#pragma unroll
-        for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-          // advance the start address by k * 32 B inside the 128 B swizzle atom
-          umma_bf16(tmem_base, da + uint64_t(k * 2), db + uint64_t(k * 2), idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+    if (elect_one()) {
+      constexpr uint32_t idesc = umma_idesc_bf16(BLOCK_M, BLOCK_N);
+      constexpr uint32_t kDescHi = uint32_t(kDescSw128Hi >> 32);       // SBO 1024, version 1, SWIZZLE_128B
+      constexpr uint32_t kLbo = 1u << 16;
+      const uint32_t ustages = uint32_t(stages);
+      const uint32_t a_lo0 = (smem_u32(smem_a) >> 4) | kLbo, b_lo0 = (smem_u32(smem_b) >> 4) | kLbo;
+      uint32_t stage = 0, phase = 0;
+      if (!halo) {
+        for (int kb = kb0; kb < kb1; ++kb) {
+          if (!dbg_no_tma) mbar_wait_a(full_a + stage * 8, phase);
+          if (dbg && kb == kb0) dbg[2] = clock64();
+          const uint32_t al = a_lo0 + stage * uint32_t(kABytes >> 4), bl = b_lo0 + stage * uint32_t(kBBytes >> 4);
+          if (!dbg_no_mma) {
+            // K advance: +32 B (2 descriptor units) inside the 128 B swizzle atom
+            umma_bf16(tmem_base, make_u64(al, kDescHi), make_u64(bl, kDescHi), idesc, kb > kb0 ? 1u : 0u);
+            umma_bf16(tmem_base, make_u64(al + 2, kDescHi), make_u64(bl + 2, kDescHi), idesc, 1u);
+            umma_bf16(tmem_base, make_u64(al + 4, kDescHi), make_u64(bl + 4, kDescHi), idesc, 1u);
+            umma_bf16(tmem_base, make_u64(al + 6, kDescHi), make_u64(bl + 6, kDescHi), idesc, 1u);
+          }
+          umma_commit_a(empty_a + stage * 8);
+          if (++stage == ustages) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&empty_bar[stage]);
-        if (kb == kb1 - 1) umma_commit(tmem_full_bar);
+      } else {
+        const uint32_t afull_a = smem_u32(a_full), aempty_a = smem_u32(a_empty);
+        const uint32_t slots = uint32_t(p.halo_slots), slot_u = uint32_t(p.halo_slot_bytes) >> 4;
+        const uint32_t off_dy = uint32_t(p.halo_w) * 128u >> 4;
+        const uint32_t off_dx = (p.halo_copies == 1 ? 128u : uint32_t(p.halo_copy_bytes)) >> 4;
+        // 8-row groups are image rows of the halo box: SBO = halo row pitch
+        const uint32_t hiA = off_dy | (1u << 14) | (2u << 29);
+        uint32_t aslot = 0, aphase = 0, dx = 0, dy = 0, a_off = 0;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          if ((dx | dy) == 0 && !dbg_no_tma) mbar_wait_a(afull_a + aslot * 8, aphase);
+          if (!dbg_no_tma) mbar_wait_a(full_a + stage * 8, phase);
+          if (dbg && kb == kb0) dbg[2] = clock64();
+          const uint32_t al = a_lo0 + aslot * slot_u + a_off, bl = b_lo0 + stage * uint32_t(kBBytes >> 4);
+          if (!dbg_no_mma) {
+            umma_bf16(tmem_base, make_u64(al, hiA), make_u64(bl, kDescHi), idesc, kb > kb0 ? 1u : 0u);
+            umma_bf16(tmem_base, make_u64(al + 2, hiA), make_u64(bl + 2, kDescHi), idesc, 1u);
+            umma_bf16(tmem_base, make_u64(al + 4, hiA), make_u64(bl + 4, kDescHi), idesc, 1u);
+            umma_bf16(tmem_base, make_u64(al + 6, hiA), make_u64(bl + 6, kDescHi), idesc, 1u);
+          }
+          umma_commit_a(empty_a + stage * 8);
+          a_off += off_dx;
+          if (++dx == 3) {
+            dx = 0;
+            a_off += off_dy - 3 * off_dx;
+            if (++dy == 3) {
+              dy = 0; a_off = 0;
+              umma_commit_a(aempty_a + aslot * 8);
+              if (++aslot == slots) { aslot = 0; aphase ^= 1; }
+            }
+          }
+          if (++stage == ustages) { stage = 0; phase ^= 1; }
+        }
       }
-      __syncwarp();
-      if (++stage == stages) { stage = 0; phase ^= 1; }
+      umma_commit_a(smem_u32(tmem_full_bar));
     }
+    __syncwarp();
   } else {
     // ===================== epilogue =====================
     const int q = warp & 3;  // TMEM lane quarter this warp may access
@@ -368,7 +484,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
         for (int i = etid; i < 2 * BLOCK_N; i += 128) colsum[i] = 0.f;
         asm volatile("bar.sync 1, 128;" ::: "memory");
       }
-      const int stat_img = p.mode == 1 ? img : int(((long long)m_tile * BLOCK_M) / (e.hw > 0 ? e.hw : 1));
+      const int stat_img = p.mode != 0 ? img : int(((long long)m_tile * BLOCK_M) / (e.hw > 0 ? e.hw : 1));
       // row addressing hoisted out of the chunk loop: after the transpose this lane stores rows
       // R = it * 4 + (lane >> 3), it = 0..7, of its warp's 32-row slab
       long long off[8];
@@ -585,7 +701,7 @@ static int launch_one(const GemmParams& p_in, int splits, cudaStream_t stream) {
   GemmParams p = p_in;
   p.dbg = g_gemm_dbg;
   if (g_dbg_cstat) { p.epi.cstat = g_dbg_cstat; p.epi.hw = g_dbg_cstat_hw; }
-  const size_t smem = gemm_smem_bytes(BN, p.stages);
+  const size_t smem = gemm_smem_bytes(BN, p.stages, p.mode == 2 ? p.halo_slots * p.halo_slot_bytes : -1);
   static bool attr_set = false;  // per template instantiation
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);

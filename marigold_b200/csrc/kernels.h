@@ -50,7 +50,8 @@ struct GemmEpilogue {
 struct GemmParams {
   CUtensorMap tmap_a;  // mode 0: 2D {K, M}; mode 1: 5D {C, W, H, P, NB}
   CUtensorMap tmap_b;  // 2D {K, N}
-  int mode;            // 0 = row-major activations, 1 = implicit conv over an NHWC image
+  int mode;            // 0 = row-major activations, 1 = implicit conv (one A tile per tap), 2 = implicit 3x3 conv
+                       // whose 9 taps read ONE shared-memory halo per channel block (see gemm_tc.cu)
   int M, N;            // logical GEMM rows / accumulator columns
   int num_kb;          // total K blocks of 64
   int kb_per_split;    // K blocks per blockIdx.z
@@ -63,6 +64,10 @@ struct GemmParams {
   int cblocks;         // Cin / 64
   int ntaps;
   int8_t tap_p[12], tap_dy[12], tap_dx[12];
+  // mode 2: halo geometry. halo_copies == 1: one (tile_h+2) x (tile_w+2) pixel box, taps address it at a
+  // 128 B-granular offset; halo_copies == 3: three (tile_h+2) x tile_w boxes (dx = -1, 0, +1), taps only shift
+  // by whole rows (1024 B-aligned operand starts).
+  int halo_w, halo_copies, halo_copy_bytes, halo_slot_bytes, halo_slots, halo_base_off;
   float* partial;      // split-K: fp32 [splits, M, N] raw accumulators (epilogue deferred)
   long long* dbg;      // optional per-CTA phase timestamps [ctas][8] (tools/gemm_phases.py), else nullptr
   GemmEpilogue epi;
@@ -74,7 +79,7 @@ void set_gemm_debug_buffer(long long* dev_ptr);  // debug hook: phase timestamps
 void set_gemm_debug_cstat(float* p, int hw);     // debug hook: force channel statistics output
 // Deferred epilogue for split-K: sums `splits` partials and applies p.epi.
 int launch_splitk_epilogue(const GemmParams& p, int block_n, int splits, cudaStream_t stream);
-size_t gemm_smem_bytes(int block_n, int stages);
+size_t gemm_smem_bytes(int block_n, int stages, int a_ring_bytes = -1 /* -1: stages x 16 KB A tiles */);
 
 // Tensor-map helpers (driver entry point fetched through the runtime; no -lcuda needed).
 int make_tmap_2d(CUtensorMap* out, const void* base, uint64_t inner, uint64_t outer, uint64_t row_stride_bytes,

@@ -101,11 +101,11 @@ static int matmul_nt(Ctx& c, const bf16* a, const bf16* b, int M, int N, int K, 
 // 3x3 conv on NHWC bf16; Hout x Wout output; kind per ops.cu
 static int conv3x3(Ctx& c, const bf16* x, int NB, int Hout, int Wout, const ConvW& W, int kind, const Epi& e) {
   int tw, th;
-  conv_tile_shape(Hout, Wout, &tw, &th);
+  conv_tile_shape(Hout, Wout, &tw, &th, kind);
   const int m_tiles = NB * ((Wout + tw - 1) / tw) * ((Hout + th - 1) / th);
   int bn, sp, st;
   const bool special = (e.flags & (EPI_SCHED | EPI_DEPTH | EPI_NORMALS | EPI_NCHW)) != 0;
-  choose_tile(m_tiles, W.cout, 9 * W.cin_pad / 64, false, !special, &bn, &sp, &st);
+  choose_tile(m_tiles, W.cout, 9 * W.cin_pad / 64, false, !special, &bn, &sp, &st, conv_halo_ring_bytes(kind));
   if (special) bn = 16;
   const size_t M = size_t(NB) * Hout * Wout;
   if (sp > 1) c.splitk_need = std::max(c.splitk_need, size_t(sp) * M * W.cout * sizeof(float));

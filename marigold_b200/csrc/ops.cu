@@ -2,6 +2,7 @@
 // geometry, tap tables) and pick tile shapes. Used by the network composition (net.cu) and by the
 // operator-level C ABI (api.cu).
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 #include "kernels.h"
@@ -13,7 +14,40 @@ static std::atomic<long long> g_launches{0};
 void count_launch(int n) { g_launches += n; }
 long long launch_count() { return g_launches.load(); }
 
-void conv_tile_shape(int Hout, int Wout, int* tile_w, int* tile_h) {
+int conv_halo_variant() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MGB_CONV_HALO");
+    v = e ? atoi(e) : 0;   // measured r01: no gain once the MMA issue loop runs at the tcgen05 floor (6.71 vs 6.54 ms/step)
+    if (v == 2) v = 1;     // (variant 2, descriptor base offset set, is numerically WRONG: the swizzle is address based)
+    if (v < 0 || v > 3) v = 0;
+  }
+  return v;
+}
+
+constexpr int kHaloTileW = 8, kHaloTileH = 16;
+static int halo_slots() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("MGB_HALO_SLOTS"); v = e ? atoi(e) : 2; if (v < 2 || v > 4) v = 2; }
+  return v;
+}
+#define kHaloSlots halo_slots()
+static int halo_copy_bytes(int variant) {
+  const int w = variant == 3 ? kHaloTileW : kHaloTileW + 2;
+  return ((w * (kHaloTileH + 2) * 128 + 1023) / 1024) * 1024;
+}
+static int halo_slot_bytes(int variant) { return halo_copy_bytes(variant) * (variant == 3 ? 3 : 1); }
+int conv_halo_ring_bytes(int kind) {
+  const int v = conv_halo_variant();
+  return (kind == 0 && v > 0) ? kHaloSlots * halo_slot_bytes(v) : 0;
+}
+
+void conv_tile_shape(int Hout, int Wout, int* tile_w, int* tile_h, int kind) {
+  if (kind == 0 && conv_halo_variant() > 0) {
+    *tile_w = kHaloTileW;
+    *tile_h = kHaloTileH;
+    return;
+  }
   int best_w = 16, best_tiles = 1 << 30;
   const int cands[5] = {128, 64, 32, 16, 8};
   for (int tw : cands) {
@@ -56,7 +90,7 @@ int fill_conv_params(GemmParams* p, const bf16* x, const bf16* w, int NB, int Ho
   p->M = NB * Hout * Wout;
   p->N = Cout;
   p->H = Hout; p->W = Wout;
-  conv_tile_shape(Hout, Wout, &p->tile_w, &p->tile_h);
+  conv_tile_shape(Hout, Wout, &p->tile_w, &p->tile_h, kind);
   p->tile_w_shift = 0;
   while ((1 << p->tile_w_shift) < p->tile_w) ++p->tile_w_shift;
   p->tiles_x = (Wout + p->tile_w - 1) / p->tile_w;
@@ -97,11 +131,27 @@ int fill_conv_params(GemmParams* p, const bf16* x, const bf16* w, int NB, int Ho
   splits = std::min(splits, p->num_kb);
   p->kb_per_split = (p->num_kb + splits - 1) / splits;
   p->stages = stages;
+  const int hv = kind == 0 ? conv_halo_variant() : 0;
+  uint32_t box_w = uint32_t(p->tile_w), box_h = uint32_t(p->tile_h);
+  if (hv > 0) {
+    // operand-reuse path: K order (channel block, tap), splits in whole channel blocks
+    p->mode = 2;
+    splits = std::min(splits, p->cblocks);
+    p->kb_per_split = 9 * ((p->cblocks + splits - 1) / splits);
+    p->halo_copies = hv == 3 ? 3 : 1;
+    p->halo_w = hv == 3 ? p->tile_w : p->tile_w + 2;
+    p->halo_copy_bytes = halo_copy_bytes(hv);
+    p->halo_slot_bytes = halo_slot_bytes(hv);
+    p->halo_slots = kHaloSlots;
+    p->halo_base_off = hv == 2;
+    box_w = uint32_t(p->halo_w);
+    box_h = uint32_t(p->tile_h + 2);
+  }
 
   const uint64_t C2 = uint64_t(Cin) * 2;
   const uint64_t dims[5] = {uint64_t(Cin), uint64_t(Wout), uint64_t(Hout), uint64_t(planes), uint64_t(NB)};
   const uint64_t strides[4] = {C2, C2 * Wout, C2 * Wout * Hout, C2 * Wout * Hout * planes};
-  const uint32_t box[5] = {64, uint32_t(p->tile_w), uint32_t(p->tile_h), 1, 1};
+  const uint32_t box[5] = {64, box_w, box_h, 1, 1};
   int rc = make_tmap_5d(&p->tmap_a, x, dims, strides, box);
   if (rc) return rc;
   const uint64_t Ktot = uint64_t(p->ntaps) * Cin;
@@ -123,7 +173,7 @@ int run_gemm(GemmParams& p, int block_n, float* splitk_ws, cudaStream_t stream) 
               p.N);
     return MGB_ERR_INVALID;
   }
-  if (p.stages < 2 || gemm_smem_bytes(block_n, p.stages) > 227 * 1024) {
+  if (p.stages < 2 || gemm_smem_bytes(block_n, p.stages, p.mode == 2 ? p.halo_slots * p.halo_slot_bytes : -1) > 227 * 1024) {
     set_error("gemm: stages=%d does not fit shared memory for block_n=%d", p.stages, block_n);
     return MGB_ERR_INVALID;
   }
@@ -160,7 +210,7 @@ int run_gemm(GemmParams& p, int block_n, float* splitk_ws, cudaStream_t stream) 
 // Tile-shape heuristic. Cost model (cycles): per CTA  num_kb * 2*BN (tcgen05 floor at M=128)
 // + epilogue ~ 6*BN + fixed 3000; CTAs run in waves of 148 (1 CTA/SM).
 void choose_tile(int m_tiles, int N, int num_kb, bool geglu, bool allow_split, int* block_n, int* splits,
-                 int* stages) {
+                 int* stages, int a_ring_bytes) {
   const int cands[6] = {256, 160, 128, 64, 32, 16};
   double best = 1e30;
   int bbn = 128, bsp = 1;
@@ -173,12 +223,13 @@ void choose_tile(int m_tiles, int N, int num_kb, bool geglu, bool allow_split, i
     (void)waste;
     for (int sp = 1; sp <= (allow_split ? 16 : 1); ++sp) {
       if (sp > 1 && num_kb / sp < 4) break;
+      if (a_ring_bytes > 0 && sp > num_kb / 9) break;
       const long long ctas = (long long)m_tiles * n_tiles * sp;
       const long long waves = (ctas + 147) / 148;
-      const int kb = (num_kb + sp - 1) / sp;
+      const int kb = a_ring_bytes > 0 ? 9 * ((num_kb / 9 + sp - 1) / sp) : (num_kb + sp - 1) / sp;
       double cta_cycles = double(kb) * 2.0 * bn + 6.0 * bn + 3000.0;
       // small tiles are smem-bandwidth bound: A (16 KB) + B per k-block at 128 B/cycle
-      const double smem_cycles = double(kb) * (16384.0 + bn * 128.0) / 128.0 + 6.0 * bn + 3000.0;
+      const double smem_cycles = double(kb) * ((a_ring_bytes > 0 ? 2560.0 : 16384.0) + bn * 128.0) / 128.0 + 6.0 * bn + 3000.0;
       cta_cycles = std::max(cta_cycles, smem_cycles);
       double t = waves * cta_cycles;
       if (sp > 1) t += 4000.0 + double(m_tiles) * 128.0 * N * sp * 4.0 / (148.0 * 64.0);  // reduce pass
@@ -187,13 +238,13 @@ void choose_tile(int m_tiles, int N, int num_kb, bool geglu, bool allow_split, i
   }
   *block_n = bbn;
   *splits = bsp;
-  const int stage_bytes = 16384 + bbn * 128;
+  const int stage_bytes = (a_ring_bytes > 0 ? 0 : 16384) + bbn * 128;
   const int kb = (num_kb + bsp - 1) / bsp;
   // Deep pipelines (the whole 200 KB) only pay off for long K loops. Short-K GEMMs are dominated by
   // prologue / first-load / epilogue latency: cap them near 110 KB so that the NEXT kernel's CTA (launched
   // early through PDL) can become resident on the same SM and overlap its prologue and first operand loads
   // with this kernel's epilogue.
-  const int budget = kb <= 12 ? 110 * 1024 : 200 * 1024;
+  const int budget = (kb <= 12 ? 110 * 1024 : 200 * 1024) - a_ring_bytes;
   int st = int((budget - 2048) / stage_bytes);
   st = std::max(2, std::min(st, 8));
   st = std::min(st, std::max(2, kb));
