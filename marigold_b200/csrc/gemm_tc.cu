@@ -7,8 +7,10 @@
 //               per pipeline stage, completion signalled on an mbarrier (complete_tx).
 //   warp 1      TMEM allocator + MMA issuer: one elected lane issues 4 x tcgen05.mma (K = 16 each)
 //               per stage and releases the stage with tcgen05.commit.
-//   warps 2..5  epilogue: tcgen05.ld the fp32 accumulator (one row per thread), apply the fused
+//   warps 2..9  epilogue: tcgen05.ld the fp32 accumulator (one row per thread), apply the fused
 //               epilogue (bias / activation / GEGLU / residual / scheduler step / output cast), store.
+//               Two warps per TMEM lane quarter (w and w+4) take alternate 32-column chunks: the epilogue
+//               is bound by per-warp load/store latency chains, not by SM store bandwidth.
 //
 // A operand addressing:
 //   mode 0  rows: 2D tensor map {K, M}; tile m covers rows [128 m, 128 m + 128).
@@ -34,7 +36,8 @@ namespace mgb {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;
 constexpr int UMMA_K = 16;
-constexpr int kGemmThreads = 192;
+constexpr int kEpiWarps = 8;                          // two warps per TMEM lane quarter, alternating column chunks
+constexpr int kGemmThreads = 64 + 32 * kEpiWarps;
 
 __host__ __device__ constexpr int a_stage_bytes() { return BLOCK_M * BLOCK_K * 2; }
 __host__ __device__ constexpr int b_stage_bytes(int block_n) { return block_n * BLOCK_K * 2; }
@@ -429,7 +432,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
     const GemmEpilogue& e = p.epi;
     const int n0 = n_tile * BLOCK_N;
 
+    const int ehalf = (warp - 2) >> 2;   // which of the two warps of this lane quarter
     if constexpr (BLOCK_N == 16) {
+      if (ehalf == 0) {
       RowCtx rc;
       rc.valid = tile_row_index(tg, row, &rc.m);
       uint32_t r[16];
@@ -456,10 +461,12 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
           epilogue_chunk<16>(e, rc, v, n0, p.N - n0);
         }
       }
+      }
     } else {
       // the operand pipeline is drained (every issued stage was consumed): its smem is the transpose
-      // scratch, two 32 x 36 fp32 tiles per warp (the second one only for GEGLU's gate chunk)
-      float* s_base = reinterpret_cast<float*>(smem_a) + (warp - 2) * (2 * 32 * kEpiPitch);
+      // scratch, one 32 x 36 fp32 tile per warp (two for GEGLU: value + gate chunk); the host checks the ring size
+      const int s_stride = ((p.partial == nullptr) && (e.flags & EPI_GEGLU)) ? 2 * 32 * kEpiPitch : 32 * kEpiPitch;
+      float* s_base = reinterpret_cast<float*>(smem_a) + (warp - 2) * s_stride;
       float* s_wr = s_base + lane * kEpiPitch;
       const int sub = lane >> 3, c4 = (lane & 7) * 4;
       const float* s_rd = s_base + sub * kEpiPitch + c4;
@@ -481,8 +488,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
       float* colsum = reinterpret_cast<float*>(smem_b + size_t(stages) * kBBytes) - 2 * BLOCK_N;   // tail of the B ring
       const int etid = threadIdx.x - 64;
       if (cstat) {
-        for (int i = etid; i < 2 * BLOCK_N; i += 128) colsum[i] = 0.f;
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        for (int i = etid; i < 2 * BLOCK_N; i += 32 * kEpiWarps) colsum[i] = 0.f;
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
       }
       const int stat_img = p.mode != 0 ? img : int(((long long)m_tile * BLOCK_M) / (e.hw > 0 ? e.hw : 1));
       // row addressing hoisted out of the chunk loop: after the transpose this lane stores rows
@@ -497,7 +504,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
         vmask |= uint32_t(ok) << it;
       }
 #pragma unroll 1
-      for (int j = 0; j < chunks; ++j) {
+      for (int j = ehalf; j < chunks; j += 2) {
         const long long c0 = (dbg && j < 2) ? clock64() : 0;
         {
           uint32_t r[32];
@@ -529,8 +536,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
         if (chunk_nv <= 0) { __syncwarp(); continue; }
         const bool vec = ld_vec && nv >= 4;
         if (!geglu && !silu && ld_vec && chunk_nv >= 32) {
-          // fast path. All 8 scratch loads and all 8 residual loads are issued BEFORE anything is consumed:
-          // with one epilogue warp per scheduler nothing else hides a ~600-cycle LDG per row.
+          // fast path. All 8 scratch loads and all 8 residual loads are issued BEFORE anything is consumed
+          // (tried and rejected, r01: requesting the next TMEM chunk / the residual rows one phase earlier made the
+          // epilogue 15% slower)
           float4 x[8], rr[8];
 #pragma unroll
           for (int it = 0; it < 8; ++it) x[it] = *reinterpret_cast<const float4*>(s_rd + it * (4 * kEpiPitch));
@@ -611,8 +619,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
         if (dbg && j < 2 && threadIdx.x == 64) { dbg[6 + j] = ((c1 - c0) << 32) | (clock64() - c1); }
       }
       if (cstat) {
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        for (int i = etid; i < 2 * BLOCK_N; i += 128) {
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
+        for (int i = etid; i < 2 * BLOCK_N; i += 32 * kEpiWarps) {
           const int cidx = n0 + (i >> 1);
           if (cidx < n_out) atomicAdd(cstat + ((long long)stat_img * ldo + cidx) * 2 + (i & 1), colsum[i]);
         }

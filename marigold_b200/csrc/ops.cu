@@ -173,7 +173,18 @@ int run_gemm(GemmParams& p, int block_n, float* splitk_ws, cudaStream_t stream) 
               p.N);
     return MGB_ERR_INVALID;
   }
-  if (p.stages < 2 || gemm_smem_bytes(block_n, p.stages, p.mode == 2 ? p.halo_slots * p.halo_slot_bytes : -1) > 227 * 1024) {
+  if (block_n > 16) {
+    // the drained operand ring doubles as the epilogue's transpose scratch (8 warps x 4.5 KB, x2 for GEGLU) and, with
+    // channel statistics, holds the per-CTA column sums at its tail: deepen the pipeline until that fits
+    const int need = 8 * ((p.epi.flags & EPI_GEGLU) ? 9216 : 4608) + (p.epi.cstat ? 2 * block_n * 4 : 0);
+    for (;;) {
+      const int ring = (p.mode == 2 ? p.halo_slots * p.halo_slot_bytes : p.stages * 16384) + p.stages * block_n * 128;
+      if (ring >= need || p.stages >= 16) break;
+      ++p.stages;
+    }
+  }
+  if (p.stages < 2 || p.stages > 8 ||
+      gemm_smem_bytes(block_n, p.stages, p.mode == 2 ? p.halo_slots * p.halo_slot_bytes : -1) > 227 * 1024) {
     set_error("gemm: stages=%d does not fit shared memory for block_n=%d", p.stages, block_n);
     return MGB_ERR_INVALID;
   }

@@ -35,8 +35,13 @@ if __name__ == "__main__":
     ap.add_argument("csv")
     ap.add_argument("--top", type=int, default=30)
     ap.add_argument("--by-grid", action="store_true")
+    ap.add_argument("--last-step", action="store_true", help="only the launches from the last select_step_kernel on")
     a = ap.parse_args()
     rows = load(a.csv)
+    if a.last_step:
+        idx = [i for i, r in enumerate(rows) if r[0].startswith("select_step_kernel")]
+        if idx:
+            rows = rows[idx[-1]:]
     tot = sum(r[3] for r in rows)
     agg = defaultdict(lambda: [0, 0.0])
     for name, grid, block, ns in rows:

@@ -6,7 +6,7 @@ set -u
 TAG=${1:-r01}
 mkdir -p gpurun_out
 STEP="python tools/step_only.py 3"
-timeout 500 ncu --metrics gpu__time_duration.sum --clock-control none --cache-control none -s 520 -c 462 --csv \
+timeout 500 ncu --metrics gpu__time_duration.sum --clock-control none --cache-control none -c 3000 --csv \
     --log-file gpurun_out/${TAG}_launches.csv $STEP > gpurun_out/${TAG}_launches.log 2>&1
 # first eager UNet step: launch #57 is select_step; conv_in is gemm #1, the first resnet's conv1 (72x2 CTAs, K=2880) gemm #2
 timeout 500 ncu --set full --clock-control none --import-source on -k regex:gemm_tc_kernel -s 1 -c 2 \
