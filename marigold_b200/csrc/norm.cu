@@ -15,38 +15,37 @@
 namespace mgb {
 
 constexpr int kGnThreads = 256;
-constexpr int kGnMaxK = 4;      // channel-quads per thread
-constexpr int kGnMaxChunks = 592;   // CTAs per image
+constexpr int kGnLoads = 8;          // float4 loads in flight per thread and round
+constexpr int kGnMaxChunks = 1184;   // CTAs per image (8 per SM)
 
+// Thread geometry: Tq lanes along channel quads x Tp lanes along pixels; a thread owns Kq quads (Kq in {1, 2, 4}) and
+// R = 8 / Kq pixels per round, so that ALL of a round's loads are issued before anything is consumed. These kernels
+// run between two GEMMs on tensors that mostly sit in L2: they are bound by dependent load latency, not bandwidth
+// (the first version walked pixels with 2-3 dependent round trips per quad and took 9-15 us on 0.7-12 MB).
 struct GnGeom {
-  int Q;        // C / 4
-  int Tq, Tp;   // thread grid: Tq channel-quad lanes x Tp pixel lanes (Tq * Tp <= 256)
-  int Kq;       // Q / Tq  (<= kGnMaxK)
-  int chunks, P;  // pixel chunks per image, pixels per chunk
+  int Q;          // C / 4
+  int Tq, Tp;     // Tq * Tp <= 256
+  int Kq, R;      // quads per thread, pixels per thread and round (Kq * R == kGnLoads)
+  int chunks, P;  // pixel chunks per image, pixels per chunk (a multiple of Tp * R)
 };
 
 static bool gn_geometry(int HW, int C, GnGeom* g) {
   if (C % 4) return false;
   g->Q = C / 4;
-  int best = -1, bestTq = 0;
-  for (int tq = 1; tq <= 256 && tq <= g->Q; ++tq) {
-    if (g->Q % tq) continue;
-    if (g->Q / tq > kGnMaxK) continue;
-    const int tp = 256 / tq;
-    if (tq * tp > best) { best = tq * tp; bestTq = tq; }
+  int best = -1;
+  for (int kq = 1; kq <= 4; kq *= 2) {
+    if (g->Q % kq) continue;
+    const int tq = g->Q / kq;
+    if (tq > kGnThreads) continue;
+    const int tp = kGnThreads / tq;
+    if (tq * tp > best) { best = tq * tp; g->Tq = tq; g->Tp = tp; g->Kq = kq; }
   }
   if (best < 0) return false;
-  g->Tq = bestTq;
-  g->Tp = 256 / bestTq;
-  g->Kq = g->Q / bestTq;
-  // ~8K elements (32 KB fp32) per chunk: enough CTAs to saturate HBM on the big VAE tensors, few enough
-  // partials that combining them stays negligible on the small UNet ones
-  long long want = ((long long)HW * C + 8191) / 8192;
-  if (want < 1) want = 1;
-  if (want > kGnMaxChunks) want = kGnMaxChunks;
-  if (want > HW) want = HW;
-  g->chunks = int(want);
-  g->P = (HW + g->chunks - 1) / g->chunks;
+  g->R = kGnLoads / g->Kq;
+  const int per_round = g->Tp * g->R;
+  long long rounds_total = (HW + per_round - 1) / per_round;
+  long long rounds = (rounds_total + kGnMaxChunks - 1) / kGnMaxChunks;
+  g->P = int(rounds) * per_round;
   g->chunks = (HW + g->P - 1) / g->P;
   return true;
 }
@@ -58,68 +57,74 @@ size_t groupnorm_ws_bytes(int NB, int HW, int C, int G) {
 
 // -------------------------------------------------------------------------------------------------
 // Per-channel statistics of x [NB, HW, C]: cs[(img * C + c) * 2 + {0,1}] += (sum, sum of squares).
-// Only used where the producer could not emit them from its epilogue (VAE-sized tensors, ragged token
-// tiles); cs must be zero on entry.
+// cs must be zero on entry (the network zeroes its whole statistics slab once per forward).
 // -------------------------------------------------------------------------------------------------
+template <int KQ>
 __global__ void __launch_bounds__(kGnThreads) chan_stats_kernel(const float* __restrict__ x, float* __restrict__ cs,
                                                                 int HW, int C, GnGeom g) {
+  constexpr int R = kGnLoads / KQ;
   extern __shared__ float s_acc[];  // [2 * C]
   pdl_launch_dependents();
-  pdl_wait();
   const int img = blockIdx.y, chunk = blockIdx.x;
-  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) s_acc[i] = 0.f;
-  __syncthreads();
+  const bool use_smem = g.Tp > 1;
+  if (use_smem) {
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) s_acc[i] = 0.f;
+    __syncthreads();
+  }
+  pdl_wait();
   const int tq = threadIdx.x % g.Tq, tp = threadIdx.x / g.Tq;
-  if (tp < g.Tp) {
-    float sum[kGnMaxK][4], sq[kGnMaxK][4];
+  const bool active = tp < g.Tp;
+  float sum[KQ][4], sq[KQ][4];
 #pragma unroll
-    for (int k = 0; k < kGnMaxK; ++k)
+  for (int k = 0; k < KQ; ++k)
 #pragma unroll
-      for (int j = 0; j < 4; ++j) { sum[k][j] = 0.f; sq[k][j] = 0.f; }
-    const int p0 = chunk * g.P, p1 = min(HW, p0 + g.P);
-    const float4* xi = reinterpret_cast<const float4*>(x + (size_t)img * HW * C);
+    for (int j = 0; j < 4; ++j) { sum[k][j] = 0.f; sq[k][j] = 0.f; }
+  const int p0 = chunk * g.P, p1 = min(HW, p0 + g.P);
+  const float4* xi = reinterpret_cast<const float4*>(x + (size_t)img * HW * C);
+  for (int pb = p0 + tp; pb < p1; pb += g.Tp * R) {
+    float4 v[KQ][R];
 #pragma unroll
-    for (int k = 0; k < kGnMaxK; ++k) {
-      if (k >= g.Kq) break;
-      const size_t qoff = size_t(tq) + size_t(k) * g.Tq;
-      int p = p0 + tp;
-      for (; p + 3 * g.Tp < p1; p += 4 * g.Tp) {
-        float4 v[4];
+    for (int k = 0; k < KQ; ++k)
 #pragma unroll
-        for (int u = 0; u < 4; ++u) v[u] = __ldg(xi + (size_t)(p + u * g.Tp) * g.Q + qoff);
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          sum[k][0] += v[u].x; sq[k][0] += v[u].x * v[u].x;
-          sum[k][1] += v[u].y; sq[k][1] += v[u].y * v[u].y;
-          sum[k][2] += v[u].z; sq[k][2] += v[u].z * v[u].z;
-          sum[k][3] += v[u].w; sq[k][3] += v[u].w * v[u].w;
-        }
+      for (int r = 0; r < R; ++r) {
+        const int p = pb + r * g.Tp;
+        v[k][r] = (active && p < p1) ? __ldg(xi + (size_t)p * g.Q + tq + k * g.Tq) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
-      for (; p < p1; p += g.Tp) {
-        const float4 v = __ldg(xi + (size_t)p * g.Q + qoff);
-        sum[k][0] += v.x; sq[k][0] += v.x * v.x;
-        sum[k][1] += v.y; sq[k][1] += v.y * v.y;
-        sum[k][2] += v.z; sq[k][2] += v.z * v.z;
-        sum[k][3] += v.w; sq[k][3] += v.w * v.w;
+#pragma unroll
+    for (int k = 0; k < KQ; ++k)
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        sum[k][0] += v[k][r].x; sq[k][0] = fmaf(v[k][r].x, v[k][r].x, sq[k][0]);
+        sum[k][1] += v[k][r].y; sq[k][1] = fmaf(v[k][r].y, v[k][r].y, sq[k][1]);
+        sum[k][2] += v[k][r].z; sq[k][2] = fmaf(v[k][r].z, v[k][r].z, sq[k][2]);
+        sum[k][3] += v[k][r].w; sq[k][3] = fmaf(v[k][r].w, v[k][r].w, sq[k][3]);
+      }
+  }
+  if (!use_smem) {
+    if (active) {
+#pragma unroll
+      for (int k = 0; k < KQ; ++k) {
+        float* dst = cs + ((size_t)img * C + 4 * (tq + k * g.Tq)) * 2;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { atomicAdd(dst + 2 * j, sum[k][j]); atomicAdd(dst + 2 * j + 1, sq[k][j]); }
       }
     }
+    return;
+  }
+  if (active) {
 #pragma unroll
-    for (int k = 0; k < kGnMaxK; ++k) {
-      if (k < g.Kq) {
-        const int c0 = 4 * (tq + k * g.Tq);
+    for (int k = 0; k < KQ; ++k) {
+      const int c0 = 4 * (tq + k * g.Tq);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          atomicAdd(&s_acc[c0 + j], sum[k][j]);
-          atomicAdd(&s_acc[C + c0 + j], sq[k][j]);
-        }
+      for (int j = 0; j < 4; ++j) {
+        atomicAdd(&s_acc[2 * (c0 + j)], sum[k][j]);
+        atomicAdd(&s_acc[2 * (c0 + j) + 1], sq[k][j]);
       }
     }
   }
   __syncthreads();
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    atomicAdd(cs + ((size_t)img * C + c) * 2, s_acc[c]);
-    atomicAdd(cs + ((size_t)img * C + c) * 2 + 1, s_acc[C + c]);
-  }
+  float* dst = cs + (size_t)img * C * 2;
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) atomicAdd(dst + i, s_acc[i]);
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -128,26 +133,63 @@ __global__ void __launch_bounds__(kGnThreads) chan_stats_kernel(const float* __r
 // optionally also the raw bf16 copy of [a | b] (operand of a ResnetBlock's 1x1 shortcut conv).
 // This is torch.cat(dim=1) + GroupNorm (+SiLU) of diffusers' up-block resnets in one pass.
 // -------------------------------------------------------------------------------------------------
+template <int KQ>
 __global__ void __launch_bounds__(kGnThreads)
     gn_apply2_kernel(const float* __restrict__ xa, const float* __restrict__ csa, int Ca, const float* __restrict__ xb,
                      const float* __restrict__ csb, int Cb, bf16* __restrict__ y, bf16* __restrict__ raw,
                      const float* __restrict__ gamma, const float* __restrict__ beta, int HW, int G, float eps, int silu,
                      GnGeom g) {
+  constexpr int R = kGnLoads / KQ;
   extern __shared__ float s_stat[];  // mean[G], rstd[G]
   pdl_launch_dependents();
   pdl_wait();
   const int img = blockIdx.y, chunk = blockIdx.x;
   const int C = Ca + Cb, cpg = C / G;
+  const int tq = threadIdx.x % g.Tq, tp = threadIdx.x / g.Tq;
+  const bool active = tp < g.Tp;
+  const int p0 = chunk * g.P, p1 = min(HW, p0 + g.P);
+  const int Qa = Ca / 4, Qb = Cb / 4;
+  const float4* xai = reinterpret_cast<const float4*>(xa + (size_t)img * HW * Ca);
+  const float4* xbi = xb ? reinterpret_cast<const float4*>(xb + (size_t)img * HW * Cb) : nullptr;
+  uint2* yo = reinterpret_cast<uint2*>(y + (size_t)img * HW * C);
+  uint2* ro = raw ? reinterpret_cast<uint2*>(raw + (size_t)img * HW * C) : nullptr;
+
+  // (1) first round of pixel loads + the affine parameters: in flight while the statistics are reduced
+  const float4* src[KQ];
+  size_t sstride[KQ];
+  float4 ga4[KQ], be4[KQ];
+  float4 v[KQ][R];
+#pragma unroll
+  for (int k = 0; k < KQ; ++k) {
+    const int qd = tq + k * g.Tq;   // quad index in the concatenated channel space
+    const bool from_a = qd < Qa;
+    src[k] = from_a ? xai + qd : xbi + (qd - Qa);
+    sstride[k] = from_a ? size_t(Qa) : size_t(Qb);
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int p = p0 + tp + r * g.Tp;
+      v[k][r] = (active && p < p1) ? __ldg(src[k] + (size_t)p * sstride[k]) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    ga4[k] = gamma ? __ldg(reinterpret_cast<const float4*>(gamma) + qd) : make_float4(1.f, 1.f, 1.f, 1.f);
+    be4[k] = beta ? __ldg(reinterpret_cast<const float4*>(beta) + qd) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  // (2) group statistics: 8 lanes per group (G * 8 <= 256 threads), up to 4 independent loads per lane and pass
   {
-    // 8 lanes per group, then a shuffle reduction (G * 8 <= 256 threads)
     const int gi = threadIdx.x >> 3, part = threadIdx.x & 7;
     double s = 0.0, q = 0.0;
     if (gi < G) {
-      for (int j = part; j < cpg; j += 8) {
-        const int c = gi * cpg + j;
-        const float2 v = c < Ca ? __ldcg(reinterpret_cast<const float2*>(csa + ((size_t)img * Ca + c) * 2))
-                                : __ldcg(reinterpret_cast<const float2*>(csb + ((size_t)img * Cb + (c - Ca)) * 2));
-        s += double(v.x); q += double(v.y);
+      for (int j0 = part; j0 < cpg; j0 += 32) {
+        float2 t[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int j = j0 + 8 * u, c = gi * cpg + j;
+          t[u] = make_float2(0.f, 0.f);
+          if (j < cpg)
+            t[u] = c < Ca ? __ldcg(reinterpret_cast<const float2*>(csa + ((size_t)img * Ca + c) * 2))
+                          : __ldcg(reinterpret_cast<const float2*>(csb + ((size_t)img * Cb + (c - Ca)) * 2));
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { s += double(t[u].x); q += double(t[u].y); }
       }
     }
 #pragma unroll
@@ -165,52 +207,46 @@ __global__ void __launch_bounds__(kGnThreads)
     }
   }
   __syncthreads();
-  const int tq = threadIdx.x % g.Tq, tp = threadIdx.x / g.Tq;
-  if (tp >= g.Tp) return;
-  const int p0 = chunk * g.P, p1 = min(HW, p0 + g.P);
-  const int Qa = Ca / 4, Qb = Cb / 4;
-  const float4* xai = reinterpret_cast<const float4*>(xa + (size_t)img * HW * Ca);
-  const float4* xbi = xb ? reinterpret_cast<const float4*>(xb + (size_t)img * HW * Cb) : nullptr;
-  uint2* yo = reinterpret_cast<uint2*>(y + (size_t)img * HW * C);
-  uint2* ro = raw ? reinterpret_cast<uint2*>(raw + (size_t)img * HW * C) : nullptr;
+  if (!active) return;
+  float sc[KQ][4], sh[KQ][4];
 #pragma unroll
-  for (int k = 0; k < kGnMaxK; ++k) {
-    if (k >= g.Kq) break;
-    const int qd = tq + k * g.Tq;                 // quad index in the concatenated channel space
-    float sc[4], sh[4];
+  for (int k = 0; k < KQ; ++k) {
+    const int qd = tq + k * g.Tq;
+    const float gav[4] = {ga4[k].x, ga4[k].y, ga4[k].z, ga4[k].w}, bev[4] = {be4[k].x, be4[k].y, be4[k].z, be4[k].w};
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const int c = 4 * qd + j, gi = c / cpg;
-      const float ga = gamma ? __ldg(gamma + c) : 1.f, be = beta ? __ldg(beta + c) : 0.f;
-      sc[j] = s_stat[G + gi] * ga;
-      sh[j] = be - s_stat[gi] * s_stat[G + gi] * ga;
+      const int gi = (4 * qd + j) / cpg;
+      const float rstd = s_stat[G + gi];
+      sc[k][j] = rstd * gav[j];
+      sh[k][j] = bev[j] - s_stat[gi] * rstd * gav[j];
     }
-    const bool from_a = qd < Qa;
-    const float4* src = from_a ? xai + qd : xbi + (qd - Qa);
-    const size_t sstride = from_a ? size_t(Qa) : size_t(Qb);
-    int p = p0 + tp;
-    for (; p + 3 * g.Tp < p1; p += 4 * g.Tp) {
-      float4 v[4];
+  }
+  // (3) apply; further rounds (only tensors too large for one round per CTA) reload in the same batched way
+  for (int pb = p0 + tp;;) {
 #pragma unroll
-      for (int u = 0; u < 4; ++u) v[u] = __ldg(src + (size_t)(p + u * g.Tp) * sstride);
+    for (int k = 0; k < KQ; ++k)
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const size_t idx = (size_t)(p + u * g.Tp) * g.Q + qd;
-        float o0 = v[u].x * sc[0] + sh[0], o1 = v[u].y * sc[1] + sh[1], o2 = v[u].z * sc[2] + sh[2],
-              o3 = v[u].w * sc[3] + sh[3];
-        if (silu) { o0 = silu_f(o0); o1 = silu_f(o1); o2 = silu_f(o2); o3 = silu_f(o3); }
-        yo[idx] = make_uint2(pack_bf16x2(o0, o1), pack_bf16x2(o2, o3));
-        if (ro) ro[idx] = make_uint2(pack_bf16x2(v[u].x, v[u].y), pack_bf16x2(v[u].z, v[u].w));
+      for (int r = 0; r < R; ++r) {
+        const int p = pb + r * g.Tp;
+        if (p < p1) {
+          const size_t idx = (size_t)p * g.Q + tq + k * g.Tq;
+          const float4 t = v[k][r];
+          float o0 = fmaf(t.x, sc[k][0], sh[k][0]), o1 = fmaf(t.y, sc[k][1], sh[k][1]),
+                o2 = fmaf(t.z, sc[k][2], sh[k][2]), o3 = fmaf(t.w, sc[k][3], sh[k][3]);
+          if (silu) { o0 = silu_f(o0); o1 = silu_f(o1); o2 = silu_f(o2); o3 = silu_f(o3); }
+          yo[idx] = make_uint2(pack_bf16x2(o0, o1), pack_bf16x2(o2, o3));
+          if (ro) ro[idx] = make_uint2(pack_bf16x2(t.x, t.y), pack_bf16x2(t.z, t.w));
+        }
       }
-    }
-    for (; p < p1; p += g.Tp) {
-      const size_t idx = (size_t)p * g.Q + qd;
-      const float4 v = __ldg(src + (size_t)p * sstride);
-      float o0 = v.x * sc[0] + sh[0], o1 = v.y * sc[1] + sh[1], o2 = v.z * sc[2] + sh[2], o3 = v.w * sc[3] + sh[3];
-      if (silu) { o0 = silu_f(o0); o1 = silu_f(o1); o2 = silu_f(o2); o3 = silu_f(o3); }
-      yo[idx] = make_uint2(pack_bf16x2(o0, o1), pack_bf16x2(o2, o3));
-      if (ro) ro[idx] = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
-    }
+    pb += g.Tp * R;
+    if (pb >= p1) break;
+#pragma unroll
+    for (int k = 0; k < KQ; ++k)
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const int p = pb + r * g.Tp;
+        v[k][r] = p < p1 ? __ldg(src[k] + (size_t)p * sstride[k]) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
   }
 }
 
@@ -218,7 +254,11 @@ int launch_chan_stats(const float* x, float* cs, int NB, int HW, int C, cudaStre
   GnGeom g;
   if (!gn_geometry(HW, C, &g)) { set_error("chan_stats: unsupported C=%d", C); return MGB_ERR_INVALID; }
   dim3 grid(g.chunks, NB);
-  cudaError_t e = launch_k(chan_stats_kernel, grid, kGnThreads, 2 * C * sizeof(float), stream, x, cs, HW, C, g);
+  const size_t smem = g.Tp > 1 ? 2 * C * sizeof(float) : 0;
+  cudaError_t e;
+  if (g.Kq == 1) e = launch_k(chan_stats_kernel<1>, grid, kGnThreads, smem, stream, x, cs, HW, C, g);
+  else if (g.Kq == 2) e = launch_k(chan_stats_kernel<2>, grid, kGnThreads, smem, stream, x, cs, HW, C, g);
+  else e = launch_k(chan_stats_kernel<4>, grid, kGnThreads, smem, stream, x, cs, HW, C, g);
   if (e == cudaSuccess) e = cudaGetLastError();
   if (e != cudaSuccess) { set_error("chan_stats launch: %s", cudaGetErrorString(e)); return MGB_ERR_CUDA; }
   return MGB_OK;
@@ -234,8 +274,17 @@ int launch_gn_apply2(const float* xa, const float* csa, int Ca, const float* xb,
     return MGB_ERR_INVALID;
   }
   dim3 grid(g.chunks, NB);
-  cudaError_t e = launch_k(gn_apply2_kernel, grid, kGnThreads, 2 * G * sizeof(float), stream, xa, csa, Ca, xb, csb, Cb, y,
-                           raw_copy, gamma, beta, HW, G, eps, silu, g);
+  const size_t smem = 2 * G * sizeof(float);
+  cudaError_t e;
+  if (g.Kq == 1)
+    e = launch_k(gn_apply2_kernel<1>, grid, kGnThreads, smem, stream, xa, csa, Ca, xb, csb, Cb, y, raw_copy, gamma, beta, HW,
+                 G, eps, silu, g);
+  else if (g.Kq == 2)
+    e = launch_k(gn_apply2_kernel<2>, grid, kGnThreads, smem, stream, xa, csa, Ca, xb, csb, Cb, y, raw_copy, gamma, beta, HW,
+                 G, eps, silu, g);
+  else
+    e = launch_k(gn_apply2_kernel<4>, grid, kGnThreads, smem, stream, xa, csa, Ca, xb, csb, Cb, y, raw_copy, gamma, beta, HW,
+                 G, eps, silu, g);
   if (e == cudaSuccess) e = cudaGetLastError();
   if (e != cudaSuccess) { set_error("groupnorm launch: %s", cudaGetErrorString(e)); return MGB_ERR_CUDA; }
   return MGB_OK;
