@@ -84,9 +84,21 @@ int mgb_op_conv2d(const void* x, const void* w, const float* bias, const float* 
 }
 
 int mgb_op_flash_attn64(const void* qkv, void* out, int32_t NB, int32_t T, int32_t C, float scale, void* stream) {
+  // split-KV workspace of the operator-level entry point: a process-wide buffer grown on demand (the network
+  // path carves it out of its arena instead)
+  static float* ws = nullptr;
+  static size_t ws_bytes = 0;
+  const size_t need = flash_attn64_ws_bytes(NB, T, C);
+  if (need > ws_bytes) {
+    cudaDeviceSynchronize();
+    if (ws) cudaFree(ws);
+    ws = nullptr; ws_bytes = 0;
+    if (cudaMalloc(&ws, need) != cudaSuccess) { set_error("op_flash_attn64: workspace cudaMalloc(%zu) failed", need); return MGB_ERR_NOMEM; }
+    ws_bytes = need;
+  }
   int rc = launch_flash_attn64(reinterpret_cast<const bf16*>(qkv), reinterpret_cast<bf16*>(out), NB, T, C, scale,
-                               reinterpret_cast<cudaStream_t>(stream));
-  if (!rc) count_launch(1);
+                               need ? ws : nullptr, need ? ws_bytes : 0, reinterpret_cast<cudaStream_t>(stream));
+  if (!rc) count_launch(need ? 2 : 1);
   return rc;
 }
 

@@ -93,7 +93,11 @@ int make_tmap_5d(CUtensorMap* out, const void* base, const uint64_t dims[5], con
 // Flash self-attention, head_dim 64 (attn_tc.cu)
 //   qkv: bf16 [NB * T, 3 * C] (Q | K | V blocks, head h at columns h*64..), out: bf16 [NB * T, C]
 // ---------------------------------------------------------------------------------------------
-int launch_flash_attn64(const bf16* qkv, bf16* out, int NB, int T, int C, float scale, cudaStream_t stream);
+// ws (optional): split-KV workspace of flash_attn64_ws_bytes(); without it the kernel runs unsplit.
+int launch_flash_attn64(const bf16* qkv, bf16* out, int NB, int T, int C, float scale, float* ws, size_t ws_bytes,
+                        cudaStream_t stream);
+int flash_attn64_splits(int NB, int T, int C);
+size_t flash_attn64_ws_bytes(int NB, int T, int C);
 
 // ---------------------------------------------------------------------------------------------
 // Memory-bound kernels (norm.cu, elementwise.cu)

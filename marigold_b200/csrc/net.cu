@@ -218,6 +218,8 @@ static int xfmr_forward(Ctx& c, const XfmrW& X, Act& x, Act& y, int NB, int T) {
   bf16* o = aalloc<bf16>(c, M * C);
   bf16* ffm = aalloc<bf16>(c, M * 4 * C);
   bf16* hsb = aalloc<bf16>(c, M * C);
+  const size_t attn_ws_bytes = flash_attn64_ws_bytes(NB, T, C);
+  float* attn_ws = attn_ws_bytes ? aalloc<float>(c, attn_ws_bytes / sizeof(float)) : nullptr;
 
   TRY(groupnorm(c, x, nullptr, a, nullptr, X.gn, NB, T, 1e-6f, 0));
   { Epi e; e.bias = X.proj_in.b; e.out_f32 = hs0; TRY(linear(c, a, int(M), X.proj_in, e)); }
@@ -225,7 +227,7 @@ static int xfmr_forward(Ctx& c, const XfmrW& X, Act& x, Act& y, int NB, int T) {
   const bool no_ln = skip_family("ln"), no_attn = skip_family("attn"), no_x = skip_family("xattn");
   if (!no_ln) LAUNCH(launch_layernorm(hs0, a, X.ln1.g, X.ln1.b, int(M), C, 1e-5f, c.stream), 1);
   { Epi e; e.out_bf16 = qkv; TRY(linear(c, a, int(M), X.qkv, e)); }
-  if (!no_attn) LAUNCH(launch_flash_attn64(qkv, o, NB, T, C, 0.125f, c.stream), 1);
+  if (!no_attn) LAUNCH(launch_flash_attn64(qkv, o, NB, T, C, 0.125f, attn_ws, attn_ws_bytes, c.stream), attn_ws ? 2 : 1);
   { Epi e; e.bias = X.o1.b; e.residual = hs0; e.out_f32 = hs1; TRY(linear(c, o, int(M), X.o1, e)); }
   // cross attention against the folded empty-prompt K/V
   if (!no_ln) LAUNCH(launch_layernorm(hs1, a, X.ln2.g, X.ln2.b, int(M), C, 1e-5f, c.stream), 1);

@@ -218,6 +218,12 @@ int run_gemm(GemmParams& p, int block_n, float* splitk_ws, cudaStream_t stream) 
   return MGB_OK;
 }
 
+static int tile_model() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("MGB_TILE_MODEL"); v = e ? atoi(e) : 1; }
+  return v;
+}
+
 // Tile-shape heuristic. Cost model (cycles): per CTA  num_kb * 2*BN (tcgen05 floor at M=128)
 // + epilogue ~ 6*BN + fixed 3000; CTAs run in waves of 148 (1 CTA/SM).
 void choose_tile(int m_tiles, int N, int num_kb, bool geglu, bool allow_split, int* block_n, int* splits,
@@ -238,12 +244,23 @@ void choose_tile(int m_tiles, int N, int num_kb, bool geglu, bool allow_split, i
       const long long ctas = (long long)m_tiles * n_tiles * sp;
       const long long waves = (ctas + 147) / 148;
       const int kb = a_ring_bytes > 0 ? 9 * ((num_kb / 9 + sp - 1) / sp) : (num_kb + sp - 1) / sp;
-      double cta_cycles = double(kb) * 2.0 * bn + 6.0 * bn + 3000.0;
-      // small tiles are smem-bandwidth bound: A (16 KB) + B per k-block at 128 B/cycle
-      const double smem_cycles = double(kb) * ((a_ring_bytes > 0 ? 2560.0 : 16384.0) + bn * 128.0) / 128.0 + 6.0 * bn + 3000.0;
-      cta_cycles = std::max(cta_cycles, smem_cycles);
-      double t = waves * cta_cycles;
-      if (sp > 1) t += 4000.0 + double(m_tiles) * 128.0 * N * sp * 4.0 / (148.0 * 64.0);  // reduce pass
+      double t;
+      if (tile_model() == 0) {
+        double cta_cycles = double(kb) * 2.0 * bn + 6.0 * bn + 3000.0;
+        // small tiles are smem-bandwidth bound: A (16 KB) + B per k-block at 128 B/cycle
+        const double smem_cycles = double(kb) * ((a_ring_bytes > 0 ? 2560.0 : 16384.0) + bn * 128.0) / 128.0 + 6.0 * bn + 3000.0;
+        cta_cycles = std::max(cta_cycles, smem_cycles);
+        t = waves * cta_cycles;
+        if (sp > 1) t += 4000.0 + double(m_tiles) * 128.0 * N * sp * 4.0 / (148.0 * 64.0);  // reduce pass
+      } else {
+        // constants measured with tools/conv_phases.py (r01): K block = max(tcgen05 floor 2*BN + 40, issue / smem floor
+        // ~260) cycles; epilogue = ceil(BN / 64) * 2000 (8 warps, 2000 cycles per 32-column chunk per warp);
+        // prologue + first operand latency 3300; a split-K reduce launch costs ~9000 cycles + its traffic
+        const double per_kb = std::max(2.0 * bn + 40.0, 260.0);
+        const double cta_cycles = double(kb) * per_kb + double((bn + 63) / 64) * 2000.0 + 3300.0;
+        t = waves * cta_cycles;
+        if (sp > 1) t += 9000.0 + double(m_tiles) * 128.0 * N * sp * 4.0 / (148.0 * 64.0);
+      }
       if (t < best) { best = t; bbn = bn; bsp = sp; }
     }
   }
