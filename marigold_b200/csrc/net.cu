@@ -50,6 +50,8 @@ struct Epi {
   const float* sched_k = nullptr;
   float* aux_out = nullptr;
   float* cstat = nullptr;   // per-channel (sum, sum^2) of the fp32 output for the consuming GroupNorm
+  float* stat_slot = nullptr;   // where those sums would go; the split-K reduce pass emits them for free
+  int stat_hw = 0;
 };
 
 // Debug only (tools/marginal_cost.py): MGB_SKIP=gn,ln,attn,xattn,concat,gemm drops a kernel family from the graph so
@@ -69,6 +71,17 @@ static void set_epi(GemmParams& p, const Epi& e, int ldo) {
 static int gemm_common(Ctx& c, GemmParams& p, int bn, int splits, const Epi& e, int ldo) {
   if (skip_family("gemm")) return MGB_OK;
   set_epi(p, e, ldo);
+  // OFF by default: measured r01 5.78 -> 6.26 ms/step. 288 reduce blocks x N columns x 2 moments of same-address global
+  // REDs (737k per launch) serialise in L2 (+17 us per launch), more than the 28 statistics launches they save.
+  static const bool splitk_stats = getenv("MGB_SPLITK_STATS") && atoi(getenv("MGB_SPLITK_STATS")) == 1;
+  if (splitk_stats && splits > 1 && !p.epi.cstat && e.stat_slot && !(e.flags & (EPI_GEGLU | EPI_SILU)) && (p.N & 31) == 0 && (ldo & 3) == 0 &&
+      e.stat_hw > 0 && p.M % e.stat_hw == 0) {
+    // the deferred split-K epilogue is a column-owner streaming kernel: the consumer GroupNorm's per-channel sums
+    // cost it 8 REDs per column quad and block, and save a statistics launch
+    p.epi.cstat = e.stat_slot;
+    p.epi.hw = e.stat_hw;
+    c.stat_filled.insert(e.stat_slot);
+  }
   if (splits > 1) {
     const size_t need = size_t(splits) * p.M * p.N * sizeof(float);
     if (need > c.splitk_cap) {
@@ -141,7 +154,10 @@ static Act act_alloc(Ctx& c, size_t M, int C, int NB) {
 // Ask the producer GEMM to accumulate y's channel statistics in its epilogue. Possible when every 128-row
 // tile lies inside one image (conv tiles always do; token tiles need hw % 128 == 0 or a single image).
 static void emit_stats(Ctx& c, Epi& e, Act& y, int NB, int hw, bool conv_mode) {
-  if (!c.fuse_stats || c.dry || !y.cs) return;
+  if (c.dry || !y.cs) return;
+  e.stat_slot = y.cs;
+  e.stat_hw = hw;
+  if (!c.fuse_stats) return;
   if (!conv_mode && NB > 1 && (hw % 128) != 0) return;
   e.cstat = y.cs;
   e.hw = hw;

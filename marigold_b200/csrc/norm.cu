@@ -8,6 +8,8 @@
 //              operand of a ResnetBlock's 1x1 shortcut conv).
 // Semantics: torch.nn.GroupNorm (biased variance) as used by diffusers ResnetBlock2D /
 // Transformer2DModel / VAE blocks; SURVEY.md App. A.1-A.2.
+#include <algorithm>
+#include <cstdlib>
 #include "common.cuh"
 #include "kernels.h"
 #include "launch.h"
@@ -29,7 +31,7 @@ struct GnGeom {
   int chunks, P;  // pixel chunks per image, pixels per chunk (a multiple of Tp * R)
 };
 
-static bool gn_geometry(int HW, int C, GnGeom* g) {
+static bool gn_geometry(int HW, int C, GnGeom* g, int max_chunks = kGnMaxChunks) {
   if (C % 4) return false;
   g->Q = C / 4;
   int best = -1;
@@ -44,7 +46,7 @@ static bool gn_geometry(int HW, int C, GnGeom* g) {
   g->R = kGnLoads / g->Kq;
   const int per_round = g->Tp * g->R;
   long long rounds_total = (HW + per_round - 1) / per_round;
-  long long rounds = (rounds_total + kGnMaxChunks - 1) / kGnMaxChunks;
+  long long rounds = (rounds_total + max_chunks - 1) / max_chunks;
   g->P = int(rounds) * per_round;
   g->chunks = (HW + g->P - 1) / g->P;
   return true;
@@ -252,7 +254,9 @@ __global__ void __launch_bounds__(kGnThreads)
 
 int launch_chan_stats(const float* x, float* cs, int NB, int HW, int C, cudaStream_t stream) {
   GnGeom g;
-  if (!gn_geometry(HW, C, &g)) { set_error("chan_stats: unsupported C=%d", C); return MGB_ERR_INVALID; }
+  // every CTA ends with 2*C same-address global REDs, which serialise in L2: fewer, longer CTAs than the apply pass
+  static const int stat_chunks = getenv("MGB_GN_STAT_CHUNKS") ? atoi(getenv("MGB_GN_STAT_CHUNKS")) : kGnMaxChunks;   // 148 / 296 / 1184 measured identical (r01)
+  if (!gn_geometry(HW, C, &g, std::max(1, stat_chunks / std::max(1, NB)))) { set_error("chan_stats: unsupported C=%d", C); return MGB_ERR_INVALID; }
   dim3 grid(g.chunks, NB);
   const size_t smem = g.Tp > 1 ? 2 * C * sizeof(float) : 0;
   cudaError_t e;
