@@ -117,6 +117,16 @@ class _MarigoldBase:
     def to(self, device=None, *a, **k):       # API compatibility with DiffusionPipeline.to
         return self
 
+    @classmethod
+    def from_pretrained(cls, pretrained_model_name_or_path, variant: Optional[str] = None, torch_dtype=None,
+                        device=None, **kwargs):
+        """Drop-in for `DiffusionPipeline.from_pretrained` as the reference calls it (script/depth/run.py:213-222):
+        a LOCAL diffusers checkpoint directory (README.md:261-290). See marigold_b200/checkpoint.py."""
+        from .checkpoint import load_pipeline
+
+        return load_pipeline(cls, pretrained_model_name_or_path, variant=variant, torch_dtype=torch_dtype, device=device,
+                             **kwargs)
+
     def _set_schedule(self, n: int):
         self.scheduler.set_timesteps(n, device=self.device)
         key = (type(self.scheduler).__name__, n)
