@@ -101,3 +101,21 @@ def test_resize_max_res_matches_reference_golden(name):
     g = GOLD[f"resize/{name}"]
     assert out.shape == g.shape
     assert np.abs(out.numpy().astype(np.int32) - g.astype(np.int32)).max() <= 1   # uint8 rounding of antialias
+
+
+def test_oracle_network_outputs_are_frozen():
+    """tests/golden/network_golden.npz pins the oracle to itself (tests/golden/make_network_golden.py): UNet at three
+    timesteps, VAE encode / decode, 4-step DDIM and LCM depth, 2-step DDIM normals on the seeded tiny model. Tolerance
+    covers oneDNN thread-count / ISA differences between the build container and the GPU box."""
+    from pathlib import Path
+
+    from tests.golden.make_network_golden import compute
+
+    gold = np.load(Path(__file__).resolve().parent / "golden" / "network_golden.npz")
+    got = compute()
+    assert set(got) == set(gold.files)
+    for k in gold.files:
+        a, b = got[k], gold[k]
+        assert a.shape == b.shape, k
+        err = np.abs(a - b).max() / (np.abs(b).max() + 1e-12)
+        assert err < 2e-4, (k, err)
