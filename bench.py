@@ -127,6 +127,12 @@ def run_b200(args):
 
     unet, vae, text = _build_models("full")
     eng = engine_from_oracle(unet, vae, text)
+    del vae                                   # weights live on the device now; only rank 0 keeps the fp32 UNet
+    if rank != 0 or args.no_cpu_baseline:     # (the checker of the cpu_baseline leg)
+        unet = None
+    import gc
+
+    gc.collect()
     K, W = args.steps, args.warmup
     ts, kx, kv, kz = _ddim_tables(W + K)
     eng.set_schedule(ts, kx, kv, kz)
