@@ -281,7 +281,11 @@ def _dominant_kernel_roofline(torch):
     ach = flop / (us * 1e-6) / 1e12
     return {"kernel": "gemm_tc_kernel (implicit-GEMM conv3x3 320->320 @96x96)", "us_per_launch": us,
             "achieved": ach, "peak": pk["tflops_burst"], "unit": "TFLOP/s", "frac": ach / pk["tflops_burst"],
-            "peak_source": pk["source"] + ", bf16_tflops (burst: kernel timed alone)"}
+            "peak_source": pk["source"] + ", bf16_tflops (burst: kernel timed alone)",
+            # one `ncu --set full` capture of this launch (profiles/r01f_ncu_full_summary.txt): dram__bytes_read.sum +
+            # dram__bytes_write.sum. Algorithmic bytes are 19.5e6 (A 5.9e6 bf16, weights 1.8e6, fp32 output 11.8e6): the
+            # operands and the output stay in the 126 MB L2 between kernels, so DRAM sees less than the algorithm moves.
+            "traffic": 7791872, "traffic_source": "ncu r01f, dram read+write bytes per launch"}
 
 
 def _cpu_baseline(unet, text, steps=1, res=RES):
