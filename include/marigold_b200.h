@@ -149,6 +149,11 @@ int mgb_op_conv2d(const void* x_bf16_dev, const void* w_bf16_dev, const float* b
                   float* out_f32_dev, void* out_bf16_dev, int32_t NB, int32_t Hout, int32_t Wout, int32_t Cin,
                   int32_t Cout, int32_t kind, int32_t flags, int32_t block_n, int32_t splits, int32_t stages,
                   float* splitk_ws_dev, void* stream);
+/* Flash self-attention, head size 64 (replaces F.scaled_dot_product_attention under diffusers' Attention, reached
+ * from marigold_depth_pipeline.py:461-463). qkv: [NB*T, 3C] (Q | K | V column blocks), out: [NB*T, C]. Long
+ * sequences are split over KV ranges and merged by a second kernel; the operator-level entry point keeps the
+ * split workspace in a process-wide buffer that it grows on demand (a synchronising cudaMalloc on first use or
+ * growth) and is therefore not re-entrant across threads. The network path carves the workspace out of its arena. */
 int mgb_op_flash_attn64(const void* qkv_bf16_dev, void* out_bf16_dev, int32_t NB, int32_t T, int32_t C, float scale,
                         void* stream);
 /* ws_dev: NB*C*2 floats of scratch (per-channel sums). */
