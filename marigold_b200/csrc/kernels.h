@@ -114,6 +114,11 @@ int launch_chan_stats(const float* x, float* cs, int NB, int HW, int C, cudaStre
 int launch_gn_apply2(const float* xa, const float* csa, int Ca, const float* xb, const float* csb, int Cb, bf16* y,
                      bf16* raw_copy, const float* gamma, const float* beta, int NB, int HW, int G, float eps, int silu,
                      cudaStream_t stream);
+// Order-independent variants (norm_fx.cu): cs holds 64-bit fixed-point sums [NB, C, 2] (zero on entry).
+int launch_chan_stats_fx(const float* x, long long* cs, int NB, int HW, int C, cudaStream_t stream);
+int launch_gn_apply2_fx(const float* xa, const long long* csa, int Ca, const float* xb, const long long* csb, int Cb, bf16* y,
+                        bf16* raw_copy, const float* gamma, const float* beta, int NB, int HW, int G, float eps, int silu,
+                        cudaStream_t stream);
 // LayerNorm over the channel dim: x_f32 [M, C] -> y_bf16 [M, C]
 int launch_layernorm(const float* x, bf16* y, const float* gamma, const float* beta, int M, int C, float eps,
                      cudaStream_t stream);

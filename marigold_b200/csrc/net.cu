@@ -139,11 +139,18 @@ static int conv3x3(Ctx& c, const bf16* x, int NB, int Hout, int Wout, const Conv
   } while (0)
 
 // fp32 trunk tensor [M, C] with its slot in the GroupNorm statistics slab
+// MGB_GN_DETERMINISTIC=1: GroupNorm statistics as 64-bit fixed point (norm_fx.cu): order-independent, hence bit-
+// reproducible runs. Opt-in until validated on the GPU.
+static bool det_stats() {
+  static const bool v = getenv("MGB_GN_DETERMINISTIC") && atoi(getenv("MGB_GN_DETERMINISTIC")) == 1;
+  return v;
+}
+
 static Act act_alloc(Ctx& c, size_t M, int C, int NB) {
   Act a;
   a.p = aalloc<float>(c, M * C);
   a.C = C;
-  const size_t n = size_t(NB) * C * 2;
+  const size_t n = size_t(NB) * C * 2 * (det_stats() ? 2 : 1);   // floats; the fixed-point sums are 8 bytes each
   const size_t off = c.stat_off;
   c.stat_off += n;
   if (c.stat_off > c.stat_need) c.stat_need = c.stat_off;
@@ -154,7 +161,7 @@ static Act act_alloc(Ctx& c, size_t M, int C, int NB) {
 // Ask the producer GEMM to accumulate y's channel statistics in its epilogue. Possible when every 128-row
 // tile lies inside one image (conv tiles always do; token tiles need hw % 128 == 0 or a single image).
 static void emit_stats(Ctx& c, Epi& e, Act& y, int NB, int hw, bool conv_mode) {
-  if (c.dry || !y.cs) return;
+  if (c.dry || !y.cs || det_stats()) return;   // (the producer-epilogue paths write fp32 sums)
   e.stat_slot = y.cs;
   e.stat_hw = hw;
   if (!c.fuse_stats) return;
@@ -174,12 +181,22 @@ static int groupnorm(Ctx& c, Act& a, Act* b, bf16* y, bf16* raw, const NormW& n,
     if (!t || !t->p) continue;
     if (!t->cs) { set_error("groupnorm: statistics slab exhausted"); return MGB_ERR_STATE; }
     if (c.stat_filled.count(t->cs)) continue;
-    TRY(launch_chan_stats(t->p, t->cs, NB, HW, t->C, c.stream));
+    if (det_stats()) {
+      TRY(launch_chan_stats_fx(t->p, reinterpret_cast<long long*>(t->cs), NB, HW, t->C, c.stream));
+    } else {
+      TRY(launch_chan_stats(t->p, t->cs, NB, HW, t->C, c.stream));
+    }
     count_launch(1);
     c.stat_filled.insert(t->cs);
   }
-  TRY(launch_gn_apply2(a.p, a.cs, a.C, b ? b->p : nullptr, b ? b->cs : nullptr, b ? b->C : 0, y, raw, n.g, n.b, NB, HW,
-                       c.groups, eps, silu, c.stream));
+  if (det_stats()) {
+    TRY(launch_gn_apply2_fx(a.p, reinterpret_cast<const long long*>(a.cs), a.C, b ? b->p : nullptr,
+                            b ? reinterpret_cast<const long long*>(b->cs) : nullptr, b ? b->C : 0, y, raw, n.g, n.b, NB, HW,
+                            c.groups, eps, silu, c.stream));
+  } else {
+    TRY(launch_gn_apply2(a.p, a.cs, a.C, b ? b->p : nullptr, b ? b->cs : nullptr, b ? b->C : 0, y, raw, n.g, n.b, NB, HW,
+                         c.groups, eps, silu, c.stream));
+  }
   count_launch(1);
   return MGB_OK;
 }

@@ -1,13 +1,12 @@
-// GroupNorm (+SiLU) and LayerNorm over NHWC / token-major fp32 activations -> bf16 GEMM operands.
-// Both are HBM-bound streaming kernels: 128-bit loads, fp32 statistics, one read of x per pass.
+// Run-to-run deterministic GroupNorm statistics (opt-in: MGB_GN_DETERMINISTIC=1; see net.cu::groupnorm).
 //
-// GroupNorm is two launches so that both are fully parallel over pixels:
-//   gn_stats : grid (chunks, NB): per-(image, chunk, group) partial sum / sum of squares
-//   gn_apply : grid (chunks, NB): combine the partials of its image (double), normalise, affine,
-//              optional SiLU, cast to bf16 (and optionally also emit a raw bf16 copy of x, the
-//              operand of a ResnetBlock's 1x1 shortcut conv).
-// Semantics: torch.nn.GroupNorm (biased variance) as used by diffusers ResnetBlock2D /
-// Transformer2DModel / VAE blocks; SURVEY.md App. A.1-A.2.
+// Same kernels as norm.cu, but the per-channel (sum, sum of squares) are accumulated as 64-bit FIXED POINT
+// (value * 2^30, two's complement through unsigned atomics): integer addition is associative, so the result does
+// not depend on the order in which CTAs reach the atomics, and with it the whole denoising path becomes bit-
+// reproducible. A thread's own partial sums stay fp32 in a fixed order; only the cross-thread / cross-CTA
+// combination is integer. Range: |sum| < 2^33 = 8.6e9 (a 768 x 768 VAE plane of |x| ~ 100 reaches 5.9e9);
+// resolution 2^-30 = 9.3e-10 per contribution.
+// STATUS (round 1): compiled, NOT yet validated on the GPU (the round's GPU budget was spent); off by default.
 #include <algorithm>
 #include <cstdlib>
 #include "common.cuh"
@@ -17,9 +16,10 @@
 
 namespace mgb {
 
-size_t groupnorm_ws_bytes(int NB, int HW, int C, int G) {
-  (void)HW; (void)G;
-  return size_t(NB) * C * 2 * sizeof(float);   // per-channel (sum, sum of squares)
+constexpr double kFxScale = 1073741824.0;        // 2^30
+constexpr double kFxInv = 1.0 / kFxScale;
+__device__ __forceinline__ unsigned long long to_fx(float v) {
+  return static_cast<unsigned long long>(__double2ll_rn(double(v) * kFxScale));
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -27,15 +27,15 @@ size_t groupnorm_ws_bytes(int NB, int HW, int C, int G) {
 // cs must be zero on entry (the network zeroes its whole statistics slab once per forward).
 // -------------------------------------------------------------------------------------------------
 template <int KQ>
-__global__ void __launch_bounds__(kGnThreads) chan_stats_kernel(const float* __restrict__ x, float* __restrict__ cs,
+__global__ void __launch_bounds__(kGnThreads) chan_stats_fx_kernel(const float* __restrict__ x, long long* __restrict__ cs,
                                                                 int HW, int C, GnGeom g) {
   constexpr int R = kGnLoads / KQ;
-  extern __shared__ float s_acc[];  // [2 * C]
+  extern __shared__ unsigned long long s_acc[];  // [2 * C] fixed point
   pdl_launch_dependents();
   const int img = blockIdx.y, chunk = blockIdx.x;
   const bool use_smem = g.Tp > 1;
   if (use_smem) {
-    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) s_acc[i] = 0.f;
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) s_acc[i] = 0ull;
     __syncthreads();
   }
   pdl_wait();
@@ -71,9 +71,9 @@ __global__ void __launch_bounds__(kGnThreads) chan_stats_kernel(const float* __r
     if (active) {
 #pragma unroll
       for (int k = 0; k < KQ; ++k) {
-        float* dst = cs + ((size_t)img * C + 4 * (tq + k * g.Tq)) * 2;
+        unsigned long long* dst = reinterpret_cast<unsigned long long*>(cs) + ((size_t)img * C + 4 * (tq + k * g.Tq)) * 2;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) { atomicAdd(dst + 2 * j, sum[k][j]); atomicAdd(dst + 2 * j + 1, sq[k][j]); }
+        for (int j = 0; j < 4; ++j) { atomicAdd(dst + 2 * j, to_fx(sum[k][j])); atomicAdd(dst + 2 * j + 1, to_fx(sq[k][j])); }
       }
     }
     return;
@@ -84,13 +84,13 @@ __global__ void __launch_bounds__(kGnThreads) chan_stats_kernel(const float* __r
       const int c0 = 4 * (tq + k * g.Tq);
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        atomicAdd(&s_acc[2 * (c0 + j)], sum[k][j]);
-        atomicAdd(&s_acc[2 * (c0 + j) + 1], sq[k][j]);
+        atomicAdd(&s_acc[2 * (c0 + j)], to_fx(sum[k][j]));
+        atomicAdd(&s_acc[2 * (c0 + j) + 1], to_fx(sq[k][j]));
       }
     }
   }
   __syncthreads();
-  float* dst = cs + (size_t)img * C * 2;
+  unsigned long long* dst = reinterpret_cast<unsigned long long*>(cs) + (size_t)img * C * 2;
   for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) atomicAdd(dst + i, s_acc[i]);
 }
 
@@ -102,8 +102,8 @@ __global__ void __launch_bounds__(kGnThreads) chan_stats_kernel(const float* __r
 // -------------------------------------------------------------------------------------------------
 template <int KQ>
 __global__ void __launch_bounds__(kGnThreads)
-    gn_apply2_kernel(const float* __restrict__ xa, const float* __restrict__ csa, int Ca, const float* __restrict__ xb,
-                     const float* __restrict__ csb, int Cb, bf16* __restrict__ y, bf16* __restrict__ raw,
+    gn_apply2_fx_kernel(const float* __restrict__ xa, const long long* __restrict__ csa, int Ca, const float* __restrict__ xb,
+                     const long long* __restrict__ csb, int Cb, bf16* __restrict__ y, bf16* __restrict__ raw,
                      const float* __restrict__ gamma, const float* __restrict__ beta, int HW, int G, float eps, int silu,
                      GnGeom g) {
   constexpr int R = kGnLoads / KQ;
@@ -143,27 +143,29 @@ __global__ void __launch_bounds__(kGnThreads)
   // (2) group statistics: 8 lanes per group (G * 8 <= 256 threads), up to 4 independent loads per lane and pass
   {
     const int gi = threadIdx.x >> 3, part = threadIdx.x & 7;
-    double s = 0.0, q = 0.0;
+    long long si = 0, qi = 0;
     if (gi < G) {
       for (int j0 = part; j0 < cpg; j0 += 32) {
-        float2 t[4];
+        longlong2 t[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
           const int j = j0 + 8 * u, c = gi * cpg + j;
-          t[u] = make_float2(0.f, 0.f);
+          t[u] = make_longlong2(0, 0);
           if (j < cpg)
-            t[u] = c < Ca ? __ldcg(reinterpret_cast<const float2*>(csa + ((size_t)img * Ca + c) * 2))
-                          : __ldcg(reinterpret_cast<const float2*>(csb + ((size_t)img * Cb + (c - Ca)) * 2));
+            t[u] = c < Ca ? __ldcg(reinterpret_cast<const longlong2*>(csa + ((size_t)img * Ca + c) * 2))
+                          : __ldcg(reinterpret_cast<const longlong2*>(csb + ((size_t)img * Cb + (c - Ca)) * 2));
         }
+        // integer accumulation: the group sums are exact and independent of any order
 #pragma unroll
-        for (int u = 0; u < 4; ++u) { s += double(t[u].x); q += double(t[u].y); }
+        for (int u = 0; u < 4; ++u) { si += t[u].x; qi += t[u].y; }
       }
     }
 #pragma unroll
     for (int o = 4; o > 0; o >>= 1) {
-      s += __shfl_xor_sync(0xffffffffu, s, o);
-      q += __shfl_xor_sync(0xffffffffu, q, o);
+      si += __shfl_xor_sync(0xffffffffu, si, o);
+      qi += __shfl_xor_sync(0xffffffffu, qi, o);
     }
+    const double s = double(si) * kFxInv, q = double(qi) * kFxInv;
     if (gi < G && part == 0) {
       const double n = double(HW) * cpg;
       const double mean = s / n;
@@ -217,127 +219,45 @@ __global__ void __launch_bounds__(kGnThreads)
   }
 }
 
-int launch_chan_stats(const float* x, float* cs, int NB, int HW, int C, cudaStream_t stream) {
+int launch_chan_stats_fx(const float* x, long long* cs, int NB, int HW, int C, cudaStream_t stream) {
   GnGeom g;
   // every CTA ends with 2*C same-address global REDs, which serialise in L2: fewer, longer CTAs than the apply pass
-  static const int stat_chunks = getenv("MGB_GN_STAT_CHUNKS") ? atoi(getenv("MGB_GN_STAT_CHUNKS")) : kGnMaxChunks;   // 148 / 296 / 1184 measured identical (r01)
-  if (!gn_geometry(HW, C, &g, std::max(1, stat_chunks / std::max(1, NB)))) { set_error("chan_stats: unsupported C=%d", C); return MGB_ERR_INVALID; }
+  const int stat_chunks = kGnMaxChunks;
+  if (!gn_geometry(HW, C, &g, std::max(1, stat_chunks / std::max(1, NB)))) { set_error("chan_stats_fx: unsupported C=%d", C); return MGB_ERR_INVALID; }
   dim3 grid(g.chunks, NB);
-  const size_t smem = g.Tp > 1 ? 2 * C * sizeof(float) : 0;
+  const size_t smem = g.Tp > 1 ? 2 * C * sizeof(unsigned long long) : 0;
   cudaError_t e;
-  if (g.Kq == 1) e = launch_k(chan_stats_kernel<1>, grid, kGnThreads, smem, stream, x, cs, HW, C, g);
-  else if (g.Kq == 2) e = launch_k(chan_stats_kernel<2>, grid, kGnThreads, smem, stream, x, cs, HW, C, g);
-  else e = launch_k(chan_stats_kernel<4>, grid, kGnThreads, smem, stream, x, cs, HW, C, g);
+  if (g.Kq == 1) e = launch_k(chan_stats_fx_kernel<1>, grid, kGnThreads, smem, stream, x, cs, HW, C, g);
+  else if (g.Kq == 2) e = launch_k(chan_stats_fx_kernel<2>, grid, kGnThreads, smem, stream, x, cs, HW, C, g);
+  else e = launch_k(chan_stats_fx_kernel<4>, grid, kGnThreads, smem, stream, x, cs, HW, C, g);
   if (e == cudaSuccess) e = cudaGetLastError();
-  if (e != cudaSuccess) { set_error("chan_stats launch: %s", cudaGetErrorString(e)); return MGB_ERR_CUDA; }
+  if (e != cudaSuccess) { set_error("chan_stats_fx launch: %s", cudaGetErrorString(e)); return MGB_ERR_CUDA; }
   return MGB_OK;
 }
 
-int launch_gn_apply2(const float* xa, const float* csa, int Ca, const float* xb, const float* csb, int Cb, bf16* y,
+int launch_gn_apply2_fx(const float* xa, const long long* csa, int Ca, const float* xb, const long long* csb, int Cb, bf16* y,
                      bf16* raw_copy, const float* gamma, const float* beta, int NB, int HW, int G, float eps, int silu,
                      cudaStream_t stream) {
   GnGeom g;
   const int C = Ca + Cb;
   if (C % G != 0 || G * 8 > kGnThreads || (Ca & 3) || (Cb & 3) || !gn_geometry(HW, C, &g)) {
-    set_error("groupnorm: unsupported C=%d+%d G=%d", Ca, Cb, G);
+    set_error("groupnorm_fx: unsupported C=%d+%d G=%d", Ca, Cb, G);
     return MGB_ERR_INVALID;
   }
   dim3 grid(g.chunks, NB);
   const size_t smem = 2 * G * sizeof(float);
   cudaError_t e;
   if (g.Kq == 1)
-    e = launch_k(gn_apply2_kernel<1>, grid, kGnThreads, smem, stream, xa, csa, Ca, xb, csb, Cb, y, raw_copy, gamma, beta, HW,
+    e = launch_k(gn_apply2_fx_kernel<1>, grid, kGnThreads, smem, stream, xa, csa, Ca, xb, csb, Cb, y, raw_copy, gamma, beta, HW,
                  G, eps, silu, g);
   else if (g.Kq == 2)
-    e = launch_k(gn_apply2_kernel<2>, grid, kGnThreads, smem, stream, xa, csa, Ca, xb, csb, Cb, y, raw_copy, gamma, beta, HW,
+    e = launch_k(gn_apply2_fx_kernel<2>, grid, kGnThreads, smem, stream, xa, csa, Ca, xb, csb, Cb, y, raw_copy, gamma, beta, HW,
                  G, eps, silu, g);
   else
-    e = launch_k(gn_apply2_kernel<4>, grid, kGnThreads, smem, stream, xa, csa, Ca, xb, csb, Cb, y, raw_copy, gamma, beta, HW,
+    e = launch_k(gn_apply2_fx_kernel<4>, grid, kGnThreads, smem, stream, xa, csa, Ca, xb, csb, Cb, y, raw_copy, gamma, beta, HW,
                  G, eps, silu, g);
   if (e == cudaSuccess) e = cudaGetLastError();
-  if (e != cudaSuccess) { set_error("groupnorm launch: %s", cudaGetErrorString(e)); return MGB_ERR_CUDA; }
-  return MGB_OK;
-}
-
-// Stand-alone GroupNorm (operator-level ABI): ws = per-channel stats scratch [NB, C, 2] (zeroed here).
-int launch_groupnorm(const float* x, bf16* y, bf16* raw_copy, const float* gamma, const float* beta, float* ws,
-                     int NB, int HW, int C, int G, float eps, int silu, cudaStream_t stream) {
-  cudaError_t e = cudaMemsetAsync(ws, 0, size_t(NB) * C * 2 * sizeof(float), stream);
-  if (e != cudaSuccess) { set_error("groupnorm memset: %s", cudaGetErrorString(e)); return MGB_ERR_CUDA; }
-  int rc = launch_chan_stats(x, ws, NB, HW, C, stream);
-  if (rc) return rc;
-  return launch_gn_apply2(x, ws, C, nullptr, nullptr, 0, y, raw_copy, gamma, beta, NB, HW, G, eps, silu, stream);
-}
-
-// -------------------------------------------------------------------------------------------------
-// LayerNorm: one warp per token, values held in registers (C <= 1280 -> <= 10 float4 per lane).
-// Two-pass (mean, then centred variance) like torch.nn.LayerNorm.
-// -------------------------------------------------------------------------------------------------
-constexpr int kLnMaxQ = 10;
-__global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, bf16* __restrict__ y,
-                                                        const float* __restrict__ gamma,
-                                                        const float* __restrict__ beta, int M, int C, float eps) {
-  pdl_launch_dependents();
-  pdl_wait();
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (warp >= M) return;
-  const int Q = C / 4;
-  const float4* xr = reinterpret_cast<const float4*>(x + (size_t)warp * C);
-  float4 v[kLnMaxQ];
-  float s = 0.f;
-#pragma unroll
-  for (int k = 0; k < kLnMaxQ; ++k) {
-    const int q = lane + 32 * k;
-    if (q < Q) {
-      v[k] = __ldg(xr + q);
-      s += v[k].x + v[k].y + v[k].z + v[k].w;
-    }
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-  const float mean = s / C;
-  float ss = 0.f;
-#pragma unroll
-  for (int k = 0; k < kLnMaxQ; ++k) {
-    const int q = lane + 32 * k;
-    if (q < Q) {
-      const float a = v[k].x - mean, b = v[k].y - mean, c = v[k].z - mean, d = v[k].w - mean;
-      ss += a * a + b * b + c * c + d * d;
-    }
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-  const float rstd = rsqrtf(ss / C + eps);
-  uint2* yr = reinterpret_cast<uint2*>(y + (size_t)warp * C);
-  const float4* g4 = reinterpret_cast<const float4*>(gamma);
-  const float4* b4 = reinterpret_cast<const float4*>(beta);
-#pragma unroll
-  for (int k = 0; k < kLnMaxQ; ++k) {
-    const int q = lane + 32 * k;
-    if (q < Q) {
-      const float4 ga = __ldg(g4 + q), be = __ldg(b4 + q);
-      const float o0 = (v[k].x - mean) * rstd * ga.x + be.x, o1 = (v[k].y - mean) * rstd * ga.y + be.y;
-      const float o2 = (v[k].z - mean) * rstd * ga.z + be.z, o3 = (v[k].w - mean) * rstd * ga.w + be.w;
-      yr[q] = make_uint2(pack_bf16x2(o0, o1), pack_bf16x2(o2, o3));
-    }
-  }
-}
-
-int launch_layernorm(const float* x, bf16* y, const float* gamma, const float* beta, int M, int C, float eps,
-                     cudaStream_t stream) {
-  if (C % 4 != 0 || C / 4 > 32 * kLnMaxQ) {
-    set_error("layernorm: unsupported C=%d", C);
-    return MGB_ERR_INVALID;
-  }
-  const int warps_per_block = 8;
-  const int blocks = (M + warps_per_block - 1) / warps_per_block;
-  launch_k(layernorm_kernel, blocks, 256, 0, stream, x, y, gamma, beta, M, C, eps);
-  cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) {
-    set_error("layernorm launch: %s", cudaGetErrorString(e));
-    return MGB_ERR_CUDA;
-  }
+  if (e != cudaSuccess) { set_error("groupnorm_fx launch: %s", cudaGetErrorString(e)); return MGB_ERR_CUDA; }
   return MGB_OK;
 }
 
