@@ -129,3 +129,23 @@ def ensemble_normals(normals: torch.Tensor, output_uncertainty: bool = False, re
         return mean_normals, unc
     idx = sim_cos.argmax(dim=0, keepdim=True).repeat(1, 3, 1, 1)
     return torch.gather(normals, 0, idx), unc
+
+
+def ensemble_iid(targets: torch.Tensor, output_uncertainty: bool = False, reduction: str = "median"
+                 ) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+    """marigold/util/ensemble.py:250-270: per-pixel statistic over the members of an
+    [E, C, H, W] stack of intrinsic-image targets. "median" is torch's LOWER median (no affine alignment and no
+    renormalisation, unlike ensemble_depth), uncertainty = median absolute deviation; "mean" pairs with the
+    (unbiased) standard deviation."""
+    unc = None
+    if reduction == "mean":
+        pred = targets.mean(dim=0, keepdim=True)
+        if output_uncertainty:
+            unc = targets.std(dim=0, keepdim=True)
+    elif reduction == "median":
+        pred = targets.median(dim=0, keepdim=True).values
+        if output_uncertainty:
+            unc = (targets - pred).abs().median(dim=0, keepdim=True).values
+    else:
+        raise ValueError(f"Unrecognized reduction method: {reduction}.")
+    return pred, unc

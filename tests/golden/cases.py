@@ -22,6 +22,12 @@ NORMALS_CASES = {
     "e10_mean": dict(E=10, H=24, W=32, seed=25, kwargs=dict(reduction="mean", output_uncertainty=True)),
     "e4_ties": dict(E=4, H=24, W=32, seed=26, ties=True),
 }
+IID_CASES = {
+    "e2_median": dict(E=2, C=6, H=24, W=32, seed=41),
+    "e5_median_unc": dict(E=5, C=6, H=24, W=32, seed=42, kwargs=dict(output_uncertainty=True)),
+    "e4_mean_unc": dict(E=4, C=9, H=16, W=24, seed=43, kwargs=dict(reduction="mean", output_uncertainty=True)),
+    "e1": dict(E=1, C=6, H=8, W=8, seed=44, kwargs=dict(output_uncertainty=True)),
+}
 RESIZE_CASES = {
     "bilinear_down": dict(H=90, W=130, max_edge=64, method="bilinear", seed=31),
     "bilinear_up": dict(H=30, W=20, max_edge=48, method="bilinear", seed=32),
@@ -61,3 +67,14 @@ def normals_input(cfg) -> torch.Tensor:
 def resize_input(cfg) -> torch.Tensor:
     rng = np.random.default_rng(cfg["seed"])
     return torch.from_numpy(rng.integers(0, 256, size=(1, 3, cfg["H"], cfg["W"]), dtype=np.uint8))
+
+
+def iid_input(cfg) -> torch.Tensor:
+    """[E, C, H, W] in [0,1]: per-member noisy copies of a smooth multi-channel target (albedo / material maps)."""
+    rng = np.random.default_rng(cfg["seed"])
+    E, C, H, W = cfg["E"], cfg["C"], cfg["H"], cfg["W"]
+    base = rng.uniform(0, 1, size=(1, C, 1, 1)) * np.ones((1, C, H, W)) + 0.1 * np.sin(np.linspace(0, 6, W))[None, None, None, :]
+    x = np.clip(base + rng.normal(0, 0.05, size=(E, C, H, W)), 0, 1).astype(np.float32)
+    if E >= 4:
+        x[1] = x[0]            # exact ties
+    return torch.from_numpy(x)

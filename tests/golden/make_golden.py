@@ -14,7 +14,8 @@ ROOT = Path(__file__).resolve().parents[2]
 sys.path.insert(0, str(ROOT))
 
 from tests.golden._ref_shim import load_reference_utils  # noqa: E402
-from tests.golden.cases import DEPTH_CASES, NORMALS_CASES, RESIZE_CASES, depth_input, normals_input, resize_input  # noqa: E402
+from tests.golden.cases import (DEPTH_CASES, IID_CASES, NORMALS_CASES, RESIZE_CASES, depth_input, iid_input,  # noqa: E402
+                                normals_input, resize_input)
 
 ref = load_reference_utils()
 out_dir = Path(__file__).resolve().parent
@@ -36,6 +37,19 @@ so.minimize = _spy
 import scipy  # noqa: E402
 
 scipy.optimize.minimize = _spy
+
+# ensemble_iid (marigold/util/ensemble.py:250-270): a separate small file so that the depth / normals goldens stay
+# byte-identical
+iid = {}
+for name, cfg in IID_CASES.items():
+    pred, unc = ref["ensemble"].ensemble_iid(iid_input(cfg).clone(), **dict(cfg.get("kwargs", {})))
+    iid[f"iid/{name}/pred"] = pred.numpy()
+    if unc is not None:
+        iid[f"iid/{name}/unc"] = unc.numpy()
+np.savez_compressed(out_dir / "iid_golden.npz", **iid)
+print("iid cases", sorted(iid))
+if "--iid-only" in sys.argv:
+    sys.exit(0)
 
 store = {}
 for name, cfg in DEPTH_CASES.items():

@@ -4,11 +4,12 @@ import numpy as np
 import pytest
 import torch
 
-from oracle.ensemble import ensemble_depth, ensemble_normals
+from oracle.ensemble import ensemble_depth, ensemble_iid, ensemble_normals
 from oracle.schedulers import DDIMSchedulerOracle, LCMSchedulerOracle
 from oracle.unet import UNet2DConditionOracle, UNetConfig
 from oracle.vae import AutoencoderKLOracle, VAEConfig
-from tests.golden.cases import DEPTH_CASES, NORMALS_CASES, RESIZE_CASES, depth_input, normals_input, resize_input
+from tests.golden.cases import (DEPTH_CASES, IID_CASES, NORMALS_CASES, RESIZE_CASES, depth_input, iid_input, normals_input,
+                                resize_input)
 
 GOLD = np.load(__file__.rsplit("/", 1)[0] + "/golden/ensemble_golden.npz")
 
@@ -119,3 +120,21 @@ def test_oracle_network_outputs_are_frozen():
         assert a.shape == b.shape, k
         err = np.abs(a - b).max() / (np.abs(b).max() + 1e-12)
         assert err < 2e-4, (k, err)
+
+
+@pytest.mark.parametrize("name", sorted(IID_CASES))
+def test_ensemble_iid_oracle_matches_reference_golden(name):
+    """ensemble_iid (ensemble.py:250-270) against outputs of the reference's own function (tests/golden/make_golden.py):
+    bit-exact, including the lower median on even E, exact ties, E = 1 (std of one member is NaN, like the reference)."""
+    from pathlib import Path
+
+    gold = np.load(Path(__file__).resolve().parent / "golden" / "iid_golden.npz")
+    cfg = IID_CASES[name]
+    pred, unc = ensemble_iid(iid_input(cfg), **dict(cfg.get("kwargs", {})))
+    assert np.array_equal(pred.numpy(), gold[f"iid/{name}/pred"])
+    if f"iid/{name}/unc" in gold.files:
+        assert np.array_equal(unc.numpy(), gold[f"iid/{name}/unc"], equal_nan=True)
+    else:
+        assert unc is None
+    with pytest.raises(ValueError):
+        ensemble_iid(iid_input(cfg), reduction="max")
