@@ -5,6 +5,8 @@ CPU restatement of the control flow of
       (marigold/marigold_depth_pipeline.py:155-338, 397-477, 479-496, 498-516)
   MarigoldNormalsPipeline.__call__ / single_infer / decode_normals
       (marigold/marigold_normals_pipeline.py:140-308, 362-442, 463-479)
+  MarigoldIIDPipeline.__call__ / single_infer / decode_targets / fill_outputs          
+      (marigold/marigold_iid_pipeline.py:239-411, 467-547, 568-585)
 driving the restated networks in oracle/unet.py, oracle/vae.py and schedulers in oracle/schedulers.py.
 
 The reference pipelines subclass diffusers.DiffusionPipeline and cannot be imported here
@@ -22,7 +24,7 @@ import numpy as np
 import torch
 import torch.nn.functional as F
 
-from .ensemble import ensemble_depth, ensemble_normals
+from .ensemble import ensemble_depth, ensemble_iid, ensemble_normals
 from .schedulers import DDIMSchedulerOracle, LCMSchedulerOracle
 
 
@@ -175,3 +177,61 @@ class OracleNormalsPipeline(_OraclePipelineBase):
         if uncert is not None:
             uncert = uncert.squeeze().cpu().numpy()
         return final_pred, uncert, target_preds
+
+
+class OracleIIDPipeline(_OraclePipelineBase):
+    """Intrinsic image decomposition: n_targets 3-channel maps from ONE UNet whose conv_in takes 4 * (n + 1) latent
+    channels and whose conv_out produces 4 * n (marigold_iid_pipeline.py:491-495; src/trainer/marigold_iid_trainer.py:
+    203-246). Returns (pred [1 or E, 3n, H, W] in [0,1], uncertainty or None, members [E, 3n, h, w])."""
+
+    def __init__(self, unet, vae, scheduler, empty_text_embed, target_names,
+                 default_denoising_steps: int = 4, default_processing_resolution: int = 768):
+        super().__init__(unet, vae, scheduler, empty_text_embed, default_denoising_steps, default_processing_resolution)
+        self.target_names = list(target_names)
+        self.n_targets = len(self.target_names)
+
+    def decode_targets(self, target_latent):
+        """:568-585 — one VAE decode per 4-channel chunk, concatenated along channels."""
+        outs = [self._decode_raw(target_latent[:, 4 * i: 4 * (i + 1)]) for i in range(self.n_targets)]
+        return torch.cat(outs, dim=1)
+
+    @torch.no_grad()
+    def single_infer(self, rgb_in, n_steps, noise, step_noise=None):
+        rgb_latent = self.encode_rgb(rgb_in)
+        assert noise.shape[1] == 4 * self.n_targets, "noise must be [B, 4 * n_targets, h, w] (:493-497)"
+        target = self.denoise(rgb_latent, noise.to(rgb_latent), n_steps, step_noise)
+        targets = self.decode_targets(target)
+        return (torch.clip(targets, -1.0, 1.0) + 1.0) / 2.0          # :543-545
+
+    @torch.no_grad()
+    def __call__(self, input_image, denoising_steps: Optional[int] = None, ensemble_size: int = 1,
+                 processing_res: Optional[int] = None, match_input_res: bool = True,
+                 resample_method: str = "bilinear", batch_size: int = 0, ensemble_kwargs=None, *,
+                 noise: torch.Tensor, step_noise: Optional[torch.Tensor] = None):
+        if denoising_steps is None:
+            denoising_steps = self.default_denoising_steps
+        if processing_res is None:
+            processing_res = self.default_processing_resolution
+        assert processing_res >= 0 and ensemble_size >= 1 and denoising_steps >= 1
+        rgb_norm, input_size = self._preprocess(input_image, processing_res, resample_method)
+        bs = batch_size if batch_size > 0 else 1
+        preds = []
+        for s0 in range(0, ensemble_size, bs):
+            e = min(ensemble_size, s0 + bs)
+            sn = step_noise[:, s0:e] if step_noise is not None else None
+            raw = self.single_infer(rgb_norm.expand(e - s0, -1, -1, -1), denoising_steps, noise[s0:e], sn)
+            assert raw.dim() == 4 and raw.shape[1] == 3 * self.n_targets          # :367-370
+            preds.append(raw)
+        members = torch.cat(preds, dim=0)
+        if ensemble_size > 1:
+            final, unc = ensemble_iid(members, **(ensemble_kwargs or {}))          # :376-380
+        else:
+            final, unc = members, None
+        if match_input_res:
+            final = _resize(final, tuple(input_size[-2:]), resample_method)        # :386-392 (uncertainty is NOT resized)
+        return final, unc, members
+
+    def split(self, final, unc=None):
+        """fill_outputs :393-411: target i owns channels [3i, 3i + 3)."""
+        return {name: (final[:, 3 * i: 3 * i + 3], None if unc is None else unc[:, 3 * i: 3 * i + 3])
+                for i, name in enumerate(self.target_names)}

@@ -138,3 +138,31 @@ def test_ensemble_iid_oracle_matches_reference_golden(name):
         assert unc is None
     with pytest.raises(ValueError):
         ensemble_iid(iid_input(cfg), reduction="max")
+
+
+def test_oracle_iid_pipeline_control_flow():
+    """OracleIIDPipeline (marigold_iid_pipeline.py:239-411,467-585) on a seeded 2-target tiny model: conv_in takes
+    4 * (n + 1) channels, conv_out gives 4 * n, every target is decoded separately, E > 1 goes through ensemble_iid."""
+    from oracle.pipeline import OracleIIDPipeline
+    from tests.helpers import synthetic_image
+
+    torch.manual_seed(0)
+    ucfg = UNetConfig.tiny()
+    ucfg.in_channels, ucfg.out_channels = 12, 8
+    unet, vae = UNet2DConditionOracle(ucfg).eval(), AutoencoderKLOracle(VAEConfig.tiny()).eval()
+    text = torch.randn(1, 2, ucfg.cross_attention_dim, generator=torch.Generator().manual_seed(7))
+    pipe = OracleIIDPipeline(unet, vae, DDIMSchedulerOracle(), text, ["albedo", "material"], 2, 128)
+    img = synthetic_image(256)[:, :, :128, :]                     # 128 x 256 input, processed at 64 x 128
+    z = torch.randn(3, 8, 8, 16, generator=torch.Generator().manual_seed(2024))
+    one, unc1, m1 = pipe(img, ensemble_size=1, noise=z[:1])
+    assert one.shape == (1, 6, 128, 256) and unc1 is None and m1.shape == (1, 6, 64, 128)
+    assert 0.0 <= float(one.min()) and float(one.max()) <= 1.0
+    ens, unc, mem = pipe(img, ensemble_size=3, noise=z, batch_size=2, ensemble_kwargs=dict(output_uncertainty=True))
+    assert ens.shape == (1, 6, 128, 256) and unc.shape == (1, 6, 64, 128) and mem.shape == (3, 6, 64, 128)
+    assert torch.allclose(mem[:1], m1, atol=1e-5)                  # member k only depends on noise row k, not on the batching
+    med = mem.median(dim=0, keepdim=True).values
+    assert torch.allclose(pipe(img, ensemble_size=3, noise=z, batch_size=2, match_input_res=False)[0], med, atol=1e-6)
+    parts = pipe.split(ens, None)
+    assert list(parts) == ["albedo", "material"] and parts["material"][0].shape == (1, 3, 128, 256)
+    with pytest.raises(AssertionError):
+        pipe(img, ensemble_size=1, noise=z[:1, :4])                # wrong latent width
