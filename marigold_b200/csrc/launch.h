@@ -17,6 +17,21 @@ inline bool pdl_enabled() {
   return on;
 }
 
+// Launches inside a PlainLaunchScope do NOT get the PDL attribute: the kernel starts only after every earlier kernel
+// of the stream has completed. Needed where a kernel reads, BEFORE its griddepcontrol.wait, memory that an earlier
+// kernel of the same stream writes: gemm_tc_kernel prefetches its first B ("weight") tiles ahead of the wait, which
+// is only safe when B really is a static weight — not for the VAE attention GEMMs whose B operand is K / V^T.
+inline int& plain_launch_depth() {
+  static thread_local int depth = 0;
+  return depth;
+}
+struct PlainLaunchScope {
+  PlainLaunchScope() { ++plain_launch_depth(); }
+  ~PlainLaunchScope() { --plain_launch_depth(); }
+  PlainLaunchScope(const PlainLaunchScope&) = delete;
+  PlainLaunchScope& operator=(const PlainLaunchScope&) = delete;
+};
+
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
                             Args&&... args) {
@@ -29,7 +44,8 @@ inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, siz
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = (pdl_enabled() && stream != nullptr) ? 1 : 0;   // not on the legacy default stream
+  // not on the legacy default stream, not inside a PlainLaunchScope
+  cfg.numAttrs = (pdl_enabled() && stream != nullptr && plain_launch_depth() == 0) ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(std::forward<Args>(args))...);
 }
 

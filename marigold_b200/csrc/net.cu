@@ -10,6 +10,7 @@
 #include <cstdlib>
 #include <cstring>
 
+#include "launch.h"
 #include "net.h"
 
 namespace mgb {
@@ -108,6 +109,9 @@ static int linear(Ctx& c, const bf16* a, int M, const LinW& W, const Epi& e) {
 // generic A[M,K] x B[N,K]^T with raw pointers (attention score / PV GEMMs in the VAE)
 static int matmul_nt(Ctx& c, const bf16* a, const bf16* b, int M, int N, int K, const Epi& e) {
   LinW W; W.w = const_cast<bf16*>(b); W.n = N; W.k = K;
+  // B is an activation written by an earlier kernel of this stream (K, or V^T straight out of the transpose): the
+  // GEMM's pre-wait B prefetch must not run ahead of its producer, so no programmatic early launch here.
+  PlainLaunchScope no_early_launch;
   return linear(c, a, M, W, e);
 }
 
