@@ -6,6 +6,7 @@ Importing the package does not load the CUDA library; the first Engine()/ensembl
 fails loudly if it is unavailable (no CPU fallback)."""
 from .engine import Engine, EngineConfig  # noqa: F401
 from .ensemble import ensemble_depth, ensemble_normals  # noqa: F401
+from .iid import IIDEntry, MarigoldIIDOutput  # noqa: F401
 from .pipeline import (  # noqa: F401
     MarigoldDepthOutput,
     MarigoldDepthPipeline,
@@ -17,4 +18,4 @@ from .schedulers import DDIMScheduler, LCMScheduler  # noqa: F401
 
 __all__ = ["Engine", "EngineConfig", "MarigoldDepthPipeline", "MarigoldNormalsPipeline", "MarigoldPipeline",
            "MarigoldDepthOutput", "MarigoldNormalsOutput", "DDIMScheduler", "LCMScheduler", "ensemble_depth",
-           "ensemble_normals"]
+           "ensemble_normals", "IIDEntry", "MarigoldIIDOutput"]

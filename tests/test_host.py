@@ -123,3 +123,35 @@ def test_colorize_and_resize_helpers():
         get_tv_resample_method("lanczos")
     img = torch.randint(0, 256, (1, 3, 90, 130), dtype=torch.uint8)
     assert resize_max_res(img, 64).shape == (1, 3, 44, 64)     # int() truncation: 90 * 64/130 = 44.3
+
+
+def test_iid_output_container_follows_the_reference():
+    """marigold_b200/iid.py vs marigold_iid_pipeline.py:59-160,393-411: channel ownership, visualisation spaces,
+    error behaviour (KeyError on unknown names, RuntimeError on refill)."""
+    import numpy as np
+    import torch
+
+    from marigold_b200.iid import MarigoldIIDOutput, fill_outputs
+
+    g = torch.Generator().manual_seed(5)
+    pred = torch.rand(1, 6, 8, 12, generator=g)
+    unc = torch.rand(1, 6, 8, 12, generator=g)
+    props = {"target_names": ["albedo", "shading"], "albedo": {"prediction_space": "srgb"},
+             "shading": {"prediction_space": "linear", "up_to_scale": True}}
+    out = MarigoldIIDOutput(props["target_names"])
+    assert not out.is_complete
+    fill_outputs(out, pred, unc, props["target_names"], props)
+    assert out.is_complete and [e.name for e in out] == ["albedo", "shading"]
+    a, s = out["albedo"], out["shading"]
+    assert a.array.shape == (3, 8, 12) and np.array_equal(a.array, pred[0, :3].numpy())
+    assert np.array_equal(s.uncertainty, unc[0, 3:].numpy())
+    assert np.array_equal(np.asarray(a.image), np.moveaxis((pred[0, :3].numpy() * 255).astype(np.uint8), 0, -1))
+    lin = pred[0, 3:].numpy()
+    lin = (lin / max(lin.max(), 1e-6)) ** (1 / 2.2)
+    assert np.array_equal(np.asarray(s.image), np.moveaxis((lin * 255).astype(np.uint8), 0, -1))
+    import pytest
+
+    with pytest.raises(RuntimeError):
+        out.fill_entry("albedo", pred[:, :3], None, props)
+    with pytest.raises(KeyError):
+        out.fill_entry("normals", pred[:, :3], None, props)
