@@ -125,6 +125,9 @@ def run_b200(args):
     dev = torch.device("cuda", local_rank)
     lib = _lib.load()
 
+    from tests.helpers import usable_cores
+
+    torch.set_num_threads(max(1, usable_cores() // max(1, world)))   # N ranks share the box's usable cores
     unet, vae, text = _build_models("full")
     eng = engine_from_oracle(unet, vae, text)
     del vae                                   # weights live on the device now; only rank 0 keeps the fp32 UNet
