@@ -118,6 +118,14 @@ int mgb_decode(mgb_handle* h, const float* latent_dev, int32_t B, int32_t lh, in
 int mgb_ens_depth_cost(mgb_handle* h, const float* depth_dev, const double* param_host, int32_t E, int64_t HW,
                        int32_t scale_invariant, int32_t shift_invariant, int32_t reduction_median,
                        double regularizer, double* cost_out, void* stream);
+/* The same objective for P parameter vectors (params_host [P][2E], or [P][E] when !shift) in ONE launch and ONE
+ * synchronisation: the 2E forward-difference points of one scipy BFGS gradient (ensemble.py:165-171; scipy's
+ * approx_derivative) are one call. costs_out_host [P]. cost(x) is bit-identical to mgb_ens_depth_cost(x). */
+int mgb_ens_depth_cost_batch(mgb_handle* h, const float* depth_dev, const double* params_host, int32_t P, int32_t E,
+                             int64_t HW, int32_t scale_invariant, int32_t shift_invariant, int32_t reduction_median,
+                             double regularizer, double* costs_out_host, void* stream);
+/* Largest ensemble size the ensembling entry points accept (sizes <= 16 run register-resident kernels). */
+int mgb_ens_max_members(void);
 /* init_param statistics (ensemble.py:91-105): per-member min and max. Synchronises. */
 int mgb_ens_minmax(mgb_handle* h, const float* depth_dev, int32_t E, int64_t HW, float* min_host, float* max_host,
                    void* stream);

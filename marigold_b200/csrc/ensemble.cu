@@ -1,8 +1,11 @@
 // Test-time ensembling on the device (reference marigold/util/ensemble.py).
 //
-//  * ens_depth_cost   : the BFGS objective of ensemble_depth (ensemble.py:138-152) in one pass over
-//                       the E aligned maps and ONE host synchronisation (the reference does C(E,2)+2
-//                       `.item()` syncs per evaluation).
+//  * ens_depth_cost   : the BFGS objective of ensemble_depth (ensemble.py:138-152) for P parameter vectors in ONE
+//                       launch (grid.y = parameter set) and ONE host synchronisation: the 2E forward-difference
+//                       points of one scipy gradient are one call (the reference does C(E,2)+2 `.item()` syncs
+//                       per point). The E maps are L2-resident (E x 2.4 MB at 768 px), so re-reading them per
+//                       parameter set costs L2 bandwidth only. Every parameter set runs the same code with the same
+//                       grid.x, so cost(x) is bit-identical whether evaluated alone or inside a batch.
 //  * ens_depth_reduce : align (ensemble.py:107-118) + median/mean (+MAD/std) (:120-136) + min-max
 //                       renormalisation (:184-194), plus the index of the member the lower median picks.
 //  * ens_normals      : ensemble_normals (:199-249): mean -> normalise -> cosine -> clamp -> argmax -> gather.
@@ -18,8 +21,14 @@
 namespace mgb {
 
 constexpr int kEnsThreads = 256;
-constexpr int kEnsMaxBlocks = 148 * 4;
-constexpr int kEnsMaxE = 16;
+constexpr int kEnsMaxBlocks = 148 * 4;     // reduce / normals kernels
+constexpr int kEnsCostBlocks = 148 * 2;    // cost kernels: blocks per parameter set
+constexpr int kEnsMaxE = 16;               // register-resident (templated) kernels; larger ensembles take the *_dyn path
+constexpr int kEnsDynMaxE = 64;
+constexpr int kEnsMaxP = 2 * kEnsDynMaxE + 1;   // parameter sets per batch call (one forward-difference gradient)
+constexpr int kDynPairs = 32;              // pairs per blockIdx.z chunk of the generic cost kernel
+constexpr int kDynBlocks = 48;
+constexpr size_t kDynPartialBytes = size_t(16) << 20;
 
 __device__ __forceinline__ float align1(float d, float s, float t, int shift) {
   // torch: depth * s + t  (two roundings; no FMA)
@@ -49,9 +58,11 @@ struct CostPartial {
 
 template <int E>
 __global__ void __launch_bounds__(kEnsThreads)
-    ens_cost_kernel(const float* __restrict__ depth, const float* __restrict__ st, long long HW, int shift, int median,
-                    CostPartial* __restrict__ partials) {
+    ens_cost_kernel(const float* __restrict__ depth, const float* __restrict__ st_all, long long HW, int shift, int median,
+                    CostPartial* __restrict__ partials_all) {
   constexpr int NP = E * (E - 1) / 2;
+  const float* st = st_all + size_t(blockIdx.y) * 2 * E;                 // this block row's parameter set
+  CostPartial* partials = partials_all + size_t(blockIdx.y) * gridDim.x;
   float s[E], t[E];
 #pragma unroll
   for (int e = 0; e < E; ++e) { s[e] = st[e]; t[e] = st[E + e]; }
@@ -120,9 +131,11 @@ __global__ void __launch_bounds__(kEnsThreads)
   }
 }
 
-__global__ void ens_cost_final_kernel(const CostPartial* __restrict__ partials, int nblocks, int E, long long HW,
-                                      double reg, double* __restrict__ out) {
-  // single block; thread k owns pair k
+__global__ void ens_cost_final_kernel(const CostPartial* __restrict__ partials_all, int nblocks, int E, long long HW,
+                                      double reg, double* __restrict__ out_all) {
+  // one block per parameter set; thread k owns pair k
+  const CostPartial* partials = partials_all + size_t(blockIdx.x) * nblocks;
+  double* out = out_all + 3 * blockIdx.x;
   const int NP = E * (E - 1) / 2;
   __shared__ double sh[128];
   double c = 0.0;
@@ -148,30 +161,181 @@ __global__ void ens_cost_final_kernel(const CostPartial* __restrict__ partials, 
 
 template <int E>
 static void launch_cost_t(const float* depth, const float* st, long long HW, int shift, int median,
-                          CostPartial* partials, int blocks, cudaStream_t stream) {
-  ens_cost_kernel<E><<<blocks, kEnsThreads, 0, stream>>>(depth, st, HW, shift, median, partials);
+                          CostPartial* partials, int blocks, int P, cudaStream_t stream) {
+  ens_cost_kernel<E><<<dim3(blocks, P), kEnsThreads, 0, stream>>>(depth, st, HW, shift, median, partials);
 }
 
-size_t ens_ws_bytes() { return sizeof(CostPartial) * kEnsMaxBlocks + 64 * sizeof(float) + 64; }
-
-// ws layout: [CostPartial x kEnsMaxBlocks][st: 2*kEnsMaxE floats][out: 4 doubles]
-int launch_ens_depth_cost(const float* depth, const float* st_host, int E, long long HW, int shift, int median,
-                          double reg, void* ws, double* out_host_pinned, cudaStream_t stream) {
-  if (E < 2 || E > kEnsMaxE) { set_error("ensemble size %d outside [2, %d]", E, kEnsMaxE); return MGB_ERR_UNSUPPORTED; }
-  CostPartial* partials = reinterpret_cast<CostPartial*>(ws);
-  float* st = reinterpret_cast<float*>(partials + kEnsMaxBlocks);
-  double* out = reinterpret_cast<double*>(st + 2 * kEnsMaxE + 2);
-  cudaError_t e = cudaMemcpyAsync(st, st_host, sizeof(float) * 2 * E, cudaMemcpyHostToDevice, stream);
-  if (e != cudaSuccess) { set_error("ens cost H2D: %s", cudaGetErrorString(e)); return MGB_ERR_CUDA; }
-  const int blocks = int(std::min<long long>((HW + kEnsThreads - 1) / kEnsThreads, kEnsMaxBlocks));
-  switch (E) {
-#define CASE(n) case n: launch_cost_t<n>(depth, st, HW, shift, median, partials, blocks, stream); break;
-    CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8) CASE(9) CASE(10) CASE(11) CASE(12) CASE(13) CASE(14)
-    CASE(15) CASE(16)
-#undef CASE
+// ---- generic ensemble size (E > 16): values in local memory, pairs in chunks of 32 over blockIdx.z ------------------
+// lower median with torch's stable tie order = the element whose rank (count of smaller values, plus equal values with
+// a smaller member index) is (E-1)/2
+__device__ __forceinline__ float select_lower_median(const float* a, int E, int* pick) {
+  const int r = (E - 1) / 2;
+  for (int e = 0; e < E; ++e) {
+    int rank = 0;
+    const float v = a[e];
+    for (int j = 0; j < E; ++j) rank += (a[j] < v) || (a[j] == v && j < e);
+    if (rank == r) { if (pick) *pick = e; return v; }
   }
-  ens_cost_final_kernel<<<1, 128, 0, stream>>>(partials, blocks, E, HW, reg, out);
-  e = cudaMemcpyAsync(out_host_pinned, out, 3 * sizeof(double), cudaMemcpyDeviceToHost, stream);
+  if (pick) *pick = 0;
+  return a[0];   // unreachable for finite inputs
+}
+
+__global__ void __launch_bounds__(kEnsThreads)
+    ens_cost_dyn_kernel(const float* __restrict__ depth, const float* __restrict__ st_all, int E, long long HW, int shift,
+                        int median, double* __restrict__ pair_part /* [P][NP][gridDim.x] */,
+                        float* __restrict__ mm_part /* [P][gridDim.x][2] */) {
+  const int NP = E * (E - 1) / 2;
+  const int ps = blockIdx.y, k0 = blockIdx.z * kDynPairs, nk = min(kDynPairs, NP - k0);
+  __shared__ float s_s[kEnsDynMaxE], s_t[kEnsDynMaxE];
+  __shared__ unsigned char s_pi[kDynPairs], s_pj[kDynPairs];
+  __shared__ double sh[kEnsThreads / 32];
+  __shared__ float shf[2][kEnsThreads / 32];
+  if (threadIdx.x < E) { s_s[threadIdx.x] = st_all[size_t(ps) * 2 * E + threadIdx.x]; s_t[threadIdx.x] = st_all[size_t(ps) * 2 * E + E + threadIdx.x]; }
+  if (threadIdx.x < kDynPairs) {
+    // pair index k0 + threadIdx.x in torch.combinations order: (0,1), (0,2), ..., (1,2), ...
+    int k = k0 + threadIdx.x, i = 0;
+    while (i < E - 1 && k >= E - 1 - i) { k -= E - 1 - i; ++i; }
+    s_pi[threadIdx.x] = (unsigned char)min(i, E - 1);
+    s_pj[threadIdx.x] = (unsigned char)min(i + 1 + k, E - 1);
+  }
+  __syncthreads();
+  float acc[kDynPairs];
+#pragma unroll
+  for (int k = 0; k < kDynPairs; ++k) acc[k] = 0.f;
+  float pmin = FLT_MAX, pmax = -FLT_MAX;
+  float a[kEnsDynMaxE];
+  for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < HW; p += (long long)gridDim.x * blockDim.x) {
+    for (int e = 0; e < E; ++e) a[e] = align1(__ldg(depth + (long long)e * HW + p), s_s[e], s_t[e], shift);
+#pragma unroll
+    for (int k = 0; k < kDynPairs; ++k) {
+      if (k < nk) {
+        const float d = a[s_pi[k]] - a[s_pj[k]];
+        acc[k] = fmaf(d, d, acc[k]);
+      }
+    }
+    if (blockIdx.z == 0) {
+      float pred;
+      if (median) {
+        pred = select_lower_median(a, E, nullptr);
+      } else {
+        float sm = 0.f;
+        for (int e = 0; e < E; ++e) sm += a[e];
+        pred = sm / float(E);
+      }
+      pmin = fminf(pmin, pred);
+      pmax = fmaxf(pmax, pred);
+    }
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < kDynPairs; ++k) {
+    if (k >= nk) break;
+    double v = double(acc[k]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) sh[warp] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double tot = 0.0;
+      for (int w = 0; w < kEnsThreads / 32; ++w) tot += sh[w];
+      pair_part[(size_t(ps) * NP + k0 + k) * gridDim.x + blockIdx.x] = tot;
+    }
+    __syncthreads();
+  }
+  if (blockIdx.z == 0) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      pmin = fminf(pmin, __shfl_xor_sync(0xffffffffu, pmin, o));
+      pmax = fmaxf(pmax, __shfl_xor_sync(0xffffffffu, pmax, o));
+    }
+    if (lane == 0) { shf[0][warp] = pmin; shf[1][warp] = pmax; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      for (int w = 1; w < kEnsThreads / 32; ++w) { pmin = fminf(pmin, shf[0][w]); pmax = fmaxf(pmax, shf[1][w]); }
+      mm_part[(size_t(ps) * gridDim.x + blockIdx.x) * 2] = pmin;
+      mm_part[(size_t(ps) * gridDim.x + blockIdx.x) * 2 + 1] = pmax;
+    }
+  }
+}
+
+__global__ void ens_cost_dyn_final_kernel(const double* __restrict__ pair_part, const float* __restrict__ mm_part, int nblocks,
+                                          int E, long long HW, double reg, double* __restrict__ out_all) {
+  const int NP = E * (E - 1) / 2, ps = blockIdx.x;
+  __shared__ double sh[128];
+  double c = 0.0;
+  for (int k = threadIdx.x; k < NP; k += blockDim.x) {
+    double tot = 0.0;
+    for (int b = 0; b < nblocks; ++b) tot += pair_part[(size_t(ps) * NP + k) * nblocks + b];
+    c += double(sqrtf(float(tot / double(HW))));
+  }
+  sh[threadIdx.x] = c;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double cost = 0.0;
+    for (int i = 0; i < int(blockDim.x); ++i) cost += sh[i];
+    float pmin = FLT_MAX, pmax = -FLT_MAX;
+    for (int b = 0; b < nblocks; ++b) {
+      pmin = fminf(pmin, mm_part[(size_t(ps) * nblocks + b) * 2]);
+      pmax = fmaxf(pmax, mm_part[(size_t(ps) * nblocks + b) * 2 + 1]);
+    }
+    if (reg > 0.0) cost += (double(fabsf(0.0f - pmin)) + double(fabsf(1.0f - pmax))) * reg;
+    double* out = out_all + 3 * ps;
+    out[0] = cost; out[1] = double(pmin); out[2] = double(pmax);
+  }
+}
+
+// ws layout: [partials: max(CostPartial x kEnsCostBlocks x (2 kEnsMaxE + 1), kDynPartialBytes + min/max)]
+//            [st: kEnsMaxP x 2 kEnsDynMaxE floats][out: kEnsMaxP x 3 doubles]
+static size_t ens_partial_bytes() {
+  const size_t t = sizeof(CostPartial) * kEnsCostBlocks * (2 * kEnsMaxE + 1);
+  const size_t d = kDynPartialBytes + size_t(kEnsMaxP) * kDynBlocks * 2 * sizeof(float);
+  return ((t > d ? t : d) + 255) & ~size_t(255);
+}
+size_t ens_ws_bytes() {
+  return ens_partial_bytes() + size_t(kEnsMaxP) * 2 * kEnsDynMaxE * sizeof(float) + size_t(kEnsMaxP) * 3 * sizeof(double) + 256;
+}
+static float* ens_ws_st(void* ws) { return reinterpret_cast<float*>(static_cast<char*>(ws) + ens_partial_bytes()); }
+static double* ens_ws_out(void* ws) { return reinterpret_cast<double*>(ens_ws_st(ws) + size_t(kEnsMaxP) * 2 * kEnsDynMaxE); }
+int ens_max_batch() { return kEnsMaxP; }
+int ens_max_members() { return kEnsDynMaxE; }
+
+// st_host: float [P][2E] = {s_0..s_{E-1}, t_0..t_{E-1}} per parameter set (pinned); out_host_pinned: double [P][3] =
+// {cost, min(pred), max(pred)}. One synchronisation for the whole batch.
+int launch_ens_depth_cost(const float* depth, const float* st_host, int P, int E, long long HW, int shift, int median,
+                          double reg, void* ws, double* out_host_pinned, int* launches, cudaStream_t stream) {
+  if (E < 2 || E > kEnsDynMaxE) { set_error("ensemble size %d outside [2, %d]", E, kEnsDynMaxE); return MGB_ERR_UNSUPPORTED; }
+  if (P < 1 || P > kEnsMaxP) { set_error("ens cost: %d parameter sets outside [1, %d]", P, kEnsMaxP); return MGB_ERR_INVALID; }
+  float* st = ens_ws_st(ws);
+  double* out = ens_ws_out(ws);
+  cudaError_t e = cudaMemcpyAsync(st, st_host, sizeof(float) * 2 * E * P, cudaMemcpyHostToDevice, stream);
+  if (e != cudaSuccess) { set_error("ens cost H2D: %s", cudaGetErrorString(e)); return MGB_ERR_CUDA; }
+  *launches = 0;
+  if (E <= kEnsMaxE) {
+    CostPartial* partials = reinterpret_cast<CostPartial*>(ws);
+    const int blocks = int(std::min<long long>((HW + kEnsThreads - 1) / kEnsThreads, kEnsCostBlocks));
+    switch (E) {
+#define CASE(n) case n: launch_cost_t<n>(depth, st, HW, shift, median, partials, blocks, P, stream); break;
+      CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8) CASE(9) CASE(10) CASE(11) CASE(12) CASE(13) CASE(14)
+      CASE(15) CASE(16)
+#undef CASE
+    }
+    ens_cost_final_kernel<<<P, 128, 0, stream>>>(partials, blocks, E, HW, reg, out);
+    *launches = 2;
+  } else {
+    const int NP = E * (E - 1) / 2, chunks = (NP + kDynPairs - 1) / kDynPairs;
+    const int blocks = int(std::min<long long>((HW + kEnsThreads - 1) / kEnsThreads, kDynBlocks));
+    double* pair_part = reinterpret_cast<double*>(ws);
+    float* mm_part = reinterpret_cast<float*>(static_cast<char*>(ws) + kDynPartialBytes);
+    const int p_max = std::max<int>(1, int(kDynPartialBytes / (size_t(NP) * blocks * sizeof(double))));
+    for (int p0 = 0; p0 < P; p0 += p_max) {
+      const int pn = std::min(p_max, P - p0);
+      ens_cost_dyn_kernel<<<dim3(blocks, pn, chunks), kEnsThreads, 0, stream>>>(depth, st + size_t(p0) * 2 * E, E, HW, shift,
+                                                                               median, pair_part, mm_part);
+      ens_cost_dyn_final_kernel<<<pn, 128, 0, stream>>>(pair_part, mm_part, blocks, E, HW, reg, out + 3 * p0);
+      *launches += 2;
+    }
+  }
+  e = cudaMemcpyAsync(out_host_pinned, out, size_t(P) * 3 * sizeof(double), cudaMemcpyDeviceToHost, stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
   if (e == cudaSuccess) e = cudaGetLastError();
   if (e != cudaSuccess) { set_error("ens cost: %s", cudaGetErrorString(e)); return MGB_ERR_CUDA; }
@@ -296,11 +460,59 @@ __global__ void __launch_bounds__(kEnsThreads)
   }
 }
 
+// generic ensemble size: values in local memory, order statistics by rank counting (same tie order as the sort)
+__global__ void __launch_bounds__(kEnsThreads)
+    ens_reduce_dyn_kernel(const float* __restrict__ depth, const float* __restrict__ st, int E, long long HW, int shift,
+                          int median, float* __restrict__ pred_out, float* __restrict__ unc_out,
+                          int* __restrict__ idx_out, float* __restrict__ block_minmax) {
+  __shared__ float s_s[kEnsDynMaxE], s_t[kEnsDynMaxE];
+  if (threadIdx.x < E) { s_s[threadIdx.x] = st[threadIdx.x]; s_t[threadIdx.x] = st[E + threadIdx.x]; }
+  __syncthreads();
+  float pmin = FLT_MAX, pmax = -FLT_MAX;
+  float a[kEnsDynMaxE], dv[kEnsDynMaxE];
+  for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < HW; p += (long long)gridDim.x * blockDim.x) {
+    for (int e = 0; e < E; ++e) a[e] = align1(__ldg(depth + (long long)e * HW + p), s_s[e], s_t[e], shift);
+    float pred, unc = 0.f;
+    int pick = -1;
+    if (median) {
+      pred = select_lower_median(a, E, &pick);
+      if (unc_out) {
+        for (int e = 0; e < E; ++e) dv[e] = fabsf(a[e] - pred);
+        unc = select_lower_median(dv, E, nullptr);
+      }
+    } else {
+      float sm = 0.f;
+      for (int e = 0; e < E; ++e) sm += a[e];
+      pred = sm / float(E);
+      if (unc_out) {
+        float q = 0.f;
+        for (int e = 0; e < E; ++e) { const float d = a[e] - pred; q += d * d; }
+        unc = sqrtf(q / float(E - 1));
+      }
+    }
+    pred_out[p] = pred;
+    if (unc_out) unc_out[p] = unc;
+    if (idx_out) idx_out[p] = pick;
+    pmin = fminf(pmin, pred); pmax = fmaxf(pmax, pred);
+  }
+  __shared__ float sh[2][kEnsThreads / 32];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    pmin = fminf(pmin, __shfl_xor_sync(0xffffffffu, pmin, o));
+    pmax = fmaxf(pmax, __shfl_xor_sync(0xffffffffu, pmax, o));
+  }
+  if ((threadIdx.x & 31) == 0) { sh[0][threadIdx.x >> 5] = pmin; sh[1][threadIdx.x >> 5] = pmax; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < kEnsThreads / 32; ++w) { pmin = fminf(pmin, sh[0][w]); pmax = fmaxf(pmax, sh[1][w]); }
+    block_minmax[2 * blockIdx.x] = pmin; block_minmax[2 * blockIdx.x + 1] = pmax;
+  }
+}
+
 int launch_ens_depth_reduce(const float* depth, const float* st_host, int E, long long HW, int shift, int median,
                             int use_min, float* pred, float* unc, int* idx, void* ws, cudaStream_t stream) {
-  if (E < 2 || E > kEnsMaxE) { set_error("ensemble size %d outside [2, %d]", E, kEnsMaxE); return MGB_ERR_UNSUPPORTED; }
-  CostPartial* partials = reinterpret_cast<CostPartial*>(ws);
-  float* st = reinterpret_cast<float*>(partials + kEnsMaxBlocks);
+  if (E < 2 || E > kEnsDynMaxE) { set_error("ensemble size %d outside [2, %d]", E, kEnsDynMaxE); return MGB_ERR_UNSUPPORTED; }
+  float* st = ens_ws_st(ws);
   float* bmm = reinterpret_cast<float*>(ws);  // reuse the partial area for block min/max
   cudaError_t e = cudaMemcpyAsync(st, st_host, sizeof(float) * 2 * E, cudaMemcpyHostToDevice, stream);
   if (e != cudaSuccess) { set_error("ens reduce H2D: %s", cudaGetErrorString(e)); return MGB_ERR_CUDA; }
@@ -310,6 +522,8 @@ int launch_ens_depth_reduce(const float* depth, const float* st_host, int E, lon
     CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8) CASE(9) CASE(10) CASE(11) CASE(12) CASE(13) CASE(14)
     CASE(15) CASE(16)
 #undef CASE
+    default:
+      ens_reduce_dyn_kernel<<<blocks, kEnsThreads, 0, stream>>>(depth, st, E, HW, shift, median, pred, unc, idx, bmm);
   }
   ens_renorm_kernel<<<blocks, kEnsThreads, 0, stream>>>(pred, unc, HW, bmm, blocks, use_min);
   e = cudaGetLastError();

@@ -160,9 +160,12 @@ int launch_transpose_bf16(const bf16* x, bf16* y, int M, int N, cudaStream_t str
 // Ensemble kernels (ensemble.cu)
 // ---------------------------------------------------------------------------------------------
 size_t ens_ws_bytes();
-// st_host: float [2E] = {s_0..s_{E-1}, t_0..t_{E-1}}; out_host_pinned: double[3] = {cost, min(pred), max(pred)}
-int launch_ens_depth_cost(const float* depth, const float* st_host, int E, long long HW, int shift, int median,
-                          double reg, void* ws, double* out_host_pinned, cudaStream_t stream);
+int ens_max_batch();     // parameter sets per launch_ens_depth_cost call
+int ens_max_members();   // largest supported ensemble size
+// st_host (pinned): float [P][2E] = {s_0..s_{E-1}, t_0..t_{E-1}} per parameter set; out_host_pinned: double [P][3] =
+// {cost, min(pred), max(pred)}; one synchronisation per call. *launches = kernels launched.
+int launch_ens_depth_cost(const float* depth, const float* st_host, int P, int E, long long HW, int shift, int median,
+                          double reg, void* ws, double* out_host_pinned, int* launches, cudaStream_t stream);
 int launch_ens_minmax(const float* depth, int E, long long HW, float* ws, float* host_pinned, int* blocks_out,
                       cudaStream_t stream);
 int launch_ens_depth_reduce(const float* depth, const float* st_host, int E, long long HW, int shift, int median,

@@ -3,7 +3,10 @@ backed by the CUDA kernels in csrc/ensemble.cu.
 
 Same signatures, defaults, error behaviour and return shapes as the reference. The scipy BFGS driver
 stays on the host exactly as in the reference (ensemble.py:165-171); what changes is the objective:
-one fused pass + one host sync per evaluation instead of C(E,2)+2 `.item()` syncs.
+one fused pass + one host sync per evaluation instead of C(E,2)+2 `.item()` syncs, and the 2E
+forward-difference points of one gradient are ONE launch + ONE sync (`mgb_ens_depth_cost_batch`): scipy's
+own `approx_derivative` still forms the differences (its `workers=` map hook receives the perturbed
+vectors), so the trajectory semantics are the reference's.
 """
 from __future__ import annotations
 
@@ -37,6 +40,40 @@ def _resize_max_res_nearest_exact(img: torch.Tensor, max_edge: int) -> torch.Ten
     h, w = img.shape[-2:]
     f = min(max_edge / w, max_edge / h)
     return torch.nn.functional.interpolate(img, size=(int(h * f), int(w * f)), mode="nearest-exact")
+
+
+_EPS = float(np.sqrt(np.finfo(np.float64).eps))   # scipy.optimize._optimize._epsilon (BFGS default `eps`)
+
+
+def _fd_jac(cost_fn, cost_batch):
+    """scipy's 2-point forward difference with an absolute step (approx_derivative as BFGS calls it with jac=None:
+    `abs_step=eps`, f0 = f(x)) restated for scipy versions without the `workers=` hook; the 2E points are one batch."""
+    def jac(x):
+        x = np.asarray(x, dtype=np.float64)
+        h = np.full_like(x, _EPS)
+        dx = (x + h) - x
+        sign = (x >= 0).astype(np.float64) * 2 - 1
+        h = np.where(dx == 0, _EPS * sign * np.maximum(1.0, np.abs(x)), h)
+        xs = np.repeat(x[None], x.size, 0)
+        xs[np.arange(x.size), np.arange(x.size)] = x + h
+        f = cost_batch(np.concatenate([x[None], xs]))
+        return (f[1:] - f[0]) / ((x + h) - x)
+    return jac
+
+
+def _bfgs(cost_fn, cost_batch, fd_map, param0, tol, max_iter):
+    """scipy.optimize.minimize(..., method="BFGS", tol=tol, options={"maxiter": max_iter}) exactly as the reference
+    calls it (ensemble.py:165-171), with the finite-difference points evaluated as one device batch."""
+    import scipy.optimize
+
+    opts = {"maxiter": max_iter, "disp": False}
+    ver = tuple(int(v) for v in scipy.__version__.split(".")[:2])
+    if ver >= (1, 16):
+        res = scipy.optimize.minimize(cost_fn, param0, method="BFGS", tol=tol, options={**opts, "workers": fd_map})
+    else:
+        res = scipy.optimize.minimize(cost_fn, param0, jac=_fd_jac(cost_fn, cost_batch), method="BFGS", tol=tol,
+                                      options=opts)
+    return res.x, res.nit
 
 
 def ensemble_depth(
@@ -89,24 +126,30 @@ def ensemble_depth(
         else:
             param0 = (np.float32(1.0) / np.maximum(mx, np.float32(1e-6))).astype(np.float64)
 
-        n_eval = [0]
+        n_eval = [0, 0]   # objective evaluations, device round trips
+
+        def cost_batch(params) -> np.ndarray:
+            """cost_fn (ensemble.py:138-152) for a stack of parameter vectors: one launch, one sync."""
+            P = np.ascontiguousarray(np.atleast_2d(np.asarray(params, dtype=np.float64)))
+            out = np.empty(P.shape[0], dtype=np.float64)
+            check(lib.mgb_ens_depth_cost_batch(h, ptr(d_align), P.ctypes.data_as(C.c_void_p), P.shape[0], E, hw_a, sc,
+                                               sh, median, float(regularizer_strength),
+                                               out.ctypes.data_as(C.c_void_p), stream_ptr()),
+                  "mgb_ens_depth_cost_batch")
+            n_eval[0] += P.shape[0]
+            n_eval[1] += 1
+            return out
 
         def cost_fn(param: np.ndarray) -> float:
-            p = np.ascontiguousarray(param, dtype=np.float64)
-            out = C.c_double()
-            check(lib.mgb_ens_depth_cost(h, ptr(d_align), p.ctypes.data_as(C.c_void_p), E, hw_a, sc, sh, median,
-                                         float(regularizer_strength), C.byref(out), stream_ptr()),
-                  "mgb_ens_depth_cost")
-            n_eval[0] += 1
-            return out.value
+            return float(cost_batch(param)[0])
+
+        def fd_map(fun, xs):
+            """scipy's finite-difference hook (`workers=`, scipy >= 1.16): all perturbed points in one call."""
+            return [np.atleast_1d(c) for c in cost_batch(list(xs))]
 
         nit = 0
         if param is None:
-            import scipy.optimize
-
-            res = scipy.optimize.minimize(cost_fn, param0, method="BFGS", tol=tol,
-                                          options={"maxiter": max_iter, "disp": False})
-            param, nit = res.x, res.nit
+            param, nit = _bfgs(cost_fn, cost_batch, fd_map, param0, tol, max_iter)
         param = np.ascontiguousarray(param, dtype=np.float64)   # (tests may inject the alignment)
 
         pred = torch.empty(1, 1, H, W, dtype=torch.float32, device=depth.device)
@@ -119,7 +162,7 @@ def ensemble_depth(
         unc = unc.to(depth.dtype)
     if return_aux:
         return pred, unc, {"param": param, "param0": param0, "member_idx": idx, "nit": nit, "nfev": n_eval[0],
-                            "cost_fn": cost_fn}
+                            "round_trips": n_eval[1], "cost_fn": cost_fn, "cost_batch": cost_batch}
     return pred, unc
 
 

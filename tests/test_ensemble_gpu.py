@@ -142,3 +142,57 @@ def test_median_and_argmax_index_properties_full_size(E):
     idx = (m * n).sum(1, keepdim=True).clamp(-1, 1).argmax(0, keepdim=True)
     assert torch.equal(aux["member_idx"].cpu().long(), idx)
     assert torch.equal(out.cpu(), torch.gather(n, 0, idx.repeat(1, 3, 1, 1)))
+
+
+def test_cost_batch_is_one_round_trip_and_bit_identical():
+    """One forward-difference gradient (2E points) = ONE device round trip, and cost(x) evaluated inside a batch
+    equals cost(x) evaluated alone bit for bit (otherwise scipy's f(x+h) - f(x) would pick up summation noise)."""
+    from marigold_b200.ensemble import ensemble_depth
+
+    E = 10
+    g = torch.Generator().manual_seed(3)
+    d = torch.rand(E, 1, 96, 128, generator=g).cuda()
+    p0 = np.concatenate([np.ones(E), np.zeros(E)])
+    _, _, aux = ensemble_depth(d, return_aux=True, param=p0)
+    rng = np.random.default_rng(0)
+    P = p0[None] + rng.normal(0, 1e-2, (2 * E + 1, 2 * E))
+    batch = aux["cost_batch"](P)
+    single = np.array([aux["cost_fn"](p) for p in P])
+    np.testing.assert_array_equal(batch, single)
+    # end to end: round trips = objective calls + gradient calls, far fewer than evaluated points
+    _, _, aux2 = ensemble_depth(d, return_aux=True)
+    assert aux2["nfev"] >= aux2["round_trips"]
+    if aux2["nit"] > 0:
+        assert aux2["round_trips"] * (E + 1) <= aux2["nfev"] + 2 * (E + 1)
+
+
+@pytest.mark.parametrize("E,reduction", [(20, "median"), (17, "mean"), (33, "median")])
+def test_large_ensembles_generic_path(E, reduction):
+    """ensemble_size > 16 (the reference accepts any size; 20 is a common setting) runs the generic kernels:
+    objective, reduce, uncertainty and the lower-median index against torch on the same inputs."""
+    from marigold_b200.ensemble import ensemble_depth
+
+    g = torch.Generator().manual_seed(E)
+    d = torch.rand(E, 1, 64, 80, generator=g)
+    d[3] = d[5]                                  # exact ties across members
+    rng = np.random.default_rng(E)
+    p = np.concatenate([1 + 0.1 * rng.standard_normal(E), 0.05 * rng.standard_normal(E)])
+    pred, unc, aux = ensemble_depth(d.cuda(), return_aux=True, param=p, reduction=reduction, output_uncertainty=True)
+    s, t = np.split(p, 2)
+    a = d * torch.from_numpy(s).float().view(E, 1, 1, 1) + torch.from_numpy(t).float().view(E, 1, 1, 1)
+    if reduction == "median":
+        med = torch.median(a, dim=0, keepdim=True).values
+        assert torch.equal(torch.gather(a, 0, aux["member_idx"].cpu().long()), med)
+        u = torch.median((a - med).abs(), dim=0, keepdim=True).values
+    else:
+        med = a.mean(0, keepdim=True)
+        u = a.std(0, keepdim=True)
+    lo, hi = med.min(), med.max()
+    assert torch.allclose(pred.cpu(), (med - lo) / (hi - lo), atol=2e-6)
+    assert torch.allclose(unc.cpu(), u / (hi - lo), atol=2e-6)
+    ref = _ref_cost(d, p, True, reduction, 0.02)
+    mine = aux["cost_fn"](p)
+    assert abs(mine - ref) <= 2e-6 * max(1.0, abs(ref)), (mine, ref)
+    # and the optimiser runs end to end
+    pred2, _ = ensemble_depth(d.cuda(), reduction=reduction, max_iter=2)
+    assert torch.isfinite(pred2).all() and float(pred2.min()) == 0.0 and abs(float(pred2.max()) - 1.0) < 1e-6

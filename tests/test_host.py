@@ -155,3 +155,39 @@ def test_iid_output_container_follows_the_reference():
         out.fill_entry("albedo", pred[:, :3], None, props)
     with pytest.raises(KeyError):
         out.fill_entry("normals", pred[:, :3], None, props)
+
+
+def test_bfgs_driver_follows_scipy_default_finite_differences():
+    """marigold_b200.ensemble._bfgs evaluates the 2E forward-difference points of a gradient as one batch; the
+    trajectory must be the one scipy's own default (jac=None) produces — with the `workers=` hook and with the
+    restated jac for older scipy versions alike (reference call: marigold/util/ensemble.py:165-171)."""
+    import scipy.optimize
+
+    from marigold_b200.ensemble import _bfgs, _fd_jac
+
+    rng = np.random.default_rng(0)
+    A = rng.standard_normal((6, 6))
+    A = A @ A.T + np.eye(6)
+    b = rng.standard_normal(6)
+
+    def f(x):
+        x = np.asarray(x, dtype=np.float64)
+        return float(np.float32(0.5 * x @ A @ x - b @ x + 0.1 * np.abs(x).sum()))   # fp32-rounded like the device cost
+
+    def f_batch(xs):
+        return np.array([f(x) for x in np.atleast_2d(xs)])
+
+    calls = []
+
+    def fd_map(fun, xs):
+        xs = list(xs)
+        calls.append(len(xs))
+        return [np.atleast_1d(c) for c in f_batch(xs)]
+
+    x0 = rng.standard_normal(6)
+    ref = scipy.optimize.minimize(f, x0, method="BFGS", tol=1e-6, options={"maxiter": 50, "disp": False})
+    x1, nit1 = _bfgs(f, f_batch, fd_map, x0, 1e-6, 50)
+    np.testing.assert_array_equal(x1, ref.x)
+    assert nit1 == ref.nit and calls and all(c == 6 for c in calls)
+    alt = scipy.optimize.minimize(f, x0, jac=_fd_jac(f, f_batch), method="BFGS", tol=1e-6, options={"maxiter": 50})
+    np.testing.assert_array_equal(alt.x, ref.x)
