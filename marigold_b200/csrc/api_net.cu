@@ -255,8 +255,7 @@ void mgb_destroy(mgb_handle* h) {
   if (h->arena.base) cudaFree(h->arena.base);
   if (h->splitk_ws) cudaFree(h->splitk_ws);
   if (h->sched_k) cudaFree(h->sched_k);
-  if (h->gn_ws) cudaFree(h->gn_ws);
-  if (h->stat_slab) cudaFree(h->stat_slab);
+  if (h->sync_slab) cudaFree(h->sync_slab);
   if (h->bias_table) cudaFree(h->bias_table);
   if (h->cur_bias) cudaFree(h->cur_bias);
   if (h->cur_sched_k) cudaFree(h->cur_sched_k);
@@ -534,16 +533,15 @@ static int ensure_workspace(mgb_handle* h, int op, int NB, int d0, int d1) {
     h->splitk_ws = static_cast<float*>(p);
     h->splitk_cap = c.splitk_need;
   }
-  const size_t stat_need = c.stat_need * sizeof(float);
-  if (stat_need > h->stat_slab_bytes) {
+  if (c.sync_need > h->sync_slab_count) {
     CUDA_TRY(cudaDeviceSynchronize());
     if (h->step_graph.exec) { cudaGraphExecDestroy(h->step_graph.exec); h->step_graph.exec = nullptr; }
-    if (h->stat_slab) CUDA_TRY(cudaFree(h->stat_slab));
-    h->stat_slab = nullptr; h->stat_slab_bytes = 0;
+    if (h->sync_slab) CUDA_TRY(cudaFree(h->sync_slab));
+    h->sync_slab = nullptr; h->sync_slab_count = 0;
     void* p = nullptr;
-    CUDA_TRY(cudaMalloc(&p, stat_need));
-    h->stat_slab = static_cast<float*>(p);
-    h->stat_slab_bytes = stat_need;
+    CUDA_TRY(cudaMalloc(&p, c.sync_need * sizeof(unsigned)));
+    h->sync_slab = static_cast<unsigned*>(p);
+    h->sync_slab_count = c.sync_need;
   }
   return MGB_OK;
 }
@@ -597,8 +595,8 @@ static Ctx make_ctx(mgb_handle* h, void* stream) {
   c.dry = false;
   c.splitk_ws = h->splitk_ws; c.splitk_cap = h->splitk_cap;
   c.groups = h->cfg.norm_groups;
-  c.stat_base = h->stat_slab;
-  c.stat_cap = h->stat_slab_bytes / sizeof(float);
+  c.sync_base = h->sync_slab;
+  c.sync_cap = h->sync_slab_count;
   return c;
 }
 
@@ -733,8 +731,6 @@ int mgb_decode(mgb_handle* h, const float* latent, int32_t B, int32_t lh, int32_
 }
 
 /* debug hooks (not in the public header) */
-void mgb_debug_set_fuse_stats(mgb_handle* h, int on) { if (h) h->dbg_fuse_stats = on != 0; }
-void* mgb_debug_stat_slab(mgb_handle* h, size_t* nfloats) { if (nfloats) *nfloats = h->stat_slab_bytes / 4; return h->stat_slab; }
 
 size_t mgb_workspace_bytes(mgb_handle* h, int32_t B, int32_t H, int32_t W) {
   if (!h || !h->finalized || B <= 0 || H % 64 || W % 64) return 0;

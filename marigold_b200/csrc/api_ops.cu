@@ -28,7 +28,6 @@ const char* mgb_build_info(void) {
 }
 int64_t mgb_launch_count(void) { return launch_count(); }
 /* debug hook (not in the public header): per-CTA clock64 phase stamps of subsequent GEMM launches */
-void mgb_debug_gemm_cstat(void* dev_buffer, int hw) { set_gemm_debug_cstat(reinterpret_cast<float*>(dev_buffer), hw); }
 void mgb_debug_gemm_timing(void* dev_buffer) { set_gemm_debug_buffer(reinterpret_cast<long long*>(dev_buffer)); }
 
 static void fill_epi(GemmEpilogue* e, const float* bias, const float* residual, float* out_f32, void* out_bf16,
@@ -101,6 +100,8 @@ int mgb_op_flash_attn64(const void* qkv, void* out, int32_t NB, int32_t T, int32
   if (!rc) count_launch(need ? 2 : 1);
   return rc;
 }
+
+size_t mgb_op_groupnorm_ws_bytes(int32_t NB, int32_t HW, int32_t C, int32_t G) { return groupnorm_ws_bytes(NB, HW, C, G); }
 
 int mgb_op_groupnorm(const float* x, void* y, const float* gamma, const float* beta, float* ws, int32_t NB, int32_t HW,
                      int32_t C, int32_t G, float eps, int32_t silu, void* stream) {

@@ -483,15 +483,6 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
       const float scale = (!raw && (e.flags & EPI_SCALE)) ? e.scale : 1.0f;
       const bool silu = !raw && (e.flags & EPI_SILU);
       const bool ld_vec = (ldo & 3) == 0;
-      float* cstat = raw ? nullptr : e.cstat;
-      // per-CTA column (sum, sum^2) in the drained B pipeline memory; one RED per column and moment per CTA
-      float* colsum = reinterpret_cast<float*>(smem_b + size_t(stages) * kBBytes) - 2 * BLOCK_N;   // tail of the B ring
-      const int etid = threadIdx.x - 64;
-      if (cstat) {
-        for (int i = etid; i < 2 * BLOCK_N; i += 32 * kEpiWarps) colsum[i] = 0.f;
-        asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
-      }
-      const int stat_img = p.mode != 0 ? img : int(((long long)m_tile * BLOCK_M) / (e.hw > 0 ? e.hw : 1));
       // row addressing hoisted out of the chunk loop: after the transpose this lane stores rows
       // R = it * 4 + (lane >> 3), it = 0..7, of its warp's 32-row slab
       long long off[8];
@@ -548,7 +539,6 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
               rr[it] = ((vmask >> it) & 1u) ? __ldg(reinterpret_cast<const float4*>(residual + off[it] + col))
                                            : make_float4(0.f, 0.f, 0.f, 0.f);
           }
-          float cs[4] = {0.f, 0.f, 0.f, 0.f}, cq[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
           for (int it = 0; it < 8; ++it) {
             float4 v = x[it];
@@ -560,28 +550,6 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
               if (out_f32) *reinterpret_cast<float4*>(out_f32 + o) = v;
               if (out_bf16)
                 *reinterpret_cast<uint2*>(out_bf16 + o) = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
-              cs[0] += v.x; cs[1] += v.y; cs[2] += v.z; cs[3] += v.w;
-              cq[0] = fmaf(v.x, v.x, cq[0]); cq[1] = fmaf(v.y, v.y, cq[1]);
-              cq[2] = fmaf(v.z, v.z, cq[2]); cq[3] = fmaf(v.w, v.w, cq[3]);
-            }
-          }
-          if (cstat) {
-            // GroupNorm statistics for the consumer: column sums over this warp's 32 rows (the 4 row
-            // sub-groups sit in lane bits 3..4), then one RED per column and moment from lanes 0..7
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              cs[k] += __shfl_xor_sync(0xffffffffu, cs[k], 8);
-              cq[k] += __shfl_xor_sync(0xffffffffu, cq[k], 8);
-              cs[k] += __shfl_xor_sync(0xffffffffu, cs[k], 16);
-              cq[k] += __shfl_xor_sync(0xffffffffu, cq[k], 16);
-            }
-            if (sub == 0) {
-              float* dst = colsum + (j * 32 + c4) * 2;      // per-CTA column sums (4 warps -> 1)
-#pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                atomicAdd(dst + 2 * k, cs[k]);
-                atomicAdd(dst + 2 * k + 1, cq[k]);
-              }
             }
           }
         } else {
@@ -618,13 +586,6 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
         __syncwarp();
         if (dbg && j < 2 && threadIdx.x == 64) { dbg[6 + j] = ((c1 - c0) << 32) | (clock64() - c1); }
       }
-      if (cstat) {
-        asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
-        for (int i = etid; i < 2 * BLOCK_N; i += 32 * kEpiWarps) {
-          const int cidx = n0 + (i >> 1);
-          if (cidx < n_out) atomicAdd(cstat + ((long long)stat_img * ldo + cidx) * 2 + (i & 1), colsum[i]);
-        }
-      }
     }
     if (dbg && threadIdx.x == 64) dbg[4] = clock64();
     tc_fence_before();
@@ -640,8 +601,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
 
 // -------------------------------------------------------------------------------------------------
 // Split-K deferred epilogue: sum the partials, then the same fused epilogue on CUDA cores.
-// Column-owner mapping: a thread owns up to kSkQuads column quads and walks a block of rows of ONE image,
-// so the per-channel GroupNorm statistics stay in registers and cost 8 REDs per quad per block.
+// Column-owner mapping: a thread owns up to kSkQuads column quads and walks a block of rows (fixed summation order
+// over the splits: deterministic).
 // -------------------------------------------------------------------------------------------------
 constexpr int kSkThreads = 256;
 constexpr int kSkQuads = 3;      // N <= 3072
@@ -663,7 +624,6 @@ __global__ void __launch_bounds__(kSkThreads) splitk_epilogue_kernel(const GemmP
     const int c = q * 4;
     float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
     if (e.bias) b4 = __ldg(reinterpret_cast<const float4*>(e.bias + c));
-    float cs[4] = {0.f, 0.f, 0.f, 0.f}, cq[4] = {0.f, 0.f, 0.f, 0.f};
     for (int m = r0; m < r1; ++m) {
       const float* src = p.partial + (size_t)m * p.N + c;
       float4 a = __ldg(reinterpret_cast<const float4*>(src));
@@ -682,13 +642,6 @@ __global__ void __launch_bounds__(kSkThreads) splitk_epilogue_kernel(const GemmP
       }
       if (e.out_f32) *reinterpret_cast<float4*>(e.out_f32 + o) = make_float4(v[0], v[1], v[2], v[3]);
       if (e.out_bf16) *reinterpret_cast<uint2*>(e.out_bf16 + o) = make_uint2(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]));
-#pragma unroll
-      for (int j = 0; j < 4; ++j) { cs[j] += v[j]; cq[j] = fmaf(v[j], v[j], cq[j]); }
-    }
-    if (e.cstat) {
-      float* dst = e.cstat + ((long long)img * e.ldo + c) * 2;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) { atomicAdd(dst + 2 * j, cs[j]); atomicAdd(dst + 2 * j + 1, cq[j]); }
     }
   }
 }
@@ -699,16 +652,10 @@ __global__ void __launch_bounds__(kSkThreads) splitk_epilogue_kernel(const GemmP
 static long long* g_gemm_dbg = nullptr;
 void set_gemm_debug_buffer(long long* dev_ptr) { g_gemm_dbg = dev_ptr; }
 
-
-static float* g_dbg_cstat = nullptr;
-static int g_dbg_cstat_hw = 0;
-void set_gemm_debug_cstat(float* p, int hw) { g_dbg_cstat = p; g_dbg_cstat_hw = hw; }
-
 template <int BN>
 static int launch_one(const GemmParams& p_in, int splits, cudaStream_t stream) {
   GemmParams p = p_in;
   p.dbg = g_gemm_dbg;
-  if (g_dbg_cstat) { p.epi.cstat = g_dbg_cstat; p.epi.hw = g_dbg_cstat_hw; }
   const size_t smem = gemm_smem_bytes(BN, p.stages, p.mode == 2 ? p.halo_slots * p.halo_slot_bytes : -1);
   static bool attr_set = false;  // per template instantiation
   if (!attr_set) {
@@ -743,7 +690,6 @@ int launch_gemm_tc(const GemmParams& p, int block_n, int splits, cudaStream_t st
 int launch_splitk_epilogue(const GemmParams& p_in, int block_n, int splits, cudaStream_t stream) {
   (void)block_n;
   GemmParams p = p_in;
-  if (g_dbg_cstat) { p.epi.cstat = g_dbg_cstat; p.epi.hw = g_dbg_cstat_hw; }
   if ((p.epi.flags & EPI_GEGLU) || (p.N & 3) || (p.epi.ldo & 3) || p.N / 4 > kSkThreads * kSkQuads) {
     set_error("split-K epilogue: unsupported shape/flags (N=%d ldo=%d flags=%d)", p.N, p.epi.ldo, p.epi.flags);
     return int(cudaErrorInvalidValue);

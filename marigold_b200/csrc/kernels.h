@@ -43,8 +43,6 @@ struct GemmEpilogue {
   const float* sched_z;   // EPI_SCHED: fresh noise     [M, ldo] or nullptr
   const float* sched_k;   // EPI_SCHED: device pointer to {kx, kv, kz}
   float* aux_out;         // EPI_SCHED: optional raw model output (acc + bias) [M, ldo], or nullptr
-  float* cstat;           // optional per-channel (sum, sum^2) of the stored fp32 output: [img, ldo, 2] += ... (GroupNorm
-                          // statistics for the consumer); needs hw (rows per image), fast path only
 };
 
 struct GemmParams {
@@ -76,7 +74,6 @@ struct GemmParams {
 // Launch. block_n in {16, 32, 64, 128, 160, 256}. Returns cudaError_t as int.
 int launch_gemm_tc(const GemmParams& p, int block_n, int splits, cudaStream_t stream);
 void set_gemm_debug_buffer(long long* dev_ptr);  // debug hook: phase timestamps of subsequent launches
-void set_gemm_debug_cstat(float* p, int hw);     // debug hook: force channel statistics output
 // Deferred epilogue for split-K: sums `splits` partials and applies p.epi.
 int launch_splitk_epilogue(const GemmParams& p, int block_n, int splits, cudaStream_t stream);
 size_t gemm_smem_bytes(int block_n, int stages, int a_ring_bytes = -1 /* -1: stages x 16 KB A tiles */);
@@ -102,23 +99,19 @@ size_t flash_attn64_ws_bytes(int NB, int T, int C);
 // ---------------------------------------------------------------------------------------------
 // Memory-bound kernels (norm.cu, elementwise.cu)
 // ---------------------------------------------------------------------------------------------
-// GroupNorm over NHWC: stats over (pixels x C/G channels) per image and group.
+// GroupNorm over NHWC: stats over (pixels x C/G channels) per image and group; ONE launch with a grid barrier,
+// run-to-run deterministic (norm.cu).
 //   x_f32 [NB, HW, C] -> y_bf16 = act((x - mean) * rstd * gamma + beta); optional raw bf16 copy.
+// ws: groupnorm_ws_bytes() of scratch.
 int launch_groupnorm(const float* x, bf16* y, bf16* raw_copy, const float* gamma, const float* beta, float* ws,
                      int NB, int HW, int C, int G, float eps, int silu, cudaStream_t stream);
 size_t groupnorm_ws_bytes(int NB, int HW, int C, int G);
-// per-channel (sum, sum of squares) of x [NB, HW, C] accumulated into cs [NB, C, 2] (must be zero on entry)
-int launch_chan_stats(const float* x, float* cs, int NB, int HW, int C, cudaStream_t stream);
-// GroupNorm(+SiLU) over the channel concat [a | b] (b optional) with group statistics derived from the
-// per-channel sums csa / csb; y bf16 [NB, HW, Ca + Cb]; optional raw bf16 copy of the concat
-int launch_gn_apply2(const float* xa, const float* csa, int Ca, const float* xb, const float* csb, int Cb, bf16* y,
-                     bf16* raw_copy, const float* gamma, const float* beta, int NB, int HW, int G, float eps, int silu,
-                     cudaStream_t stream);
-// Order-independent variants (norm_fx.cu): cs holds 64-bit fixed-point sums [NB, C, 2] (zero on entry).
-int launch_chan_stats_fx(const float* x, long long* cs, int NB, int HW, int C, cudaStream_t stream);
-int launch_gn_apply2_fx(const float* xa, const long long* csa, int Ca, const float* xb, const long long* csb, int Cb, bf16* y,
-                        bf16* raw_copy, const float* gamma, const float* beta, int NB, int HW, int G, float eps, int silu,
-                        cudaStream_t stream);
+size_t groupnorm_part_bytes(int NB, int HW, int C, int G);
+// GroupNorm(+SiLU) over the channel concat [a | b] (b optional): y bf16 [NB, HW, Ca + Cb]; optional raw bf16 copy of
+// the concat. part: groupnorm_part_bytes(NB, HW, Ca + Cb, G) of scratch; counters: NB unsigned, zero on entry.
+int launch_gn_fused(const float* xa, int Ca, const float* xb, int Cb, bf16* y, bf16* raw_copy, const float* gamma,
+                    const float* beta, int NB, int HW, int G, float eps, int silu, void* part, unsigned* counters,
+                    cudaStream_t stream);
 // LayerNorm over the channel dim: x_f32 [M, C] -> y_bf16 [M, C]
 int launch_layernorm(const float* x, bf16* y, const float* gamma, const float* beta, int M, int C, float eps,
                      cudaStream_t stream);

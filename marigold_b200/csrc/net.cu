@@ -50,9 +50,6 @@ struct Epi {
   const float* sched_z = nullptr;
   const float* sched_k = nullptr;
   float* aux_out = nullptr;
-  float* cstat = nullptr;   // per-channel (sum, sum^2) of the fp32 output for the consuming GroupNorm
-  float* stat_slot = nullptr;   // where those sums would go; the split-K reduce pass emits them for free
-  int stat_hw = 0;
 };
 
 // Debug only (tools/marginal_cost.py): MGB_SKIP=gn,ln,attn,xattn,concat,gemm drops a kernel family from the graph so
@@ -66,23 +63,11 @@ static void set_epi(GemmParams& p, const Epi& e, int ldo) {
   p.epi.bias = e.bias; p.epi.residual = e.residual; p.epi.out_f32 = e.out_f32; p.epi.out_bf16 = e.out_bf16;
   p.epi.ldo = ldo; p.epi.flags = e.flags; p.epi.hw = e.hw; p.epi.scale = e.scale;
   p.epi.sched_x = e.sched_x; p.epi.sched_z = e.sched_z; p.epi.sched_k = e.sched_k; p.epi.aux_out = e.aux_out;
-  p.epi.cstat = e.cstat;
 }
 
 static int gemm_common(Ctx& c, GemmParams& p, int bn, int splits, const Epi& e, int ldo) {
   if (skip_family("gemm")) return MGB_OK;
   set_epi(p, e, ldo);
-  // OFF by default: measured r01 5.78 -> 6.26 ms/step. 288 reduce blocks x N columns x 2 moments of same-address global
-  // REDs (737k per launch) serialise in L2 (+17 us per launch), more than the 28 statistics launches they save.
-  static const bool splitk_stats = getenv("MGB_SPLITK_STATS") && atoi(getenv("MGB_SPLITK_STATS")) == 1;
-  if (splitk_stats && splits > 1 && !p.epi.cstat && e.stat_slot && !(e.flags & (EPI_GEGLU | EPI_SILU)) && (p.N & 31) == 0 && (ldo & 3) == 0 &&
-      e.stat_hw > 0 && p.M % e.stat_hw == 0) {
-    // the deferred split-K epilogue is a column-owner streaming kernel: the consumer GroupNorm's per-channel sums
-    // cost it 8 REDs per column quad and block, and save a statistics launch
-    p.epi.cstat = e.stat_slot;
-    p.epi.hw = e.stat_hw;
-    c.stat_filled.insert(e.stat_slot);
-  }
   if (splits > 1) {
     const size_t need = size_t(splits) * p.M * p.N * sizeof(float);
     if (need > c.splitk_cap) {
@@ -142,65 +127,29 @@ static int conv3x3(Ctx& c, const bf16* x, int NB, int Hout, int Wout, const Conv
     }                              \
   } while (0)
 
-// fp32 trunk tensor [M, C] with its slot in the GroupNorm statistics slab
-// MGB_GN_DETERMINISTIC=1: GroupNorm statistics as 64-bit fixed point (norm_fx.cu): order-independent, hence bit-
-// reproducible runs. Opt-in until validated on the GPU.
-static bool det_stats() {
-  static const bool v = getenv("MGB_GN_DETERMINISTIC") && atoi(getenv("MGB_GN_DETERMINISTIC")) == 1;
-  return v;
-}
-
-static Act act_alloc(Ctx& c, size_t M, int C, int NB) {
+// fp32 trunk tensor [M, C]
+static Act act_alloc(Ctx& c, size_t M, int C) {
   Act a;
   a.p = aalloc<float>(c, M * C);
   a.C = C;
-  const size_t n = size_t(NB) * C * 2 * (det_stats() ? 2 : 1);   // floats; the fixed-point sums are 8 bytes each
-  const size_t off = c.stat_off;
-  c.stat_off += n;
-  if (c.stat_off > c.stat_need) c.stat_need = c.stat_off;
-  a.cs = c.dry ? nullptr : (c.stat_off <= c.stat_cap ? c.stat_base + off : nullptr);
   return a;
 }
 
-// Ask the producer GEMM to accumulate y's channel statistics in its epilogue. Possible when every 128-row
-// tile lies inside one image (conv tiles always do; token tiles need hw % 128 == 0 or a single image).
-static void emit_stats(Ctx& c, Epi& e, Act& y, int NB, int hw, bool conv_mode) {
-  if (c.dry || !y.cs || det_stats()) return;   // (the producer-epilogue paths write fp32 sums)
-  e.stat_slot = y.cs;
-  e.stat_hw = hw;
-  if (!c.fuse_stats) return;
-  if (!conv_mode && NB > 1 && (hw % 128) != 0) return;
-  e.cstat = y.cs;
-  e.hw = hw;
-  c.stat_filled.insert(y.cs);
-}
-
-// GroupNorm (+SiLU) over [a | b] (b.p == nullptr: single source) -> bf16 operand; stats come from the
-// producers' epilogues, or from a stats kernel when a producer could not emit them.
-static int groupnorm(Ctx& c, Act& a, Act* b, bf16* y, bf16* raw, const NormW& n, int NB, int HW, float eps, int silu) {
+// GroupNorm (+SiLU) over [a | b] (b == nullptr: single source) -> bf16 operand; one deterministic launch (norm.cu).
+// Scratch: partials from the arena (released by the caller's mark), one barrier counter per image from the per-forward
+// counter slab (zeroed once per forward by zero_counters()).
+static int groupnorm(Ctx& c, const Act& a, const Act* b, bf16* y, bf16* raw, const NormW& n, int NB, int HW, float eps,
+                     int silu) {
   if (skip_family("gn")) return MGB_OK;
+  const int Cb = (b && b->p) ? b->C : 0;
+  void* part = c.arena->alloc(groupnorm_part_bytes(NB, HW, a.C + Cb, c.groups));
+  const size_t coff = c.sync_off;
+  c.sync_off += size_t(NB);
+  if (c.sync_off > c.sync_need) c.sync_need = c.sync_off;
   if (c.dry) return MGB_OK;
-  Act* srcs[2] = {&a, b};
-  for (Act* t : srcs) {
-    if (!t || !t->p) continue;
-    if (!t->cs) { set_error("groupnorm: statistics slab exhausted"); return MGB_ERR_STATE; }
-    if (c.stat_filled.count(t->cs)) continue;
-    if (det_stats()) {
-      TRY(launch_chan_stats_fx(t->p, reinterpret_cast<long long*>(t->cs), NB, HW, t->C, c.stream));
-    } else {
-      TRY(launch_chan_stats(t->p, t->cs, NB, HW, t->C, c.stream));
-    }
-    count_launch(1);
-    c.stat_filled.insert(t->cs);
-  }
-  if (det_stats()) {
-    TRY(launch_gn_apply2_fx(a.p, reinterpret_cast<const long long*>(a.cs), a.C, b ? b->p : nullptr,
-                            b ? reinterpret_cast<const long long*>(b->cs) : nullptr, b ? b->C : 0, y, raw, n.g, n.b, NB, HW,
-                            c.groups, eps, silu, c.stream));
-  } else {
-    TRY(launch_gn_apply2(a.p, a.cs, a.C, b ? b->p : nullptr, b ? b->cs : nullptr, b ? b->C : 0, y, raw, n.g, n.b, NB, HW,
-                         c.groups, eps, silu, c.stream));
-  }
+  if (c.sync_off > c.sync_cap) { set_error("groupnorm: barrier counter slab exhausted"); return MGB_ERR_STATE; }
+  TRY(launch_gn_fused(a.p, a.C, Cb ? b->p : nullptr, Cb, y, raw, n.g, n.b, NB, HW, c.groups, eps, silu, part,
+                      c.sync_base + coff, c.stream));
   count_launch(1);
   return MGB_OK;
 }
@@ -214,17 +163,15 @@ static int resnet_forward(Ctx& c, const ResnetW& R, Act& x, Act* skip, Act& y, i
   // sources, and the 1x1 shortcut reads the bf16 copy GroupNorm emits)
   const size_t M = size_t(NB) * H * W;
   const size_t mk = c.arena->mark();
-  const size_t smk = c.stat_off;
   bf16* t1 = aalloc<bf16>(c, M * R.cin);
   bf16* raw = R.has_sc ? aalloc<bf16>(c, M * R.cin) : nullptr;
-  Act h = act_alloc(c, M, R.cout, NB);
+  Act h = act_alloc(c, M, R.cout);
   bf16* t2 = aalloc<bf16>(c, M * R.cout);
   float* sc = R.has_sc ? aalloc<float>(c, M * R.cout) : nullptr;
   TRY(groupnorm(c, x, skip, t1, raw, R.n1, NB, H * W, R.eps, 1));
   Epi e1;
   e1.bias = (R.bias_off >= 0 && c.cur_bias) ? c.cur_bias + R.bias_off : R.c1.b;
   e1.out_f32 = h.p;
-  emit_stats(c, e1, h, NB, H * W, true);
   TRY(conv3x3(c, t1, NB, H, W, R.c1, 0, e1));
   TRY(groupnorm(c, h, nullptr, t2, nullptr, R.n2, NB, H * W, R.eps, 1));
   const float* residual = x.p;
@@ -234,10 +181,8 @@ static int resnet_forward(Ctx& c, const ResnetW& R, Act& x, Act* skip, Act& y, i
     residual = sc;
   }
   Epi e2; e2.bias = R.c2.b; e2.residual = residual; e2.out_f32 = y.p;
-  emit_stats(c, e2, y, NB, H * W, true);
   TRY(conv3x3(c, t2, NB, H, W, R.c2, 0, e2));
   c.arena->release(mk);
-  (void)smk;   // h's statistics slot stays reserved for this graph execution (the slab is zeroed once per graph)
   return MGB_OK;
 }
 
@@ -277,7 +222,6 @@ static int xfmr_forward(Ctx& c, const XfmrW& X, Act& x, Act& y, int NB, int T) {
   { Epi e; e.bias = X.ff2.b; e.residual = hs0; e.out_bf16 = hsb; TRY(linear(c, ffm, int(M), X.ff2, e)); }
   {
     Epi e; e.bias = X.proj_out.b; e.residual = x.p; e.out_f32 = y.p;
-    emit_stats(c, e, y, NB, T, false);
     TRY(linear(c, hsb, int(M), X.proj_out, e));
   }
   c.arena->release(mk);
@@ -320,12 +264,12 @@ static int vae_attn_forward(Ctx& c, const VaeAttnW& A, Act& x, Act& y, int NB, i
 // UNet step. rgb / tgt: fp32 NHWC [NB, lh, lw, 4]. tgt is updated in place by the fused
 // conv_out + scheduler epilogue. raw_out (or null): fp32 NHWC [NB, lh, lw, 4] model output.
 // ---------------------------------------------------------------------------------------------
-static int zero_stats(Ctx& c) {
-  c.stat_filled.clear();
-  // one memset (a memset node under capture) for every GroupNorm statistic of this graph execution
-  if (c.dry || !c.stat_base || c.stat_cap == 0) return MGB_OK;
-  if (cudaMemsetAsync(c.stat_base, 0, c.stat_cap * sizeof(float), c.stream) != cudaSuccess) {
-    set_error("statistics slab memset failed");
+static int zero_counters(Ctx& c) {
+  // one memset (a memset node under capture) for the grid-barrier counters of every GroupNorm of this forward
+  c.sync_off = 0;
+  if (c.dry || !c.sync_base || c.sync_cap == 0) return MGB_OK;
+  if (cudaMemsetAsync(c.sync_base, 0, c.sync_cap * sizeof(unsigned), c.stream) != cudaSuccess) {
+    set_error("barrier counter memset failed");
     return MGB_ERR_CUDA;
   }
   return MGB_OK;
@@ -339,9 +283,7 @@ int unet_forward(mgb_handle* hd, Ctx& c, const float* rgb, float* tgt, const flo
   const int* ch = cfg.unet_block_channels;
   int H = lh, W = lw;
   size_t M = size_t(NB) * H * W;
-  c.stat_off = 0;
-  c.fuse_stats = hd->dbg_fuse_stats;
-  TRY(zero_stats(c));
+  TRY(zero_counters(c));
 
   std::vector<Act> skips;
   size_t ri = 0, xi = 0;
@@ -352,10 +294,9 @@ int unet_forward(mgb_handle* hd, Ctx& c, const float* rgb, float* tgt, const flo
   c.cur_bias = hd->cur_bias;
   bf16* x0 = aalloc<bf16>(c, M * 64);
   LAUNCH(launch_pack_latents(rgb, tgt, x0, int(M), c.stream), 1);
-  Act h = act_alloc(c, M, ch[0], NB);
+  Act h = act_alloc(c, M, ch[0]);
   {
     Epi e; e.bias = U.conv_in.b; e.out_f32 = h.p;
-    emit_stats(c, e, h, NB, H * W, true);
     TRY(conv3x3(c, x0, NB, H, W, U.conv_in, 0, e));
   }
   skips.push_back(h);
@@ -364,11 +305,11 @@ int unet_forward(mgb_handle* hd, Ctx& c, const float* rgb, float* tgt, const flo
   for (int i = 0; i < 4; ++i) {
     const bool last = i == 3;
     for (int j = 0; j < L; ++j) {
-      Act y = act_alloc(c, M, ch[i], NB);
+      Act y = act_alloc(c, M, ch[i]);
       TRY(resnet_forward(c, U.resnets[ri++], h, nullptr, y, NB, H, W));
       h = y; cur = ch[i];
       if (!last) {
-        Act y2 = act_alloc(c, M, cur, NB);
+        Act y2 = act_alloc(c, M, cur);
         TRY(xfmr_forward(c, U.xfmrs[xi++], h, y2, NB, H * W));
         h = y2;
       }
@@ -378,10 +319,9 @@ int unet_forward(mgb_handle* hd, Ctx& c, const float* rgb, float* tgt, const flo
       bf16* planes = aalloc<bf16>(c, M * cur);
       LAUNCH(launch_space_to_depth(h.p, planes, NB, H, W, cur, c.stream), 1);
       H /= 2; W /= 2; M = size_t(NB) * H * W;
-      Act y = act_alloc(c, M, cur, NB);
+      Act y = act_alloc(c, M, cur);
       {
         Epi e; e.bias = U.downs[i].b; e.out_f32 = y.p;
-        emit_stats(c, e, y, NB, H * W, true);
         TRY(conv3x3(c, planes, NB, H, W, U.downs[i], 2, e));
       }
       h = y;
@@ -390,11 +330,11 @@ int unet_forward(mgb_handle* hd, Ctx& c, const float* rgb, float* tgt, const flo
   }
   // mid
   {
-    Act y = act_alloc(c, M, cur, NB);
+    Act y = act_alloc(c, M, cur);
     TRY(resnet_forward(c, U.resnets[ri++], h, nullptr, y, NB, H, W));
-    Act y2 = act_alloc(c, M, cur, NB);
+    Act y2 = act_alloc(c, M, cur);
     TRY(xfmr_forward(c, U.xfmrs[xi++], y, y2, NB, H * W));
-    Act y3 = act_alloc(c, M, cur, NB);
+    Act y3 = act_alloc(c, M, cur);
     TRY(resnet_forward(c, U.resnets[ri++], y2, nullptr, y3, NB, H, W));
     h = y3;
   }
@@ -404,11 +344,11 @@ int unet_forward(mgb_handle* hd, Ctx& c, const float* rgb, float* tgt, const flo
     for (int j = 0; j < L + 1; ++j) {
       Act sk = skips.back();
       skips.pop_back();
-      Act y = act_alloc(c, M, cout, NB);
+      Act y = act_alloc(c, M, cout);
       TRY(resnet_forward(c, U.resnets[ri++], h, &sk, y, NB, H, W));
       h = y; cur = cout;
       if (i > 0) {
-        Act y2 = act_alloc(c, M, cur, NB);
+        Act y2 = act_alloc(c, M, cur);
         TRY(xfmr_forward(c, U.xfmrs[xi++], h, y2, NB, H * W));
         h = y2;
       }
@@ -417,10 +357,9 @@ int unet_forward(mgb_handle* hd, Ctx& c, const float* rgb, float* tgt, const flo
       bf16* up = aalloc<bf16>(c, M * 4 * cur);
       LAUNCH(launch_upsample2x(h.p, up, NB, H, W, cur, c.stream), 1);
       H *= 2; W *= 2; M = size_t(NB) * H * W;
-      Act y = act_alloc(c, M, cur, NB);
+      Act y = act_alloc(c, M, cur);
       {
         Epi e; e.bias = U.ups[i].b; e.out_f32 = y.p;
-        emit_stats(c, e, y, NB, H * W, true);
         TRY(conv3x3(c, up, NB, H, W, U.ups[i], 0, e));
       }
       h = y;
@@ -443,8 +382,6 @@ int unet_forward(mgb_handle* hd, Ctx& c, const float* rgb, float* tgt, const flo
 
 // ---------------------------------------------------------------------------------------------
 // VAE encoder: rgb fp32 NCHW [NB,3,H,W] -> latent fp32 NCHW [NB,4,H/8,W/8] (mean * latent_scale)
-// The VAE tensors are HBM-sized (up to 590k pixels): their GroupNorm statistics come from the streaming
-// chan_stats kernel rather than from epilogue atomics (which would contend on 128-512 addresses).
 // ---------------------------------------------------------------------------------------------
 int vae_encode_forward(mgb_handle* hd, Ctx& c, const float* rgb, float* latent_out, int NB, int H, int W) {
   const VaeW& V = hd->vae;
@@ -453,22 +390,18 @@ int vae_encode_forward(mgb_handle* hd, Ctx& c, const float* rgb, float* latent_o
   const int L = cfg.vae_layers_per_block;
   size_t M = size_t(NB) * H * W;
   size_t ri = 0;
-  c.stat_off = 0;
-  c.fuse_stats = false;
-  TRY(zero_stats(c));
+  TRY(zero_counters(c));
   const size_t mk0 = c.arena->mark();
   bf16* x0 = aalloc<bf16>(c, M * 64);
   LAUNCH(launch_pack_rgb(rgb, x0, NB, H * W, c.stream), 1);
-  Act h = act_alloc(c, M, ch[0], NB);
+  Act h = act_alloc(c, M, ch[0]);
   { Epi e; e.bias = V.enc_in.b; e.out_f32 = h.p; TRY(conv3x3(c, x0, NB, H, W, V.enc_in, 0, e)); }
   int cur = ch[0];
   for (int i = 0; i < 4; ++i) {
     // ping-pong trunk buffers for this resolution
-    Act buf[2] = {act_alloc(c, M, ch[i], NB), act_alloc(c, M, ch[i], NB)};
+    Act buf[2] = {act_alloc(c, M, ch[i]), act_alloc(c, M, ch[i])};
     for (int j = 0; j < L; ++j) {
       Act y = buf[j & 1];
-      // a ping-pong buffer is reused: its statistics slot must be a fresh (zeroed) one
-      if (j >= 2) { Act fresh = act_alloc(c, 0, ch[i], NB); y.cs = fresh.cs; }
       TRY(resnet_forward(c, V.enc_res[ri++], h, nullptr, y, NB, H, W));
       h = y; cur = ch[i];
     }
@@ -476,17 +409,17 @@ int vae_encode_forward(mgb_handle* hd, Ctx& c, const float* rgb, float* latent_o
       bf16* planes = aalloc<bf16>(c, M * cur);
       LAUNCH(launch_space_to_depth(h.p, planes, NB, H, W, cur, c.stream), 1);
       H /= 2; W /= 2; M = size_t(NB) * H * W;
-      Act y = act_alloc(c, M, cur, NB);
+      Act y = act_alloc(c, M, cur);
       { Epi e; e.bias = V.enc_down[i].b; e.out_f32 = y.p; TRY(conv3x3(c, planes, NB, H, W, V.enc_down[i], 3, e)); }
       h = y;
     }
   }
   {
-    Act y1 = act_alloc(c, M, cur, NB);
+    Act y1 = act_alloc(c, M, cur);
     TRY(resnet_forward(c, V.enc_res[ri++], h, nullptr, y1, NB, H, W));
-    Act y2 = act_alloc(c, M, cur, NB);
+    Act y2 = act_alloc(c, M, cur);
     TRY(vae_attn_forward(c, V.enc_attn, y1, y2, NB, H * W));
-    Act y3 = act_alloc(c, M, cur, NB);
+    Act y3 = act_alloc(c, M, cur);
     TRY(resnet_forward(c, V.enc_res[ri++], y2, nullptr, y3, NB, H, W));
     h = y3;
   }
@@ -512,30 +445,27 @@ int vae_decode_forward(mgb_handle* hd, Ctx& c, const float* latent, float* out, 
   int H = lh, W = lw;
   size_t M = size_t(NB) * H * W;
   size_t ri = 0;
-  c.stat_off = 0;
-  c.fuse_stats = false;
-  TRY(zero_stats(c));
+  TRY(zero_counters(c));
   const size_t mk0 = c.arena->mark();
   bf16* z = aalloc<bf16>(c, M * 64);
   LAUNCH(launch_pack_decoder_latent(latent, V.pq_w, V.pq_b, 1.0f / cfg.latent_scale, z, NB, H * W, c.stream), 1);
   int cur = ch[3];
-  Act h = act_alloc(c, M, cur, NB);
+  Act h = act_alloc(c, M, cur);
   { Epi e; e.bias = V.dec_in.b; e.out_f32 = h.p; TRY(conv3x3(c, z, NB, H, W, V.dec_in, 0, e)); }
   {
-    Act y1 = act_alloc(c, M, cur, NB);
+    Act y1 = act_alloc(c, M, cur);
     TRY(resnet_forward(c, V.dec_res[ri++], h, nullptr, y1, NB, H, W));
-    Act y2 = act_alloc(c, M, cur, NB);
+    Act y2 = act_alloc(c, M, cur);
     TRY(vae_attn_forward(c, V.dec_attn, y1, y2, NB, H * W));
-    Act y3 = act_alloc(c, M, cur, NB);
+    Act y3 = act_alloc(c, M, cur);
     TRY(resnet_forward(c, V.dec_res[ri++], y2, nullptr, y3, NB, H, W));
     h = y3;
   }
   for (int i = 0; i < 4; ++i) {
     const int cout = ch[3 - i];
-    Act buf[2] = {act_alloc(c, M, cout, NB), act_alloc(c, M, cout, NB)};
+    Act buf[2] = {act_alloc(c, M, cout), act_alloc(c, M, cout)};
     for (int j = 0; j < L + 1; ++j) {
       Act y = buf[j & 1];
-      if (j >= 2) { Act fresh = act_alloc(c, 0, cout, NB); y.cs = fresh.cs; }
       TRY(resnet_forward(c, V.dec_res[ri++], h, nullptr, y, NB, H, W));
       h = y; cur = cout;
     }
@@ -543,7 +473,7 @@ int vae_decode_forward(mgb_handle* hd, Ctx& c, const float* latent, float* out, 
       bf16* up = aalloc<bf16>(c, M * 4 * cur);
       LAUNCH(launch_upsample2x(h.p, up, NB, H, W, cur, c.stream), 1);
       H *= 2; W *= 2; M = size_t(NB) * H * W;
-      Act y = act_alloc(c, M, cur, NB);
+      Act y = act_alloc(c, M, cur);
       { Epi e; e.bias = V.dec_up[i].b; e.out_f32 = y.p; TRY(conv3x3(c, up, NB, H, W, V.dec_up[i], 0, e)); }
       h = y;
     }

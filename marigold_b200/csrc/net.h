@@ -71,13 +71,10 @@ struct Arena {
   void release(size_t m) { off = m; }
 };
 
-// A trunk activation: fp32 [M, C] plus (optionally) the per-channel (sum, sum^2) its producer accumulated for
-// the GroupNorm that consumes it (cs: [NB, C, 2]). Whether the slot has been filled is tracked per slot in
-// Ctx::stat_filled, NOT in the Act: Acts are copied around (skip connections) and have two consumers.
+// A trunk activation: fp32 [M, C]
 struct Act {
   float* p = nullptr;
   int C = 0;
-  float* cs = nullptr;
 };
 
 struct Ctx {
@@ -89,11 +86,9 @@ struct Ctx {
   size_t splitk_need = 0;  // bytes needed (dry run)
   int groups = 32;
   const float* cur_bias = nullptr;  // current step's concatenated resnet conv1 biases (device)
-  // per-graph slab of GroupNorm channel statistics (zeroed once at the start of the graph)
-  float* stat_base = nullptr;
-  size_t stat_off = 0, stat_cap = 0, stat_need = 0;
-  std::unordered_set<const float*> stat_filled;   // slots whose sums are (being) produced in this forward
-  bool fuse_stats = true;           // producers emit statistics from their epilogues (UNet); else a stats kernel
+  // grid-barrier counters of the GroupNorm launches of one forward (one per image and launch; zeroed once per forward)
+  unsigned* sync_base = nullptr;
+  size_t sync_off = 0, sync_cap = 0, sync_need = 0;
 };
 
 struct UNetW {
@@ -159,17 +154,9 @@ struct mgb_handle {
   std::vector<int> timesteps_idx_scratch;  // [0, 1, 2, ...]: host source for arming the device step counter
   cudaStream_t capture_stream = nullptr;
   bool use_graph = true;
-  // small persistent buffers
-  float* gn_ws = nullptr;
-  size_t gn_ws_bytes = 0;
-  // GroupNorm statistics from producer epilogues (RED into the slab). OFF by default in round 1: it is
-  // numerically validated per kernel (tools/debug_cstat.py) but one producer in the composed UNet still
-  // disagrees with the stats kernel and it gave no net speed-up (atomics ~ cost of the stats launches);
-  // the default path is chan_stats + gn_apply2 (2 launches per GroupNorm, concat fused).
-  bool dbg_fuse_stats = false;
-  float* stat_slab = nullptr;   // GroupNorm channel statistics of one graph execution
-  size_t stat_slab_bytes = 0;
+  unsigned* sync_slab = nullptr;   // GroupNorm grid-barrier counters of one forward
+  size_t sync_slab_count = 0;
   // ensemble scratch
   void* ens_ws = nullptr;
-  double* ens_pinned = nullptr;  // pinned host, 64 doubles
+  double* ens_pinned = nullptr;  // pinned host staging (api_ens.cu)
 };

@@ -1,13 +1,19 @@
 // GroupNorm (+SiLU) and LayerNorm over NHWC / token-major fp32 activations -> bf16 GEMM operands.
-// Both are HBM-bound streaming kernels: 128-bit loads, fp32 statistics, one read of x per pass.
 //
-// GroupNorm is two launches so that both are fully parallel over pixels:
-//   gn_stats : grid (chunks, NB): per-(image, chunk, group) partial sum / sum of squares
-//   gn_apply : grid (chunks, NB): combine the partials of its image (double), normalise, affine,
-//              optional SiLU, cast to bf16 (and optionally also emit a raw bf16 copy of x, the
-//              operand of a ResnetBlock's 1x1 shortcut conv).
-// Semantics: torch.nn.GroupNorm (biased variance) as used by diffusers ResnetBlock2D /
-// Transformer2DModel / VAE blocks; SURVEY.md App. A.1-A.2.
+// GroupNorm is ONE launch with a grid-wide barrier in the middle (all CTAs of the grid are co-resident by
+// construction: the host caps the grid at the occupancy the kernel is compiled for):
+//   phase 1  every CTA reduces its pixel chunk to per-group (sum, sum of squares) in a FIXED order (per-thread
+//            fp32 sums -> per-channel slots in shared memory -> 8 lanes per group -> shuffle tree) and stores
+//            the 2 G floats to its own slot of a partial buffer: no atomics on data;
+//   barrier  one arrival counter per image (RED + acquire spin by one thread per CTA);
+//   phase 2  every CTA sums the partials of its image in CTA order (double), which makes the statistics — and
+//            with them the whole denoising path — bit-reproducible from run to run (the first version accumulated
+//            with fp32 atomics: ~1e-2 run-to-run differences at the worst pixel after bf16 rounding), then
+//            normalises + affine (+SiLU) + casts its chunk, whose first round of pixels is still in registers.
+// The concat [a | b] of diffusers' up-block resnets is consumed directly (torch.cat is never materialised), and
+// the raw bf16 copy for a ResnetBlock's 1x1 shortcut conv is emitted in the same pass.
+// Semantics: torch.nn.GroupNorm (biased variance) as used by diffusers ResnetBlock2D / Transformer2DModel / VAE
+// blocks; SURVEY.md App. A.1-A.2. Reached from reference marigold_depth_pipeline.py:461-463,491-492,512-513.
 #include <algorithm>
 #include <cstdlib>
 #include "common.cuh"
@@ -17,100 +23,22 @@
 
 namespace mgb {
 
-size_t groupnorm_ws_bytes(int NB, int HW, int C, int G) {
-  (void)HW; (void)G;
-  return size_t(NB) * C * 2 * sizeof(float);   // per-channel (sum, sum of squares)
+constexpr int kGnCtasPerSm = 2;   // __launch_bounds__ below guarantees this residency (<= 128 registers, <= 40 KB smem)
+
+static __device__ __noinline__ void gn_barrier_timeout(unsigned seen, unsigned want) {
+  printf("mgb: groupnorm grid barrier timeout block=(%d,%d) arrived=%u of %u\n", blockIdx.x, blockIdx.y, seen, want);
+  __trap();
 }
 
-// -------------------------------------------------------------------------------------------------
-// Per-channel statistics of x [NB, HW, C]: cs[(img * C + c) * 2 + {0,1}] += (sum, sum of squares).
-// cs must be zero on entry (the network zeroes its whole statistics slab once per forward).
-// -------------------------------------------------------------------------------------------------
 template <int KQ>
-__global__ void __launch_bounds__(kGnThreads) chan_stats_kernel(const float* __restrict__ x, float* __restrict__ cs,
-                                                                int HW, int C, GnGeom g) {
+__global__ void __launch_bounds__(kGnThreads, kGnCtasPerSm)
+    gn_fused_kernel(const float* __restrict__ xa, int Ca, const float* __restrict__ xb, int Cb, bf16* __restrict__ y,
+                    bf16* __restrict__ raw, const float* __restrict__ gamma, const float* __restrict__ beta, int HW, int G,
+                    float eps, int silu, GnGeom g, float2* __restrict__ part /* [NB][chunks][G] */,
+                    unsigned* __restrict__ counter /* [NB], zero on entry */) {
   constexpr int R = kGnLoads / KQ;
-  extern __shared__ float s_acc[];  // [2 * C]
-  pdl_launch_dependents();
-  const int img = blockIdx.y, chunk = blockIdx.x;
-  const bool use_smem = g.Tp > 1;
-  if (use_smem) {
-    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) s_acc[i] = 0.f;
-    __syncthreads();
-  }
-  pdl_wait();
-  const int tq = threadIdx.x % g.Tq, tp = threadIdx.x / g.Tq;
-  const bool active = tp < g.Tp;
-  float sum[KQ][4], sq[KQ][4];
-#pragma unroll
-  for (int k = 0; k < KQ; ++k)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) { sum[k][j] = 0.f; sq[k][j] = 0.f; }
-  const int p0 = chunk * g.P, p1 = min(HW, p0 + g.P);
-  const float4* xi = reinterpret_cast<const float4*>(x + (size_t)img * HW * C);
-  for (int pb = p0 + tp; pb < p1; pb += g.Tp * R) {
-    float4 v[KQ][R];
-#pragma unroll
-    for (int k = 0; k < KQ; ++k)
-#pragma unroll
-      for (int r = 0; r < R; ++r) {
-        const int p = pb + r * g.Tp;
-        v[k][r] = (active && p < p1) ? __ldg(xi + (size_t)p * g.Q + tq + k * g.Tq) : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-#pragma unroll
-    for (int k = 0; k < KQ; ++k)
-#pragma unroll
-      for (int r = 0; r < R; ++r) {
-        sum[k][0] += v[k][r].x; sq[k][0] = fmaf(v[k][r].x, v[k][r].x, sq[k][0]);
-        sum[k][1] += v[k][r].y; sq[k][1] = fmaf(v[k][r].y, v[k][r].y, sq[k][1]);
-        sum[k][2] += v[k][r].z; sq[k][2] = fmaf(v[k][r].z, v[k][r].z, sq[k][2]);
-        sum[k][3] += v[k][r].w; sq[k][3] = fmaf(v[k][r].w, v[k][r].w, sq[k][3]);
-      }
-  }
-  if (!use_smem) {
-    if (active) {
-#pragma unroll
-      for (int k = 0; k < KQ; ++k) {
-        float* dst = cs + ((size_t)img * C + 4 * (tq + k * g.Tq)) * 2;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) { atomicAdd(dst + 2 * j, sum[k][j]); atomicAdd(dst + 2 * j + 1, sq[k][j]); }
-      }
-    }
-    return;
-  }
-  if (active) {
-#pragma unroll
-    for (int k = 0; k < KQ; ++k) {
-      const int c0 = 4 * (tq + k * g.Tq);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        atomicAdd(&s_acc[2 * (c0 + j)], sum[k][j]);
-        atomicAdd(&s_acc[2 * (c0 + j) + 1], sq[k][j]);
-      }
-    }
-  }
-  __syncthreads();
-  float* dst = cs + (size_t)img * C * 2;
-  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) atomicAdd(dst + i, s_acc[i]);
-}
-
-// -------------------------------------------------------------------------------------------------
-// GroupNorm apply over the channel concatenation [a | b] (b optional): group statistics come from the
-// per-channel sums of each source; y = act((x - mean) * rstd * gamma + beta) as bf16 [NB, HW, Ca + Cb];
-// optionally also the raw bf16 copy of [a | b] (operand of a ResnetBlock's 1x1 shortcut conv).
-// This is torch.cat(dim=1) + GroupNorm (+SiLU) of diffusers' up-block resnets in one pass.
-// -------------------------------------------------------------------------------------------------
-template <int KQ>
-__global__ void __launch_bounds__(kGnThreads)
-    gn_apply2_kernel(const float* __restrict__ xa, const float* __restrict__ csa, int Ca, const float* __restrict__ xb,
-                     const float* __restrict__ csb, int Cb, bf16* __restrict__ y, bf16* __restrict__ raw,
-                     const float* __restrict__ gamma, const float* __restrict__ beta, int HW, int G, float eps, int silu,
-                     GnGeom g) {
-  constexpr int R = kGnLoads / KQ;
-  extern __shared__ float s_stat[];  // mean[G], rstd[G]
-  pdl_launch_dependents();
-  pdl_wait();
-  const int img = blockIdx.y, chunk = blockIdx.x;
+  extern __shared__ float2 s_ch[];   // phase 1: [Tp][C] per-channel (sum, sumsq); phase 2: mean[G] | rstd[G] as floats
+  const int img = blockIdx.y, chunk = blockIdx.x, chunks = gridDim.x;
   const int C = Ca + Cb, cpg = C / G;
   const int tq = threadIdx.x % g.Tq, tp = threadIdx.x / g.Tq;
   const bool active = tp < g.Tp;
@@ -118,42 +46,118 @@ __global__ void __launch_bounds__(kGnThreads)
   const int Qa = Ca / 4, Qb = Cb / 4;
   const float4* xai = reinterpret_cast<const float4*>(xa + (size_t)img * HW * Ca);
   const float4* xbi = xb ? reinterpret_cast<const float4*>(xb + (size_t)img * HW * Cb) : nullptr;
-  uint2* yo = reinterpret_cast<uint2*>(y + (size_t)img * HW * C);
-  uint2* ro = raw ? reinterpret_cast<uint2*>(raw + (size_t)img * HW * C) : nullptr;
+  pdl_wait();
 
-  // (1) first round of pixel loads + the affine parameters: in flight while the statistics are reduced
-  const float4* src[KQ];
-  size_t sstride[KQ];
-  float4 ga4[KQ], be4[KQ];
+  // ---- phase 1: first round of pixels (kept in registers for phase 2), further rounds streamed ----
+  // quad qd of the concatenated channel space lives in source a (qd < Qa) or b
+  auto px = [&](int k, int p) -> const float4* {
+    const int qd = tq + k * g.Tq;
+    return qd < Qa ? xai + (size_t)p * Qa + qd : xbi + (size_t)p * Qb + (qd - Qa);
+  };
   float4 v[KQ][R];
+  float sum[KQ][4], sq[KQ][4];
 #pragma unroll
   for (int k = 0; k < KQ; ++k) {
-    const int qd = tq + k * g.Tq;   // quad index in the concatenated channel space
-    const bool from_a = qd < Qa;
-    src[k] = from_a ? xai + qd : xbi + (qd - Qa);
-    sstride[k] = from_a ? size_t(Qa) : size_t(Qb);
 #pragma unroll
     for (int r = 0; r < R; ++r) {
       const int p = p0 + tp + r * g.Tp;
-      v[k][r] = (active && p < p1) ? __ldg(src[k] + (size_t)p * sstride[k]) : make_float4(0.f, 0.f, 0.f, 0.f);
+      v[k][r] = (active && p < p1) ? __ldg(px(k, p)) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { sum[k][j] = 0.f; sq[k][j] = 0.f; }
+  }
+#pragma unroll
+  for (int k = 0; k < KQ; ++k)
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      sum[k][0] += v[k][r].x; sq[k][0] = fmaf(v[k][r].x, v[k][r].x, sq[k][0]);
+      sum[k][1] += v[k][r].y; sq[k][1] = fmaf(v[k][r].y, v[k][r].y, sq[k][1]);
+      sum[k][2] += v[k][r].z; sq[k][2] = fmaf(v[k][r].z, v[k][r].z, sq[k][2]);
+      sum[k][3] += v[k][r].w; sq[k][3] = fmaf(v[k][r].w, v[k][r].w, sq[k][3]);
+    }
+  if (active) {
+    for (int pb = p0 + tp + g.Tp * R; pb < p1; pb += g.Tp * R) {   // tensors too large for one round per CTA (VAE)
+      float4 w[KQ][R];
+#pragma unroll
+      for (int k = 0; k < KQ; ++k)
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          const int p = pb + r * g.Tp;
+          w[k][r] = p < p1 ? __ldg(px(k, p)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+      for (int k = 0; k < KQ; ++k)
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          sum[k][0] += w[k][r].x; sq[k][0] = fmaf(w[k][r].x, w[k][r].x, sq[k][0]);
+          sum[k][1] += w[k][r].y; sq[k][1] = fmaf(w[k][r].y, w[k][r].y, sq[k][1]);
+          sum[k][2] += w[k][r].z; sq[k][2] = fmaf(w[k][r].z, w[k][r].z, sq[k][2]);
+          sum[k][3] += w[k][r].w; sq[k][3] = fmaf(w[k][r].w, w[k][r].w, sq[k][3]);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < KQ; ++k) {
+      float2* dst = s_ch + (size_t)tp * C + 4 * (tq + k * g.Tq);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) dst[j] = make_float2(sum[k][j], sq[k][j]);
+    }
+  }
+  __syncthreads();
+  const int gi = threadIdx.x >> 3, lane8 = threadIdx.x & 7;
+  {
+    // group partial of this CTA: 8 lanes per group, channels j = lane8, lane8 + 8, ... and pixel lanes in order
+    float s = 0.f, q = 0.f;
+    if (gi < G) {
+      for (int j = lane8; j < cpg; j += 8)
+        for (int t = 0; t < g.Tp; ++t) {
+          const float2 e = s_ch[(size_t)t * C + gi * cpg + j];
+          s += e.x; q += e.y;
+        }
+    }
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) {
+      s += __shfl_xor_sync(0xffffffffu, s, o);
+      q += __shfl_xor_sync(0xffffffffu, q, o);
+    }
+    if (gi < G && lane8 == 0) part[((size_t)img * chunks + chunk) * G + gi] = make_float2(s, q);
+  }
+  // ---- grid barrier over the CTAs of this image ----
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(counter + img, 1u);
+    unsigned seen;
+    const long long t0 = clock64();
+    for (;;) {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(counter + img) : "memory");
+      if (seen >= unsigned(chunks)) break;
+      if (clock64() - t0 > (1ll << 31)) gn_barrier_timeout(seen, unsigned(chunks));
+    }
+  }
+  __syncthreads();
+  // only now may the next kernel's CTAs take SM resources: every CTA of this grid is resident
+  pdl_launch_dependents();
+  // affine parameters: in flight while the statistics are reduced
+  float4 ga4[KQ], be4[KQ];
+#pragma unroll
+  for (int k = 0; k < KQ; ++k) {
+    const int qd = tq + k * g.Tq;
     ga4[k] = gamma ? __ldg(reinterpret_cast<const float4*>(gamma) + qd) : make_float4(1.f, 1.f, 1.f, 1.f);
     be4[k] = beta ? __ldg(reinterpret_cast<const float4*>(beta) + qd) : make_float4(0.f, 0.f, 0.f, 0.f);
   }
-  // (2) group statistics: 8 lanes per group (G * 8 <= 256 threads), up to 4 independent loads per lane and pass
+  float* s_stat = reinterpret_cast<float*>(s_ch);
   {
-    const int gi = threadIdx.x >> 3, part = threadIdx.x & 7;
+    // every CTA of the image sums the same partials in the same (CTA index) order: identical statistics everywhere,
+    // independent of scheduling. Loads bypass L1 (written by other SMs) and are issued 4 at a time.
     double s = 0.0, q = 0.0;
     if (gi < G) {
-      for (int j0 = part; j0 < cpg; j0 += 32) {
+      const float2* pp = part + (size_t)img * chunks * G + gi;
+      for (int c0 = lane8; c0 < chunks; c0 += 32) {
         float2 t[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-          const int j = j0 + 8 * u, c = gi * cpg + j;
-          t[u] = make_float2(0.f, 0.f);
-          if (j < cpg)
-            t[u] = c < Ca ? __ldcg(reinterpret_cast<const float2*>(csa + ((size_t)img * Ca + c) * 2))
-                          : __ldcg(reinterpret_cast<const float2*>(csb + ((size_t)img * Cb + (c - Ca)) * 2));
+          const int c = c0 + 8 * u;
+          t[u] = c < chunks ? __ldcg(pp + (size_t)c * G) : make_float2(0.f, 0.f);
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u) { s += double(t[u].x); q += double(t[u].y); }
@@ -164,7 +168,8 @@ __global__ void __launch_bounds__(kGnThreads)
       s += __shfl_xor_sync(0xffffffffu, s, o);
       q += __shfl_xor_sync(0xffffffffu, q, o);
     }
-    if (gi < G && part == 0) {
+    __syncthreads();   // s_ch (phase 1) is dead: reuse as s_stat
+    if (gi < G && lane8 == 0) {
       const double n = double(HW) * cpg;
       const double mean = s / n;
       double var = q / n - mean * mean;
@@ -175,6 +180,7 @@ __global__ void __launch_bounds__(kGnThreads)
   }
   __syncthreads();
   if (!active) return;
+  // ---- phase 2: normalise + affine (+SiLU) + cast ----
   float sc[KQ][4], sh[KQ][4];
 #pragma unroll
   for (int k = 0; k < KQ; ++k) {
@@ -182,13 +188,14 @@ __global__ void __launch_bounds__(kGnThreads)
     const float gav[4] = {ga4[k].x, ga4[k].y, ga4[k].z, ga4[k].w}, bev[4] = {be4[k].x, be4[k].y, be4[k].z, be4[k].w};
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const int gi = (4 * qd + j) / cpg;
-      const float rstd = s_stat[G + gi];
+      const int gj = (4 * qd + j) / cpg;
+      const float rstd = s_stat[G + gj];
       sc[k][j] = rstd * gav[j];
-      sh[k][j] = bev[j] - s_stat[gi] * rstd * gav[j];
+      sh[k][j] = bev[j] - s_stat[gj] * rstd * gav[j];
     }
   }
-  // (3) apply; further rounds (only tensors too large for one round per CTA) reload in the same batched way
+  uint2* yo = reinterpret_cast<uint2*>(y + (size_t)img * HW * C);
+  uint2* ro = raw ? reinterpret_cast<uint2*>(raw + (size_t)img * HW * C) : nullptr;
   for (int pb = p0 + tp;;) {
 #pragma unroll
     for (int k = 0; k < KQ; ++k)
@@ -212,61 +219,84 @@ __global__ void __launch_bounds__(kGnThreads)
 #pragma unroll
       for (int r = 0; r < R; ++r) {
         const int p = pb + r * g.Tp;
-        v[k][r] = p < p1 ? __ldg(src[k] + (size_t)p * sstride[k]) : make_float4(0.f, 0.f, 0.f, 0.f);
+        v[k][r] = p < p1 ? __ldg(px(k, p)) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
   }
 }
 
-int launch_chan_stats(const float* x, float* cs, int NB, int HW, int C, cudaStream_t stream) {
-  GnGeom g;
-  // every CTA ends with 2*C same-address global REDs, which serialise in L2: fewer, longer CTAs than the apply pass
-  static const int stat_chunks = getenv("MGB_GN_STAT_CHUNKS") ? atoi(getenv("MGB_GN_STAT_CHUNKS")) : kGnMaxChunks;   // 148 / 296 / 1184 measured identical (r01)
-  if (!gn_geometry(HW, C, &g, std::max(1, stat_chunks / std::max(1, NB)))) { set_error("chan_stats: unsupported C=%d", C); return MGB_ERR_INVALID; }
-  dim3 grid(g.chunks, NB);
-  const size_t smem = g.Tp > 1 ? 2 * C * sizeof(float) : 0;
-  cudaError_t e;
-  if (g.Kq == 1) e = launch_k(chan_stats_kernel<1>, grid, kGnThreads, smem, stream, x, cs, HW, C, g);
-  else if (g.Kq == 2) e = launch_k(chan_stats_kernel<2>, grid, kGnThreads, smem, stream, x, cs, HW, C, g);
-  else e = launch_k(chan_stats_kernel<4>, grid, kGnThreads, smem, stream, x, cs, HW, C, g);
-  if (e == cudaSuccess) e = cudaGetLastError();
-  if (e != cudaSuccess) { set_error("chan_stats launch: %s", cudaGetErrorString(e)); return MGB_ERR_CUDA; }
-  return MGB_OK;
+// CTAs that are guaranteed co-resident (the grid barrier needs all of them on the device at once)
+static int gn_max_ctas() {
+  static int v = -1;
+  if (v < 0) {
+    int dev = 0, sms = 0, occ = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    int worst = kGnCtasPerSm;
+    const size_t smem = 40 * 1024;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, gn_fused_kernel<1>, kGnThreads, smem) == cudaSuccess) worst = std::min(worst, occ);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, gn_fused_kernel<2>, kGnThreads, smem) == cudaSuccess) worst = std::min(worst, occ);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, gn_fused_kernel<4>, kGnThreads, smem) == cudaSuccess) worst = std::min(worst, occ);
+    v = std::max(1, worst) * std::max(1, sms);
+  }
+  return v;
 }
 
-int launch_gn_apply2(const float* xa, const float* csa, int Ca, const float* xb, const float* csb, int Cb, bf16* y,
-                     bf16* raw_copy, const float* gamma, const float* beta, int NB, int HW, int G, float eps, int silu,
-                     cudaStream_t stream) {
+static bool gn_plan(int NB, int HW, int C, int G, GnGeom* g) {
+  if (C % G != 0 || G * 8 > kGnThreads || NB < 1) return false;
+  const int per_img = std::max(1, std::min(kGnMaxChunks, gn_max_ctas() / NB));
+  if (gn_max_ctas() < NB) return false;
+  return gn_geometry(HW, C, g, per_img);
+}
+
+// scratch of one GroupNorm call: [NB][chunks][G] float2 partials
+size_t groupnorm_part_bytes(int NB, int HW, int C, int G) {
+  GnGeom g;
+  if (!gn_plan(NB, HW, C, G, &g)) return 0;
+  return size_t(NB) * g.chunks * G * sizeof(float2);
+}
+// stand-alone workspace: partials + NB barrier counters
+size_t groupnorm_ws_bytes(int NB, int HW, int C, int G) {
+  return ((groupnorm_part_bytes(NB, HW, C, G) + 255) & ~size_t(255)) + size_t(NB) * sizeof(unsigned);
+}
+
+// GroupNorm(+SiLU) over the channel concat [a | b] (b optional). part: groupnorm_part_bytes() of scratch; counters: NB
+// unsigned, ZERO on entry (the network zeroes all counters of a forward with one memset).
+int launch_gn_fused(const float* xa, int Ca, const float* xb, int Cb, bf16* y, bf16* raw_copy, const float* gamma,
+                    const float* beta, int NB, int HW, int G, float eps, int silu, void* part, unsigned* counters,
+                    cudaStream_t stream) {
   GnGeom g;
   const int C = Ca + Cb;
-  if (C % G != 0 || G * 8 > kGnThreads || (Ca & 3) || (Cb & 3) || !gn_geometry(HW, C, &g)) {
-    set_error("groupnorm: unsupported C=%d+%d G=%d", Ca, Cb, G);
+  if ((Ca & 3) || (Cb & 3) || !gn_plan(NB, HW, C, G, &g)) {
+    set_error("groupnorm: unsupported NB=%d C=%d+%d G=%d", NB, Ca, Cb, G);
     return MGB_ERR_INVALID;
   }
   dim3 grid(g.chunks, NB);
-  const size_t smem = 2 * G * sizeof(float);
+  const size_t smem = std::max(size_t(g.Tp) * C * sizeof(float2), size_t(2) * G * sizeof(float));
+  if (smem > 40 * 1024) { set_error("groupnorm: C=%d needs %zu B of shared memory", C, smem); return MGB_ERR_INVALID; }
+  float2* pp = static_cast<float2*>(part);
   cudaError_t e;
   if (g.Kq == 1)
-    e = launch_k(gn_apply2_kernel<1>, grid, kGnThreads, smem, stream, xa, csa, Ca, xb, csb, Cb, y, raw_copy, gamma, beta, HW,
-                 G, eps, silu, g);
+    e = launch_k(gn_fused_kernel<1>, grid, kGnThreads, smem, stream, xa, Ca, xb, Cb, y, raw_copy, gamma, beta, HW, G, eps,
+                 silu, g, pp, counters);
   else if (g.Kq == 2)
-    e = launch_k(gn_apply2_kernel<2>, grid, kGnThreads, smem, stream, xa, csa, Ca, xb, csb, Cb, y, raw_copy, gamma, beta, HW,
-                 G, eps, silu, g);
+    e = launch_k(gn_fused_kernel<2>, grid, kGnThreads, smem, stream, xa, Ca, xb, Cb, y, raw_copy, gamma, beta, HW, G, eps,
+                 silu, g, pp, counters);
   else
-    e = launch_k(gn_apply2_kernel<4>, grid, kGnThreads, smem, stream, xa, csa, Ca, xb, csb, Cb, y, raw_copy, gamma, beta, HW,
-                 G, eps, silu, g);
+    e = launch_k(gn_fused_kernel<4>, grid, kGnThreads, smem, stream, xa, Ca, xb, Cb, y, raw_copy, gamma, beta, HW, G, eps,
+                 silu, g, pp, counters);
   if (e == cudaSuccess) e = cudaGetLastError();
   if (e != cudaSuccess) { set_error("groupnorm launch: %s", cudaGetErrorString(e)); return MGB_ERR_CUDA; }
   return MGB_OK;
 }
 
-// Stand-alone GroupNorm (operator-level ABI): ws = per-channel stats scratch [NB, C, 2] (zeroed here).
+// Stand-alone GroupNorm (operator-level ABI): ws = groupnorm_ws_bytes() of scratch (counters zeroed here).
 int launch_groupnorm(const float* x, bf16* y, bf16* raw_copy, const float* gamma, const float* beta, float* ws,
                      int NB, int HW, int C, int G, float eps, int silu, cudaStream_t stream) {
-  cudaError_t e = cudaMemsetAsync(ws, 0, size_t(NB) * C * 2 * sizeof(float), stream);
+  const size_t pb = (groupnorm_part_bytes(NB, HW, C, G) + 255) & ~size_t(255);
+  unsigned* counters = reinterpret_cast<unsigned*>(reinterpret_cast<char*>(ws) + pb);
+  cudaError_t e = cudaMemsetAsync(counters, 0, size_t(NB) * sizeof(unsigned), stream);
   if (e != cudaSuccess) { set_error("groupnorm memset: %s", cudaGetErrorString(e)); return MGB_ERR_CUDA; }
-  int rc = launch_chan_stats(x, ws, NB, HW, C, stream);
-  if (rc) return rc;
-  return launch_gn_apply2(x, ws, C, nullptr, nullptr, 0, y, raw_copy, gamma, beta, NB, HW, G, eps, silu, stream);
+  return launch_gn_fused(x, C, nullptr, 0, y, raw_copy, gamma, beta, NB, HW, G, eps, silu, ws, counters, stream);
 }
 
 // -------------------------------------------------------------------------------------------------

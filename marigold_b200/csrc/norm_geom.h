@@ -1,4 +1,4 @@
-// Thread geometry shared by the GroupNorm kernels (norm.cu, norm_fx.cu).
+// Thread geometry of the GroupNorm kernel (norm.cu).
 #pragma once
 
 namespace mgb {

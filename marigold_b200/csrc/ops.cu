@@ -167,16 +167,10 @@ int run_gemm(GemmParams& p, int block_n, float* splitk_ws, cudaStream_t stream) 
     set_error("GEGLU epilogue needs block_n %% 64 == 0 (got %d)", block_n);
     return MGB_ERR_INVALID;
   }
-  if (p.epi.cstat && (block_n < 32 || (p.epi.flags & (EPI_GEGLU | EPI_SILU)) || (p.N & 31) || (p.epi.ldo & 3) ||
-                      p.epi.hw <= 0)) {
-    set_error("gemm: channel statistics need block_n >= 32, N %% 32 == 0 and a plain epilogue (block_n=%d N=%d)", block_n,
-              p.N);
-    return MGB_ERR_INVALID;
-  }
   if (block_n > 16) {
-    // the drained operand ring doubles as the epilogue's transpose scratch (8 warps x 4.5 KB, x2 for GEGLU) and, with
-    // channel statistics, holds the per-CTA column sums at its tail: deepen the pipeline until that fits
-    const int need = 8 * ((p.epi.flags & EPI_GEGLU) ? 9216 : 4608) + (p.epi.cstat ? 2 * block_n * 4 : 0);
+    // the drained operand ring doubles as the epilogue's transpose scratch (8 warps x 4.5 KB, x2 for GEGLU): deepen
+    // the pipeline until that fits
+    const int need = 8 * ((p.epi.flags & EPI_GEGLU) ? 9216 : 4608);
     for (;;) {
       const int ring = (p.mode == 2 ? p.halo_slots * p.halo_slot_bytes : p.stages * 16384) + p.stages * block_n * 128;
       if (ring >= need || p.stages >= 16) break;

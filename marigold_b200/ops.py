@@ -51,7 +51,10 @@ def flash_attn64(qkv, NB, T, C, scale):
 def groupnorm(x, gamma, beta, NB, HW, C, G, eps, silu):
     lib = _lib.load()
     y = torch.empty(NB, HW, C, dtype=torch.bfloat16, device=x.device)
-    ws = torch.empty(NB * C * 2, dtype=torch.float32, device=x.device)
+    nbytes = int(lib.mgb_op_groupnorm_ws_bytes(NB, HW, C, G))
+    if nbytes == 0:
+        raise _lib.MgbError(f"groupnorm: unsupported shape NB={NB} HW={HW} C={C} G={G}")
+    ws = torch.empty((nbytes + 3) // 4, dtype=torch.float32, device=x.device)
     check(lib.mgb_op_groupnorm(ptr(x), ptr(y), ptr(gamma), ptr(beta), ptr(ws), NB, HW, C, G, float(eps), int(silu),
                                stream_ptr()), "mgb_op_groupnorm")
     return y

@@ -82,3 +82,19 @@ def synthetic_image(S: int, seed: int = 1234) -> torch.Tensor:
 def rel_err(a: torch.Tensor, b: torch.Tensor) -> float:
     a, b = a.detach().float().cpu(), b.detach().float().cpu()
     return ((a - b).abs().max() / (b.abs().max() + 1e-12)).item()
+
+
+def record(name: str, value: float) -> float:
+    """Append a measured parity value to gpurun_out/parity_values.jsonl (the tolerances asserted in the GPU tests are
+    these measurements plus a margin; the file travels back from the GPU box)."""
+    import json
+    from pathlib import Path
+
+    out = Path(__file__).resolve().parents[1] / "gpurun_out"
+    try:
+        out.mkdir(exist_ok=True)
+        with open(out / "parity_values.jsonl", "a") as f:
+            f.write(json.dumps({"name": name, "value": float(value)}) + "\n")
+    except OSError:
+        pass
+    return float(value)

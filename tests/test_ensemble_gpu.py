@@ -162,8 +162,8 @@ def test_cost_batch_is_one_round_trip_and_bit_identical():
     # end to end: round trips = objective calls + gradient calls, far fewer than evaluated points
     _, _, aux2 = ensemble_depth(d, return_aux=True)
     assert aux2["nfev"] >= aux2["round_trips"]
-    if aux2["nit"] > 0:
-        assert aux2["round_trips"] * (E + 1) <= aux2["nfev"] + 2 * (E + 1)
+    if aux2["nit"] > 0:   # without batching every evaluated point is a round trip
+        assert aux2["round_trips"] * 4 <= aux2["nfev"]
 
 
 @pytest.mark.parametrize("E,reduction", [(20, "median"), (17, "mean"), (33, "median")])

@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 import torch
 
-from tests.helpers import engine_from_oracle, oracle_models, rel_err
+from tests.helpers import engine_from_oracle, oracle_models, record, rel_err
 
 pytestmark = pytest.mark.gpu
 
@@ -41,7 +41,7 @@ def test_unet_step_matches_oracle(tiny, B, lh, lw):
         tgt = x.cuda().clone()
         out = eng.unet_step(rgb.cuda(), tgt, step, want_model_out=True)
         torch.cuda.synchronize()
-        e = rel_err(out, ref)
+        e = record(f"tiny/unet_step{step}/B{B}", rel_err(out, ref))
         assert e < 3e-2, f"unet step {step}: rel err {e}"   # bf16 operands through ~60 GEMM layers
         upd = kx[step] * x + kv[step] * out.cpu()
         assert rel_err(tgt, upd) < 1e-5                     # fused scheduler epilogue is fp32-exact
@@ -55,7 +55,7 @@ def test_vae_encode_matches_oracle(tiny):
         ref = vae.quant_conv(vae.encoder(rgb))[:, :4] * 0.18215
     out = eng.encode(rgb.cuda())
     torch.cuda.synchronize()
-    assert rel_err(out, ref) < 3e-2
+    assert record("tiny/encode", rel_err(out, ref)) < 3e-2
 
 
 @pytest.mark.parametrize("mode", [0, 1, 2])
@@ -81,9 +81,12 @@ def test_vae_decode_matches_oracle(tiny, mode):
         assert torch.allclose(torch.norm(o, dim=1), torch.ones_like(o[:, 0]), atol=1e-4)
         strong = torch.norm(raw.clip(-1, 1), dim=1) > 0.3
         cos = (o * ref).sum(1)[strong]
-        assert cos.min() > 0.995, f"min cosine {cos.min()}"
+        assert record("tiny/decode_normals_min_cos", cos.min()) > 0.995, f"min cosine {cos.min()}"
+        # channel order and sign everywhere the vector is not tiny: max component error
+        strong3 = strong[:, None].expand_as(o)
+        assert record("tiny/decode_normals_max_abs", (o - ref).abs()[strong3].max()) < 5e-2
     else:
-        assert rel_err(out, ref) < 3e-2
+        assert record(f"tiny/decode_mode{mode}", rel_err(out, ref)) < 3e-2
 
 
 def test_denoise_trajectory_ddim_and_lcm(tiny):
@@ -113,4 +116,4 @@ def test_denoise_trajectory_ddim_and_lcm(tiny):
                 x = o.step(v, t, x, noise=zs[i] if (kind == "lcm" and i < n - 1) else None)
         out = eng.denoise(rgb.cuda(), x0.cuda(), zs.cuda() if kind == "lcm" else None)
         torch.cuda.synchronize()
-        assert rel_err(out, x) < 3e-2, kind
+        assert record(f"tiny/trajectory_{kind}", rel_err(out, x)) < 3e-2, kind

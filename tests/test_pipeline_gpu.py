@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 import torch
 
-from tests.helpers import engine_from_oracle, oracle_models, synthetic_image
+from tests.helpers import engine_from_oracle, oracle_models, record, synthetic_image
 
 pytestmark = pytest.mark.gpu
 
@@ -38,8 +38,11 @@ def test_depth_pipeline_single_member_matches_oracle(setup):
     ref, _, _ = ora(img, ensemble_size=1, noise=z0)
     assert out.depth_np.shape == (128, 128) and out.uncertainty is None and out.depth_colored is not None
     # bf16 operand tolerance for a 4-step trajectory + decoder (the map lives in [0,1])
-    assert np.abs(out.depth_np - ref).max() < 3e-2
-    assert np.abs(out.depth_np - ref).mean() < 5e-3
+    assert record("tiny/pipe_depth_max", np.abs(out.depth_np - ref).max()) < 3e-2
+    assert record("tiny/pipe_depth_mean", np.abs(out.depth_np - ref).mean()) < 5e-3
+    # run-to-run reproducibility: every kernel sums in a fixed order (no data atomics anywhere on the path)
+    out2 = pipe(img, ensemble_size=1, noise=z0, show_progress_bar=False)
+    np.testing.assert_array_equal(out.depth_np, out2.depth_np)
 
 
 def test_depth_pipeline_ensemble_and_resize(setup):
@@ -67,7 +70,7 @@ def test_depth_pipeline_ensemble_and_resize(setup):
     rgb_norm, _ = pipe._preprocess(img, 128, "bilinear")
     members = pipe._infer_members(rgb_norm, 3, 2, 2, None, z0, None, 0)
     assert members.shape == ref_members.shape == (3, 1, 64, 128)
-    assert (members.cpu() - ref_members).abs().max() < 3e-2
+    assert record("tiny/pipe_members_max", (members.cpu() - ref_members).abs().max()) < 3e-2
     # ... and the ensemble of IDENTICAL members matches the oracle's ensemble when given the same alignment
     # (the BFGS trajectory itself is rounding-chaotic on such near-flat random-weight maps; test_ensemble_gpu)
     from marigold_b200.ensemble import ensemble_depth
@@ -92,7 +95,7 @@ def test_depth_pipeline_lcm(setup):
     out = pipe(img, ensemble_size=1, noise=z0[:1], step_noise=zs[:, :1], show_progress_bar=False)
     ora = OracleDepthPipeline(unet, vae, LCMSchedulerOracle(), text, 4, 128)
     ref, _, _ = ora(img, ensemble_size=1, noise=z0[:1], step_noise=zs[:, :1])
-    assert np.abs(out.depth_np - ref).max() < 3e-2
+    assert record("tiny/pipe_lcm_max", np.abs(out.depth_np - ref).max()) < 3e-2
 
 
 def test_normals_pipeline_and_errors(setup):
@@ -113,6 +116,9 @@ def test_normals_pipeline_and_errors(setup):
     strong = np.linalg.norm(ref, axis=0) > 0.5
     cos = (out.normals_np * ref).sum(0)[strong]
     assert np.median(cos) > 0.99
+    # every strong pixel, not just the median: a wrong channel order or sign anywhere would show here
+    assert record("tiny/pipe_normals_min_cos", cos.min()) > 0.9
+    assert record("tiny/pipe_normals_p01_cos", np.quantile(cos, 0.01)) > 0.98
     with pytest.raises(RuntimeError):
         MarigoldNormalsPipeline(eng, LCMScheduler(), text, 2, 128)(img, noise=z0[:1])
     with pytest.raises(TypeError):

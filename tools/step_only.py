@@ -13,11 +13,6 @@ steps = int(sys.argv[1]) if len(sys.argv) > 1 else 3
 res = int(sys.argv[2]) if len(sys.argv) > 2 else 768
 unet, vae, text = oracle_models("full")
 eng = engine_from_oracle(unet, vae, text)
-import ctypes as C, os
-from marigold_b200 import _lib
-if os.environ.get('MGB_DBG_FUSE') is not None:
-    raw = C.CDLL(str(_lib.lib_path())); raw.mgb_debug_set_fuse_stats.argtypes = [C.c_void_p, C.c_int]
-    raw.mgb_debug_set_fuse_stats(eng._h, int(os.environ['MGB_DBG_FUSE']))
 s = DDIMScheduler()
 s.set_timesteps(max(steps, 1))
 eng.set_schedule(s.timesteps, *s.coefficients())
