@@ -602,8 +602,8 @@ static Ctx make_ctx(mgb_handle* h, void* stream) {
 
 int mgb_encode(mgb_handle* h, const float* rgb, int32_t B, int32_t H, int32_t W, float* latent, void* stream) {
   TRY(check_ready(h, false));
-  if (!rgb || !latent || B <= 0 || H <= 0 || W <= 0 || H % 64 || W % 64) {
-    set_error("mgb_encode: need B > 0 and H, W positive multiples of 64 (got %d x %d)", H, W);
+  if (!rgb || !latent || B <= 0 || H < 8 || W < 8) {
+    set_error("mgb_encode: need B > 0 and H, W >= 8 (got %d x %d)", H, W);
     return MGB_ERR_INVALID;
   }
   TRY(ensure_workspace(h, OP_ENCODE, B, H, W));
@@ -616,8 +616,8 @@ int mgb_encode(mgb_handle* h, const float* rgb, int32_t B, int32_t H, int32_t W,
 int mgb_unet_step(mgb_handle* h, const float* rgb_latent, float* target, const float* noise, float* model_out,
                   int32_t step_index, int32_t B, int32_t lh, int32_t lw, void* stream) {
   TRY(check_ready(h, true));
-  if (!rgb_latent || !target || B <= 0 || lh <= 0 || lw <= 0 || lh % 8 || lw % 8) {
-    set_error("mgb_unet_step: latent H, W must be positive multiples of 8 (got %d x %d)", lh, lw);
+  if (!rgb_latent || !target || B <= 0 || lh <= 0 || lw <= 0) {
+    set_error("mgb_unet_step: bad argument (latent %d x %d)", lh, lw);
     return MGB_ERR_INVALID;
   }
   if (step_index < 0 || step_index >= h->n_steps) { set_error("step_index %d outside schedule of %d", step_index, h->n_steps); return MGB_ERR_INVALID; }
@@ -632,8 +632,8 @@ int mgb_unet_step(mgb_handle* h, const float* rgb_latent, float* target, const f
 int mgb_denoise_range(mgb_handle* h, const float* rgb_latent, float* target, const float* step_noise,
                       int32_t first_step, int32_t num_steps, int32_t B, int32_t lh, int32_t lw, void* stream) {
   TRY(check_ready(h, true));
-  if (!rgb_latent || !target || B <= 0 || lh <= 0 || lw <= 0 || lh % 8 || lw % 8) {
-    set_error("mgb_denoise: latent H, W must be positive multiples of 8 (got %d x %d)", lh, lw);
+  if (!rgb_latent || !target || B <= 0 || lh <= 0 || lw <= 0) {
+    set_error("mgb_denoise: bad argument (latent %d x %d)", lh, lw);
     return MGB_ERR_INVALID;
   }
   if (first_step < 0 || num_steps < 0 || first_step + num_steps > h->n_steps) {
@@ -719,7 +719,7 @@ int mgb_denoise(mgb_handle* h, const float* rgb_latent, float* target, const flo
 int mgb_decode(mgb_handle* h, const float* latent, int32_t B, int32_t lh, int32_t lw, int32_t mode, float* out,
                void* stream) {
   TRY(check_ready(h, false));
-  if (!latent || !out || B <= 0 || lh <= 0 || lw <= 0 || lh % 8 || lw % 8 || mode < 0 || mode > 2) {
+  if (!latent || !out || B <= 0 || lh <= 0 || lw <= 0 || mode < 0 || mode > 2) {
     set_error("mgb_decode: bad argument (latent %d x %d, mode %d)", lh, lw, mode);
     return MGB_ERR_INVALID;
   }
@@ -733,7 +733,7 @@ int mgb_decode(mgb_handle* h, const float* latent, int32_t B, int32_t lh, int32_
 /* debug hooks (not in the public header) */
 
 size_t mgb_workspace_bytes(mgb_handle* h, int32_t B, int32_t H, int32_t W) {
-  if (!h || !h->finalized || B <= 0 || H % 64 || W % 64) return 0;
+  if (!h || !h->finalized || B <= 0 || H < 8 || W < 8) return 0;
   size_t peak = 0;
   for (int op = 0; op < 3; ++op) {
     Arena dry; dry.dry = true;

@@ -126,7 +126,7 @@ int mgb_op_space_to_depth(const float* x, void* y, int32_t NB, int32_t H, int32_
 }
 
 int mgb_op_upsample2x(const float* x, void* y, int32_t NB, int32_t H, int32_t W, int32_t C, void* stream) {
-  int rc = launch_upsample2x(x, reinterpret_cast<bf16*>(y), NB, H, W, C, reinterpret_cast<cudaStream_t>(stream));
+  int rc = launch_upsample2x(x, reinterpret_cast<bf16*>(y), NB, H, W, C, 2 * H, 2 * W, reinterpret_cast<cudaStream_t>(stream));
   if (!rc) count_launch(1);
   return rc;
 }

@@ -319,7 +319,20 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 __device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
-__device__ __forceinline__ float gelu_erf_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+// Exact-erf GELU (diffusers GEGLU: F.gelu(gate), default approximate="none"). erf by Abramowitz-Stegun 7.1.26
+// (|error| <= 1.5e-7, far below the bf16 rounding of the product that follows): one MUFU.RCP + one MUFU.EX2 + 8 FMA
+// instead of erff's ~35 instructions; this epilogue runs 11.8 M times per 96 x 96 feed-forward.
+__device__ __forceinline__ float gelu_erf_f(float x) {
+  const float z = fabsf(x) * 0.70710678118654752f;
+  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  const float e = ex2_approx(-1.4426950408889634f * z * z);      // exp(-z^2)
+  const float erf_abs = fmaf(-poly * t, e, 1.0f);                  // erf(|x| / sqrt 2)
+  return 0.5f * x * (1.0f + copysignf(erf_abs, x));
+}
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);

@@ -23,55 +23,61 @@ static inline int grid_for(size_t n, int threads) {
     return MGB_OK;                                                   \
   } while (0)
 
-// x fp32 [NB, H, W, C] -> y bf16 [NB, 4, H/2, W/2, C], plane = (h & 1) * 2 + (w & 1)
+// x fp32 [NB, H, W, C] -> y bf16 [NB, 4, ceil(H/2), ceil(W/2), C], plane = (h & 1) * 2 + (w & 1); plane elements whose
+// source pixel lies outside the image (odd H or W) are zero = the convolution's zero padding there.
 __global__ void s2d_kernel(const float4* __restrict__ x, uint2* __restrict__ y, int NB, int H, int W, int Q) {
   pdl_launch_dependents();
   pdl_wait();
-  const size_t total = (size_t)NB * H * W * Q;
-  const int H2 = H / 2, W2 = W / 2;
+  const int H2 = (H + 1) / 2, W2 = (W + 1) / 2;
+  const size_t total = (size_t)NB * 4 * H2 * W2 * Q;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     const int q = int(i % Q);
     size_t r = i / Q;
-    const int w = int(r % W); r /= W;
-    const int h = int(r % H);
-    const int n = int(r / H);
-    const float4 v = __ldg(x + i);
-    const int plane = (h & 1) * 2 + (w & 1);
-    const size_t o = ((((size_t)n * 4 + plane) * H2 + (h >> 1)) * W2 + (w >> 1)) * Q + q;
-    y[o] = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+    const int w2 = int(r % W2); r /= W2;
+    const int h2 = int(r % H2); r /= H2;
+    const int plane = int(r & 3);
+    const int n = int(r >> 2);
+    const int h = 2 * h2 + (plane >> 1), w = 2 * w2 + (plane & 1);
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (h < H && w < W) v = __ldg(x + (((size_t)n * H + h) * W + w) * Q + q);
+    y[i] = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
   }
 }
 int launch_space_to_depth(const float* x, bf16* y, int NB, int H, int W, int C, cudaStream_t stream) {
-  if ((H | W) & 1 || C % 4) { set_error("space_to_depth: H, W must be even, C %% 4 == 0"); return MGB_ERR_INVALID; }
-  const size_t n = (size_t)NB * H * W * (C / 4);
+  if (C % 4 || H < 1 || W < 1) { set_error("space_to_depth: C %% 4 == 0 required"); return MGB_ERR_INVALID; }
+  const size_t n = (size_t)NB * 4 * ((H + 1) / 2) * ((W + 1) / 2) * (C / 4);
   launch_k(s2d_kernel, grid_for(n, 256), 256, 0, stream, reinterpret_cast<const float4*>(x), reinterpret_cast<uint2*>(y),
            NB, H, W, C / 4);
   MGB_LAUNCH_CHECK("space_to_depth");
 }
 
-// nearest x2: x fp32 [NB, H, W, C] -> y bf16 [NB, 2H, 2W, C]   (F.interpolate(scale_factor=2, mode="nearest"))
-__global__ void upsample2x_kernel(const float4* __restrict__ x, uint2* __restrict__ y, int NB, int H, int W, int Q) {
+// nearest upsampling to Ho x Wo with Ho in {2H - 1, 2H} (same for W): x fp32 [NB, H, W, C] -> y bf16 [NB, Ho, Wo, C].
+// F.interpolate(scale_factor=2, mode="nearest"), or F.interpolate(size=(Ho, Wo), mode="nearest") as diffusers'
+// Upsample2D does when the UNet forwards `upsample_size`: for Ho = 2H - 1 the source index floor(d * H / Ho) equals
+// d >> 1 for every d < Ho (d = 2k + 1: k + (k + H) / (2H - 1) < k + 1 because k <= H - 2), i.e. x2 then crop.
+__global__ void upsample2x_kernel(const float4* __restrict__ x, uint2* __restrict__ y, int NB, int H, int W, int Ho, int Wo,
+                                  int Q) {
   pdl_launch_dependents();
   pdl_wait();
-  const size_t total = (size_t)NB * H * W * Q;
+  const size_t total = (size_t)NB * Ho * Wo * Q;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     const int q = int(i % Q);
     size_t r = i / Q;
-    const int w = int(r % W); r /= W;
-    const int h = int(r % H);
-    const int n = int(r / H);
-    const float4 v = __ldg(x + i);
-    const uint2 o = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
-    const size_t row0 = (((size_t)n * 2 * H + 2 * h) * 2 * W + 2 * w) * Q + q;
-    const size_t row1 = row0 + (size_t)2 * W * Q;
-    y[row0] = o; y[row0 + Q] = o; y[row1] = o; y[row1 + Q] = o;
+    const int w = int(r % Wo); r /= Wo;
+    const int h = int(r % Ho);
+    const int n = int(r / Ho);
+    const float4 v = __ldg(x + (((size_t)n * H + (h >> 1)) * W + (w >> 1)) * Q + q);
+    y[i] = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
   }
 }
-int launch_upsample2x(const float* x, bf16* y, int NB, int H, int W, int C, cudaStream_t stream) {
-  if (C % 4) { set_error("upsample2x: C %% 4 != 0"); return MGB_ERR_INVALID; }
-  const size_t n = (size_t)NB * H * W * (C / 4);
+int launch_upsample2x(const float* x, bf16* y, int NB, int H, int W, int C, int Ho, int Wo, cudaStream_t stream) {
+  if (C % 4 || (Ho != 2 * H && Ho != 2 * H - 1) || (Wo != 2 * W && Wo != 2 * W - 1)) {
+    set_error("upsample2x: C %% 4 != 0 or target %d x %d is not 2x / 2x - 1 of %d x %d", Ho, Wo, H, W);
+    return MGB_ERR_INVALID;
+  }
+  const size_t n = (size_t)NB * Ho * Wo * (C / 4);
   launch_k(upsample2x_kernel, grid_for(n, 256), 256, 0, stream, reinterpret_cast<const float4*>(x),
-           reinterpret_cast<uint2*>(y), NB, H, W, C / 4);
+           reinterpret_cast<uint2*>(y), NB, H, W, Ho, Wo, C / 4);
   MGB_LAUNCH_CHECK("upsample2x");
 }
 
@@ -272,12 +278,15 @@ int launch_timestep_embedding(const float* t, float* emb, int M, int dim, cudaSt
   MGB_LAUNCH_CHECK("timestep_embedding");
 }
 
-// In-place row softmax on bf16 scores (fp32 math): s[M, ld], first n columns valid. One CTA per row.
-__global__ void __launch_bounds__(256) softmax_rows_kernel(bf16* __restrict__ s, int n, int ld) {
+// Row softmax of fp32 scores s[M, ld] (first n columns valid) -> bf16 probabilities p[M, ld], columns [n, ld) zeroed
+// (ld is the K extent of the P V GEMM that follows: a multiple of 64). One CTA per row; the row is read three times
+// from L2 (max, sum, write), all math fp32 on unrounded logits.
+__global__ void __launch_bounds__(256) softmax_rows_kernel(const float* __restrict__ s, bf16* __restrict__ p, int n, int ld) {
   __shared__ float red[32];
-  bf16* row = s + (size_t)blockIdx.x * ld;
+  const float* row = s + (size_t)blockIdx.x * ld;
+  bf16* out = p + (size_t)blockIdx.x * ld;
   float mx = -INFINITY;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) mx = fmaxf(mx, __bfloat162float(row[i]));
+  for (int i = threadIdx.x; i < n; i += blockDim.x) mx = fmaxf(mx, row[i]);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
@@ -286,7 +295,7 @@ __global__ void __launch_bounds__(256) softmax_rows_kernel(bf16* __restrict__ s,
   for (int i = 1; i < int(blockDim.x >> 5); ++i) mx = fmaxf(mx, red[i]);
   __syncthreads();
   float sum = 0.f;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) sum += __expf(__bfloat162float(row[i]) - mx);
+  for (int i = threadIdx.x; i < n; i += blockDim.x) sum += __expf(row[i] - mx);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sum;
@@ -294,31 +303,31 @@ __global__ void __launch_bounds__(256) softmax_rows_kernel(bf16* __restrict__ s,
   sum = 0.f;
   for (int i = 0; i < int(blockDim.x >> 5); ++i) sum += red[i];
   const float inv = 1.f / sum;
-  for (int i = threadIdx.x; i < n; i += blockDim.x)
-    row[i] = __float2bfloat16(__expf(__bfloat162float(row[i]) - mx) * inv);
+  for (int i = threadIdx.x; i < ld; i += blockDim.x)
+    out[i] = i < n ? __float2bfloat16(__expf(row[i] - mx) * inv) : __float2bfloat16(0.f);
 }
-int launch_softmax_rows(bf16* s, int M, int n, int ld, cudaStream_t stream) {
-  softmax_rows_kernel<<<M, 256, 0, stream>>>(s, n, ld);
+int launch_softmax_rows(const float* s, bf16* p, int M, int n, int ld, cudaStream_t stream) {
+  softmax_rows_kernel<<<M, 256, 0, stream>>>(s, p, n, ld);
   MGB_LAUNCH_CHECK("softmax_rows");
 }
 
-// x bf16 [M, N] -> y bf16 [N, M] through a padded smem tile
-__global__ void transpose_bf16_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, int M, int N) {
+// x bf16 [M, N] -> y bf16 [N, ld] (ld >= M; columns [M, ld) zeroed) through a padded smem tile
+__global__ void transpose_bf16_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, int M, int N, int ld) {
   __shared__ bf16 tile[32][33];
   const int m0 = blockIdx.y * 32, n0 = blockIdx.x * 32;
   for (int r = threadIdx.y; r < 32; r += blockDim.y) {
     const int m = m0 + r, n = n0 + threadIdx.x;
-    if (m < M && n < N) tile[r][threadIdx.x] = x[(size_t)m * N + n];
+    tile[r][threadIdx.x] = (m < M && n < N) ? x[(size_t)m * N + n] : __float2bfloat16(0.f);
   }
   __syncthreads();
   for (int r = threadIdx.y; r < 32; r += blockDim.y) {
     const int n = n0 + r, m = m0 + threadIdx.x;
-    if (m < M && n < N) y[(size_t)n * M + m] = tile[threadIdx.x][r];
+    if (m < ld && n < N) y[(size_t)n * ld + m] = tile[threadIdx.x][r];
   }
 }
-int launch_transpose_bf16(const bf16* x, bf16* y, int M, int N, cudaStream_t stream) {
-  dim3 grid((N + 31) / 32, (M + 31) / 32), block(32, 8);
-  transpose_bf16_kernel<<<grid, block, 0, stream>>>(x, y, M, N);
+int launch_transpose_bf16(const bf16* x, bf16* y, int M, int N, int ld, cudaStream_t stream) {
+  dim3 grid((N + 31) / 32, (ld + 31) / 32), block(32, 8);
+  transpose_bf16_kernel<<<grid, block, 0, stream>>>(x, y, M, N, ld);
   MGB_LAUNCH_CHECK("transpose_bf16");
 }
 

@@ -115,10 +115,11 @@ int launch_gn_fused(const float* xa, int Ca, const float* xb, int Cb, bf16* y, b
 // LayerNorm over the channel dim: x_f32 [M, C] -> y_bf16 [M, C]
 int launch_layernorm(const float* x, bf16* y, const float* gamma, const float* beta, int M, int C, float eps,
                      cudaStream_t stream);
-// y[NB, 4, H/2, W/2, C] (parity planes p = (h&1)*2 + (w&1)) from x fp32 [NB, H, W, C]
+// y[NB, 4, ceil(H/2), ceil(W/2), C] (parity planes p = (h&1)*2 + (w&1), zero where the source pixel does not exist) from
+// x fp32 [NB, H, W, C]
 int launch_space_to_depth(const float* x, bf16* y, int NB, int H, int W, int C, cudaStream_t stream);
-// nearest x2: x fp32 [NB, H, W, C] -> y bf16 [NB, 2H, 2W, C]
-int launch_upsample2x(const float* x, bf16* y, int NB, int H, int W, int C, cudaStream_t stream);
+// nearest upsampling: x fp32 [NB, H, W, C] -> y bf16 [NB, Ho, Wo, C], Ho in {2H - 1, 2H}, Wo in {2W - 1, 2W}
+int launch_upsample2x(const float* x, bf16* y, int NB, int H, int W, int C, int Ho, int Wo, cudaStream_t stream);
 // channel concat (fp32): out[M, Ca + Cb] = [a | b]
 int launch_concat(const float* a, const float* b, float* out, int M, int Ca, int Cb, cudaStream_t stream);
 // fp32 -> bf16 cast
@@ -144,10 +145,10 @@ int launch_linear_small(const float* x, const float* w, const float* b, float* y
                         int silu_in, int silu_out, cudaStream_t stream);
 // sinusoidal timestep embedding (flip_sin_to_cos, shift 0): t[M] -> emb[M, dim] = [cos | sin]
 int launch_timestep_embedding(const float* t, float* emb, int M, int dim, cudaStream_t stream);
-// row softmax over bf16 scores in place: s[M, ld] (first n valid), fp32 math
-int launch_softmax_rows(bf16* s, int M, int n, int ld, cudaStream_t stream);
-// out[M, N] fp32 row-major -> bf16 transposed [N, M]
-int launch_transpose_bf16(const bf16* x, bf16* y, int M, int N, cudaStream_t stream);
+// row softmax: fp32 scores s[M, ld] (first n valid) -> bf16 p[M, ld] with columns [n, ld) zeroed
+int launch_softmax_rows(const float* s, bf16* p, int M, int n, int ld, cudaStream_t stream);
+// x bf16 [M, N] -> y bf16 [N, ld] (columns [M, ld) zeroed)
+int launch_transpose_bf16(const bf16* x, bf16* y, int M, int N, int ld, cudaStream_t stream);
 
 // ---------------------------------------------------------------------------------------------
 // Ensemble kernels (ensemble.cu)

@@ -78,8 +78,8 @@ static int gemm_common(Ctx& c, GemmParams& p, int bn, int splits, const Epi& e, 
   return run_gemm(p, bn, c.splitk_ws, c.stream);
 }
 
-// y = a[M,K] W^T (+ epilogue)
-static int linear(Ctx& c, const bf16* a, int M, const LinW& W, const Epi& e) {
+// y = a[M,K] W^T (+ epilogue); ldo = row stride of the outputs (0: W.n, or W.n / 2 for GEGLU)
+static int linear(Ctx& c, const bf16* a, int M, const LinW& W, const Epi& e, int ldo = 0) {
   int bn, sp, st;
   const bool geglu = (e.flags & EPI_GEGLU) != 0;
   choose_tile((M + 127) / 128, W.n, W.k / 64, geglu, true, &bn, &sp, &st);
@@ -88,20 +88,21 @@ static int linear(Ctx& c, const bf16* a, int M, const LinW& W, const Epi& e) {
   if (c.dry) return MGB_OK;
   GemmParams p;
   TRY(fill_linear_params(&p, a, W.w, M, W.n, W.k, bn, sp, st));
-  return gemm_common(c, p, bn, effective_splits(p), e, geglu ? W.n / 2 : W.n);
+  return gemm_common(c, p, bn, effective_splits(p), e, ldo > 0 ? ldo : (geglu ? W.n / 2 : W.n));
 }
 
 // generic A[M,K] x B[N,K]^T with raw pointers (attention score / PV GEMMs in the VAE)
-static int matmul_nt(Ctx& c, const bf16* a, const bf16* b, int M, int N, int K, const Epi& e) {
+static int matmul_nt(Ctx& c, const bf16* a, const bf16* b, int M, int N, int K, const Epi& e, int ldo = 0) {
   LinW W; W.w = const_cast<bf16*>(b); W.n = N; W.k = K;
   // B is an activation written by an earlier kernel of this stream (K, or V^T straight out of the transpose): the
   // GEMM's pre-wait B prefetch must not run ahead of its producer, so no programmatic early launch here.
   PlainLaunchScope no_early_launch;
-  return linear(c, a, M, W, e);
+  return linear(c, a, M, W, e, ldo);
 }
 
 // 3x3 conv on NHWC bf16; Hout x Wout output; kind per ops.cu
-static int conv3x3(Ctx& c, const bf16* x, int NB, int Hout, int Wout, const ConvW& W, int kind, const Epi& e) {
+static int conv3x3(Ctx& c, const bf16* x, int NB, int Hout, int Wout, const ConvW& W, int kind, const Epi& e,
+                   int Hsrc = 0, int Wsrc = 0) {
   int tw, th;
   conv_tile_shape(Hout, Wout, &tw, &th, kind);
   const int m_tiles = NB * ((Wout + tw - 1) / tw) * ((Hout + th - 1) / th);
@@ -113,7 +114,7 @@ static int conv3x3(Ctx& c, const bf16* x, int NB, int Hout, int Wout, const Conv
   if (sp > 1) c.splitk_need = std::max(c.splitk_need, size_t(sp) * M * W.cout * sizeof(float));
   if (c.dry) return MGB_OK;
   GemmParams p;
-  TRY(fill_conv_params(&p, x, W.w, NB, Hout, Wout, W.cin_pad, W.cout, kind, bn, sp, st));
+  TRY(fill_conv_params(&p, x, W.w, NB, Hout, Wout, W.cin_pad, W.cout, kind, bn, sp, st, Hsrc, Wsrc));
   Epi e2 = e;
   e2.hw = Hout * Wout;
   return gemm_common(c, p, bn, effective_splits(p), e2, W.cout);
@@ -230,18 +231,21 @@ static int xfmr_forward(Ctx& c, const XfmrW& X, Act& x, Act& y, int NB, int T) {
 
 // ---------------------------------------------------------------------------------------------
 // VAE mid-block attention: single head, dim C (512), over T = h*w tokens. x, y fp32 [NB*T, C].
-// Scores are materialised per image in bf16 (T x T), softmaxed in place, then P V via V^T.
+// Per image: fp32 scores S = Q K^T / sqrt(C) (T x Tp, Tp = T rounded up to 64), fp32 row softmax -> bf16 P with the
+// pad columns zeroed, O = P V through V^T [C, Tp] (pad zeroed): any T works, and the logits are never rounded to bf16.
 // ---------------------------------------------------------------------------------------------
 static int vae_attn_forward(Ctx& c, const VaeAttnW& A, Act& x, Act& y, int NB, int T) {
   const int C = A.C;
   const size_t M = size_t(NB) * T;
+  const int Tp = (T + 63) / 64 * 64;
   const size_t mk = c.arena->mark();
   bf16* a = aalloc<bf16>(c, M * C);
   bf16* q = aalloc<bf16>(c, M * C);
   bf16* k = aalloc<bf16>(c, M * C);
   bf16* v = aalloc<bf16>(c, M * C);
-  bf16* vt = aalloc<bf16>(c, size_t(T) * C);
-  bf16* s = aalloc<bf16>(c, size_t(T) * T);
+  bf16* vt = aalloc<bf16>(c, size_t(C) * Tp);
+  float* s = aalloc<float>(c, size_t(T) * Tp);
+  bf16* pr = aalloc<bf16>(c, size_t(T) * Tp);
   bf16* o = aalloc<bf16>(c, M * C);
   TRY(groupnorm(c, x, nullptr, a, nullptr, A.gn, NB, T, 1e-6f, 0));
   { Epi e; e.bias = A.q.b; e.out_bf16 = q; TRY(linear(c, a, int(M), A.q, e)); }
@@ -250,10 +254,10 @@ static int vae_attn_forward(Ctx& c, const VaeAttnW& A, Act& x, Act& y, int NB, i
   const float scale = 1.0f / sqrtf(float(C));
   for (int n = 0; n < NB; ++n) {
     const size_t off = size_t(n) * T * C;
-    { Epi e; e.out_bf16 = s; e.flags = EPI_SCALE; e.scale = scale; TRY(matmul_nt(c, q + off, k + off, T, T, C, e)); }
-    LAUNCH(launch_softmax_rows(s, T, T, T, c.stream), 1);
-    LAUNCH(launch_transpose_bf16(v + off, vt, T, C, c.stream), 1);
-    { Epi e; e.out_bf16 = o + off; TRY(matmul_nt(c, s, vt, T, C, T, e)); }
+    { Epi e; e.out_f32 = s; e.flags = EPI_SCALE; e.scale = scale; TRY(matmul_nt(c, q + off, k + off, T, T, C, e, Tp)); }
+    LAUNCH(launch_softmax_rows(s, pr, T, T, Tp, c.stream), 1);
+    LAUNCH(launch_transpose_bf16(v + off, vt, T, C, Tp, c.stream), 1);
+    { Epi e; e.out_bf16 = o + off; TRY(matmul_nt(c, pr, vt, T, C, Tp, e)); }
   }
   { Epi e; e.bias = A.o.b; e.residual = x.p; e.out_f32 = y.p; TRY(linear(c, o, int(M), A.o, e)); }
   c.arena->release(mk);
@@ -284,6 +288,10 @@ int unet_forward(mgb_handle* hd, Ctx& c, const float* rgb, float* tgt, const flo
   int H = lh, W = lw;
   size_t M = size_t(NB) * H * W;
   TRY(zero_counters(c));
+  // level sizes: a stride-2 pad-1 conv gives ceil(s / 2); coming back up the target is the skip connection's size
+  // (diffusers forwards `upsample_size` when a latent dim is not a multiple of 8), i.e. 2s or 2s - 1
+  int lvH[4] = {lh, 0, 0, 0}, lvW[4] = {lw, 0, 0, 0};
+  for (int i = 1; i < 4; ++i) { lvH[i] = (lvH[i - 1] + 1) / 2; lvW[i] = (lvW[i - 1] + 1) / 2; }
 
   std::vector<Act> skips;
   size_t ri = 0, xi = 0;
@@ -316,9 +324,10 @@ int unet_forward(mgb_handle* hd, Ctx& c, const float* rgb, float* tgt, const flo
       skips.push_back(h);
     }
     if (!last) {
-      bf16* planes = aalloc<bf16>(c, M * cur);
+      const int Hn = lvH[i + 1], Wn = lvW[i + 1];
+      bf16* planes = aalloc<bf16>(c, size_t(NB) * 4 * Hn * Wn * cur);
       LAUNCH(launch_space_to_depth(h.p, planes, NB, H, W, cur, c.stream), 1);
-      H /= 2; W /= 2; M = size_t(NB) * H * W;
+      H = Hn; W = Wn; M = size_t(NB) * H * W;
       Act y = act_alloc(c, M, cur);
       {
         Epi e; e.bias = U.downs[i].b; e.out_f32 = y.p;
@@ -354,9 +363,10 @@ int unet_forward(mgb_handle* hd, Ctx& c, const float* rgb, float* tgt, const flo
       }
     }
     if (i < 3) {
-      bf16* up = aalloc<bf16>(c, M * 4 * cur);
-      LAUNCH(launch_upsample2x(h.p, up, NB, H, W, cur, c.stream), 1);
-      H *= 2; W *= 2; M = size_t(NB) * H * W;
+      const int Hn = lvH[2 - i], Wn = lvW[2 - i];
+      bf16* up = aalloc<bf16>(c, size_t(NB) * Hn * Wn * cur);
+      LAUNCH(launch_upsample2x(h.p, up, NB, H, W, cur, Hn, Wn, c.stream), 1);
+      H = Hn; W = Wn; M = size_t(NB) * H * W;
       Act y = act_alloc(c, M, cur);
       {
         Epi e; e.bias = U.ups[i].b; e.out_f32 = y.p;
@@ -406,11 +416,13 @@ int vae_encode_forward(mgb_handle* hd, Ctx& c, const float* rgb, float* latent_o
       h = y; cur = ch[i];
     }
     if (i < 3) {
-      bf16* planes = aalloc<bf16>(c, M * cur);
+      // F.pad(x, (0,1,0,1)) + 3x3 stride 2 pad 0: floor(s / 2) outputs; the parity planes hold ceil(s / 2) entries
+      const int Hp = (H + 1) / 2, Wp = (W + 1) / 2;
+      bf16* planes = aalloc<bf16>(c, size_t(NB) * 4 * Hp * Wp * cur);
       LAUNCH(launch_space_to_depth(h.p, planes, NB, H, W, cur, c.stream), 1);
       H /= 2; W /= 2; M = size_t(NB) * H * W;
       Act y = act_alloc(c, M, cur);
-      { Epi e; e.bias = V.enc_down[i].b; e.out_f32 = y.p; TRY(conv3x3(c, planes, NB, H, W, V.enc_down[i], 3, e)); }
+      { Epi e; e.bias = V.enc_down[i].b; e.out_f32 = y.p; TRY(conv3x3(c, planes, NB, H, W, V.enc_down[i], 3, e, Hp, Wp)); }
       h = y;
     }
   }
@@ -471,7 +483,7 @@ int vae_decode_forward(mgb_handle* hd, Ctx& c, const float* latent, float* out, 
     }
     if (i < 3) {
       bf16* up = aalloc<bf16>(c, M * 4 * cur);
-      LAUNCH(launch_upsample2x(h.p, up, NB, H, W, cur, c.stream), 1);
+      LAUNCH(launch_upsample2x(h.p, up, NB, H, W, cur, 2 * H, 2 * W, c.stream), 1);
       H *= 2; W *= 2; M = size_t(NB) * H * W;
       Act y = act_alloc(c, M, cur);
       { Epi e; e.bias = V.dec_up[i].b; e.out_f32 = y.p; TRY(conv3x3(c, up, NB, H, W, V.dec_up[i], 0, e)); }

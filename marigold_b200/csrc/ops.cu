@@ -80,7 +80,12 @@ int fill_linear_params(GemmParams* p, const bf16* a, const bf16* w, int M, int N
 }
 
 int fill_conv_params(GemmParams* p, const bf16* x, const bf16* w, int NB, int Hout, int Wout, int Cin, int Cout,
-                     int kind, int block_n, int splits, int stages) {
+                     int kind, int block_n, int splits, int stages, int Hsrc, int Wsrc) {
+  // Hsrc x Wsrc: spatial extent of the tensor the taps address (the image for stride 1; one parity plane for
+  // stride 2, i.e. ceil(Hin / 2) x ceil(Win / 2), which exceeds the output by one for the VAE's pad-(0,1,0,1) conv
+  // on an odd input). <= 0: same as the output.
+  if (Hsrc <= 0) Hsrc = Hout;
+  if (Wsrc <= 0) Wsrc = Wout;
   memset(p, 0, sizeof(*p));
   if (Cin % 64 != 0 || NB <= 0 || Hout <= 0 || Wout <= 0) {
     set_error("conv2d: need Cin %% 64 == 0 (got NB=%d H=%d W=%d Cin=%d)", NB, Hout, Wout, Cin);
@@ -149,8 +154,8 @@ int fill_conv_params(GemmParams* p, const bf16* x, const bf16* w, int NB, int Ho
   }
 
   const uint64_t C2 = uint64_t(Cin) * 2;
-  const uint64_t dims[5] = {uint64_t(Cin), uint64_t(Wout), uint64_t(Hout), uint64_t(planes), uint64_t(NB)};
-  const uint64_t strides[4] = {C2, C2 * Wout, C2 * Wout * Hout, C2 * Wout * Hout * planes};
+  const uint64_t dims[5] = {uint64_t(Cin), uint64_t(Wsrc), uint64_t(Hsrc), uint64_t(planes), uint64_t(NB)};
+  const uint64_t strides[4] = {C2, C2 * Wsrc, C2 * Wsrc * Hsrc, C2 * Wsrc * Hsrc * planes};
   const uint32_t box[5] = {64, box_w, box_h, 1, 1};
   int rc = make_tmap_5d(&p->tmap_a, x, dims, strides, box);
   if (rc) return rc;

@@ -72,7 +72,7 @@ def layernorm(x, gamma, beta, eps=1e-5):
 def space_to_depth(x):
     lib = _lib.load()
     NB, H, W, Cc = x.shape
-    y = torch.empty(NB, 4, H // 2, W // 2, Cc, dtype=torch.bfloat16, device=x.device)
+    y = torch.empty(NB, 4, (H + 1) // 2, (W + 1) // 2, Cc, dtype=torch.bfloat16, device=x.device)
     check(lib.mgb_op_space_to_depth(ptr(x), ptr(y), NB, H, W, Cc, stream_ptr()), "mgb_op_space_to_depth")
     return y
 

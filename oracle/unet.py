@@ -168,8 +168,12 @@ class Upsample2D(nn.Module):
         super().__init__()
         self.conv = nn.Conv2d(c, c, 3, padding=1)
 
-    def forward(self, x):
-        return self.conv(F.interpolate(x, scale_factor=2.0, mode="nearest"))
+    def forward(self, x, output_size=None):
+        # diffusers Upsample2D.forward: scale_factor=2 by default; when the UNet forwards `upsample_size` (latent sizes
+        # that are not a multiple of 2**num_upsamplers) the target is the skip connection's size: interpolate(size=...)
+        if output_size is None:
+            return self.conv(F.interpolate(x, scale_factor=2.0, mode="nearest"))
+        return self.conv(F.interpolate(x, size=output_size, mode="nearest"))
 
 
 class DownBlock(nn.Module):
@@ -223,14 +227,17 @@ class UpBlock(nn.Module):
             [Transformer2DModel(cout, cfg.cross_attention_dim, cfg.head_dim, g) for _ in skip_channels]) if attn else None
         self.upsamplers = nn.ModuleList([Upsample2D(cout)]) if up else None
 
-    def forward(self, x, skips, temb, ctx):
+    def forward(self, x, skips, temb, ctx, forward_upsample_size=False):
         for i, r in enumerate(self.resnets):
             x = torch.cat([x, skips.pop()], dim=1)
             x = r(x, temb)
             if self.attentions is not None:
                 x = self.attentions[i](x, ctx)
         if self.upsamplers is not None:
-            x = self.upsamplers[0](x)
+            # UNet2DConditionModel.forward: `upsample_size = down_block_res_samples[-1].shape[2:]` (the next skip) when
+            # any latent dim % 2**num_upsamplers != 0; this is how odd sizes such as 54 -> 27 -> 14 -> 7 come back up
+            size = tuple(skips[-1].shape[2:]) if forward_upsample_size else None
+            x = self.upsamplers[0](x, size)
         return x
 
 
@@ -272,6 +279,8 @@ class UNet2DConditionOracle(nn.Module):
             h, outs = blk(h, temb, encoder_hidden_states)
             skips += outs
         h = self.mid_block(h, temb, encoder_hidden_states)
+        up_factor = 2 ** (len(self.up_blocks) - 1)
+        fwd_size = any(d % up_factor != 0 for d in x.shape[-2:])
         for blk in self.up_blocks:
-            h = blk(h, skips, temb, encoder_hidden_states)
+            h = blk(h, skips, temb, encoder_hidden_states, fwd_size)
         return self.conv_out(F.silu(self.conv_norm_out(h)))

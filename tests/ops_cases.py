@@ -57,6 +57,7 @@ def cases():
     add("layernorm_320", case_layernorm, M=9216, C=320)
     add("layernorm_1280", case_layernorm, M=576, C=1280)
     add("s2d", case_s2d, NB=2, H=24, W=16, C=128)
+    add("s2d_odd", case_s2d, NB=1, H=27, W=13, C=64)
     add("upsample", case_upsample, NB=2, H=12, W=8, C=64)
     return cases
 
@@ -266,7 +267,9 @@ def case_s2d(NB, H, W, C):
 
     x = torch.randn(NB, H, W, C, device="cuda")
     out = ops.space_to_depth(x)
-    ref = torch.stack([x[:, a::2, b::2] for a in (0, 1) for b in (0, 1)], dim=1).to(torch.bfloat16)
+    # odd sizes: planes hold ceil(H/2) x ceil(W/2) entries, zero where the source pixel does not exist
+    xp = torch.nn.functional.pad(x, (0, 0, 0, W % 2, 0, H % 2))
+    ref = torch.stack([xp[:, a::2, b::2] for a in (0, 1) for b in (0, 1)], dim=1).to(torch.bfloat16)
     return {"ok": bool(torch.equal(out, ref))}
 
 

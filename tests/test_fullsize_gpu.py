@@ -65,7 +65,8 @@ def _encode_refs(ref, yard, img):
     return r, y
 
 
-@pytest.mark.parametrize("h,w", [(768, 768), (1024, 1024), (768, 576)])
+# 768 x 432: a 16:9 photo at processing_res 768 (54 x 96 latents: odd level sizes 27 x 48, 14 x 24, 7 x 12)
+@pytest.mark.parametrize("h,w", [(768, 768), (1024, 1024), (768, 576), (432, 768)])
 def test_stages_match_oracle_within_the_bf16_yardstick(full, h, w):
     from marigold_b200.schedulers import DDIMScheduler
 

@@ -26,7 +26,9 @@ def _ddim(n):
     return s
 
 
-@pytest.mark.parametrize("B,lh,lw", [(1, 16, 16), (2, 8, 24)])
+# (27, 12), (7, 9): latent sizes that are not multiples of 8 exercise the ceil(s/2) stride-2 convs and the
+# skip-sized ("upsample_size") nearest upsampling of diffusers, as a 16:9 photo at processing_res 768 does (54 x 96)
+@pytest.mark.parametrize("B,lh,lw", [(1, 16, 16), (2, 8, 24), (1, 27, 12), (2, 7, 9)])
 def test_unet_step_matches_oracle(tiny, B, lh, lw):
     unet, vae, text, eng = tiny
     s = _ddim(4)
@@ -47,22 +49,26 @@ def test_unet_step_matches_oracle(tiny, B, lh, lw):
         assert rel_err(tgt, upd) < 1e-5                     # fused scheduler epilogue is fp32-exact
 
 
-def test_vae_encode_matches_oracle(tiny):
+@pytest.mark.parametrize("B,H,W", [(2, 64, 128), (1, 100, 50), (1, 77, 131)])
+def test_vae_encode_matches_oracle(tiny, B, H, W):
+    """Any H x W >= 8 (the reference resizes to max-edge and encodes whatever results, image_util.py:90-120): the
+    pad-(0,1,0,1) stride-2 convs give floor(s/2) at every level."""
     unet, vae, text, eng = tiny
     g = torch.Generator().manual_seed(12)
-    rgb = torch.rand(2, 3, 64, 128, generator=g) * 2 - 1
+    rgb = torch.rand(B, 3, H, W, generator=g) * 2 - 1
     with torch.no_grad():
         ref = vae.quant_conv(vae.encoder(rgb))[:, :4] * 0.18215
     out = eng.encode(rgb.cuda())
     torch.cuda.synchronize()
-    assert record("tiny/encode", rel_err(out, ref)) < 3e-2
+    assert out.shape == ref.shape == (B, 4, H // 8, W // 8)
+    assert record(f"tiny/encode_{H}x{W}", rel_err(out, ref)) < 3e-2
 
 
 @pytest.mark.parametrize("mode", [0, 1, 2])
 def test_vae_decode_matches_oracle(tiny, mode):
     unet, vae, text, eng = tiny
     g = torch.Generator().manual_seed(13)
-    lat = torch.randn(2, 4, 8, 16, generator=g)
+    lat = torch.randn(2, 4, 8, 16, generator=g) if mode != 0 else torch.randn(2, 4, 9, 13, generator=g)
     with torch.no_grad():
         raw = vae.decoder(vae.post_quant_conv(lat / 0.18215))
     if mode == 0:

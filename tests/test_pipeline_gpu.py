@@ -56,8 +56,14 @@ def test_depth_pipeline_ensemble_and_resize(setup):
     z0, _ = _noise(3, 8, 16, 2)
     pipe = MarigoldDepthPipeline(eng, DDIMScheduler(), text, default_denoising_steps=2,
                                  default_processing_resolution=128)
-    with pytest.raises(Exception):
-        pipe(img, ensemble_size=3, noise=z0, processing_res=100, show_progress_bar=False)  # 50x100: not /64
+    # processing_res=100 -> 50 x 100 pixels -> 6 x 12 latents -> 48 x 96 decoded, resized back to the input size:
+    # sizes that are not multiples of 64 run like in the reference (image_util.py:90-120, VAE floor semantics)
+    z1 = torch.randn(1, 4, 6, 12, generator=torch.Generator().manual_seed(5))
+    odd = pipe(img, ensemble_size=1, noise=z1, processing_res=100, show_progress_bar=False)
+    ora100 = OracleDepthPipeline(unet, vae, DDIMSchedulerOracle(), text, 2, 100)
+    ref100, _, _ = ora100(img, ensemble_size=1, noise=z1)
+    assert odd.depth_np.shape == ref100.shape == (128, 256)
+    assert record("tiny/pipe_depth_50x100_max", np.abs(odd.depth_np - ref100).max()) < 3e-2
     out = pipe(img, ensemble_size=3, noise=z0, batch_size=2, show_progress_bar=False,
                ensemble_kwargs=dict(output_uncertainty=True))
     ora = OracleDepthPipeline(unet, vae, DDIMSchedulerOracle(), text, 2, 128)
