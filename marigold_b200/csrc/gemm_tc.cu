@@ -193,8 +193,13 @@ __device__ __forceinline__ void scratch_put(float* s_wr, const uint32_t (&r)[32]
 // -------------------------------------------------------------------------------------------------
 // The kernel
 // -------------------------------------------------------------------------------------------------
-template <int BLOCK_N>
-__global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_constant__ GemmParams p) {
+// MINB = CTAs per SM the kernel is compiled for. 1: up to 156 registers per thread, deep operand ring (one output tile
+// per SM at a time; single-wave grids). 2: <= 96 registers and <= 113 KB of shared memory, so TWO CTAs share an SM and
+// the epilogue of one tile (TMEM -> registers -> global, latency-bound) runs under the K loop of the other — the
+// overlap a persistent kernel gets from a double-buffered accumulator, obtained from the hardware scheduler instead
+// (2 x 256 TMEM columns = the whole tensor memory). Used for multi-wave grids (GEGLU feed-forward, QKV, VAE convs).
+template <int BLOCK_N, int MINB>
+__global__ void __launch_bounds__(kGemmThreads, MINB) gemm_tc_kernel(const __grid_constant__ GemmParams p) {
   pdl_launch_dependents();
   const long long t_entry = clock64();
   extern __shared__ uint8_t smem_raw[];
@@ -483,16 +488,19 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
       const float scale = (!raw && (e.flags & EPI_SCALE)) ? e.scale : 1.0f;
       const bool silu = !raw && (e.flags & EPI_SILU);
       const bool ld_vec = (ldo & 3) == 0;
-      // row addressing hoisted out of the chunk loop: after the transpose this lane stores rows
-      // R = it * 4 + (lane >> 3), it = 0..7, of its warp's 32-row slab
-      long long off[8];
+      // row addressing: after the transpose this lane stores rows R = it * 4 + (lane >> 3), it = 0..7, of its warp's
+      // 32-row slab. MINB == 1: hoisted out of the chunk loop (8 offsets live); MINB == 2: recomputed per batch of 4 rows
+      constexpr int RB = MINB == 2 ? 4 : 8;   // rows in flight per lane
+      long long off[MINB == 2 ? 1 : 8];
       uint32_t vmask = 0;
+      if constexpr (MINB == 1) {
 #pragma unroll
-      for (int it = 0; it < 8; ++it) {
-        long long m;
-        const bool ok = tile_row_index(tg, q * 32 + it * 4 + sub, &m);
-        off[it] = m * (long long)ldo;
-        vmask |= uint32_t(ok) << it;
+        for (int it = 0; it < 8; ++it) {
+          long long m;
+          const bool ok = tile_row_index(tg, q * 32 + it * 4 + sub, &m);
+          off[it] = m * (long long)ldo;
+          vmask |= uint32_t(ok) << it;
+        }
       }
 #pragma unroll 1
       for (int j = ehalf; j < chunks; j += 2) {
@@ -527,29 +535,45 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
         if (chunk_nv <= 0) { __syncwarp(); continue; }
         const bool vec = ld_vec && nv >= 4;
         if (!geglu && !silu && ld_vec && chunk_nv >= 32) {
-          // fast path. All 8 scratch loads and all 8 residual loads are issued BEFORE anything is consumed
+          // fast path. All scratch loads and residual loads of a batch of RB rows are issued BEFORE anything is consumed
           // (tried and rejected, r01: requesting the next TMEM chunk / the residual rows one phase earlier made the
           // epilogue 15% slower)
-          float4 x[8], rr[8];
 #pragma unroll
-          for (int it = 0; it < 8; ++it) x[it] = *reinterpret_cast<const float4*>(s_rd + it * (4 * kEpiPitch));
-          if (residual) {
+          for (int r0 = 0; r0 < 8; r0 += RB) {
+            float4 x[RB], rr[RB];
+            long long ob[RB];
+            uint32_t vm = 0;
 #pragma unroll
-            for (int it = 0; it < 8; ++it)
-              rr[it] = ((vmask >> it) & 1u) ? __ldg(reinterpret_cast<const float4*>(residual + off[it] + col))
+            for (int it = 0; it < RB; ++it) {
+              if constexpr (MINB == 1) {
+                ob[it] = off[r0 + it];
+                vm |= ((vmask >> (r0 + it)) & 1u) << it;
+              } else {
+                long long m;
+                const bool ok = tile_row_index(tg, q * 32 + (r0 + it) * 4 + sub, &m);
+                ob[it] = m * (long long)ldo;
+                vm |= uint32_t(ok) << it;
+              }
+              x[it] = *reinterpret_cast<const float4*>(s_rd + (r0 + it) * (4 * kEpiPitch));
+            }
+            if (residual) {
+#pragma unroll
+              for (int it = 0; it < RB; ++it)
+                rr[it] = ((vm >> it) & 1u) ? __ldg(reinterpret_cast<const float4*>(residual + ob[it] + col))
                                            : make_float4(0.f, 0.f, 0.f, 0.f);
-          }
+            }
 #pragma unroll
-          for (int it = 0; it < 8; ++it) {
-            float4 v = x[it];
-            v.x = fmaf(v.x, scale, b4.x); v.y = fmaf(v.y, scale, b4.y);
-            v.z = fmaf(v.z, scale, b4.z); v.w = fmaf(v.w, scale, b4.w);
-            if (residual) { v.x += rr[it].x; v.y += rr[it].y; v.z += rr[it].z; v.w += rr[it].w; }
-            if ((vmask >> it) & 1u) {
-              const long long o = off[it] + col;
-              if (out_f32) *reinterpret_cast<float4*>(out_f32 + o) = v;
-              if (out_bf16)
-                *reinterpret_cast<uint2*>(out_bf16 + o) = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+            for (int it = 0; it < RB; ++it) {
+              float4 v = x[it];
+              v.x = fmaf(v.x, scale, b4.x); v.y = fmaf(v.y, scale, b4.y);
+              v.z = fmaf(v.z, scale, b4.z); v.w = fmaf(v.w, scale, b4.w);
+              if (residual) { v.x += rr[it].x; v.y += rr[it].y; v.z += rr[it].z; v.w += rr[it].w; }
+              if ((vm >> it) & 1u) {
+                const long long o = ob[it] + col;
+                if (out_f32) *reinterpret_cast<float4*>(out_f32 + o) = v;
+                if (out_bf16)
+                  *reinterpret_cast<uint2*>(out_bf16 + o) = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+              }
             }
           }
         } else {
@@ -652,14 +676,14 @@ __global__ void __launch_bounds__(kSkThreads) splitk_epilogue_kernel(const GemmP
 static long long* g_gemm_dbg = nullptr;
 void set_gemm_debug_buffer(long long* dev_ptr) { g_gemm_dbg = dev_ptr; }
 
-template <int BN>
+template <int BN, int MINB>
 static int launch_one(const GemmParams& p_in, int splits, cudaStream_t stream) {
   GemmParams p = p_in;
   p.dbg = g_gemm_dbg;
   const size_t smem = gemm_smem_bytes(BN, p.stages, p.mode == 2 ? p.halo_slots * p.halo_slot_bytes : -1);
   static bool attr_set = false;  // per template instantiation
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return int(e);
     attr_set = true;
   }
@@ -670,19 +694,28 @@ static int launch_one(const GemmParams& p_in, int splits, cudaStream_t stream) {
     m_tiles = (p.M / (p.H * p.W)) * p.tiles_x * p.tiles_y;
   }
   dim3 grid(m_tiles, (p.N + BN - 1) / BN, splits);
-  cudaError_t le = launch_k(gemm_tc_kernel<BN>, grid, kGemmThreads, smem, stream, p);
+  cudaError_t le = launch_k(gemm_tc_kernel<BN, MINB>, grid, kGemmThreads, smem, stream, p);
   if (le != cudaSuccess) return int(le);
   return int(cudaGetLastError());
 }
 
-int launch_gemm_tc(const GemmParams& p, int block_n, int splits, cudaStream_t stream) {
+int launch_gemm_tc(const GemmParams& p, int block_n, int splits, int ctas_per_sm, cudaStream_t stream) {
+  if (ctas_per_sm == 2) {
+    switch (block_n) {
+      case 64: return launch_one<64, 2>(p, splits, stream);
+      case 128: return launch_one<128, 2>(p, splits, stream);
+      case 160: return launch_one<160, 2>(p, splits, stream);
+      case 256: return launch_one<256, 2>(p, splits, stream);
+      default: break;
+    }
+  }
   switch (block_n) {
-    case 16: return launch_one<16>(p, splits, stream);
-    case 32: return launch_one<32>(p, splits, stream);
-    case 64: return launch_one<64>(p, splits, stream);
-    case 128: return launch_one<128>(p, splits, stream);
-    case 160: return launch_one<160>(p, splits, stream);
-    case 256: return launch_one<256>(p, splits, stream);
+    case 16: return launch_one<16, 1>(p, splits, stream);
+    case 32: return launch_one<32, 1>(p, splits, stream);
+    case 64: return launch_one<64, 1>(p, splits, stream);
+    case 128: return launch_one<128, 1>(p, splits, stream);
+    case 160: return launch_one<160, 1>(p, splits, stream);
+    case 256: return launch_one<256, 1>(p, splits, stream);
     default: return int(cudaErrorInvalidValue);
   }
 }

@@ -71,8 +71,9 @@ struct GemmParams {
   GemmEpilogue epi;
 };
 
-// Launch. block_n in {16, 32, 64, 128, 160, 256}. Returns cudaError_t as int.
-int launch_gemm_tc(const GemmParams& p, int block_n, int splits, cudaStream_t stream);
+// Launch. block_n in {16, 32, 64, 128, 160, 256}; ctas_per_sm 1 or 2 (2: p.stages must keep gemm_smem_bytes <= 113 KB,
+// block_n >= 64). Returns cudaError_t as int.
+int launch_gemm_tc(const GemmParams& p, int block_n, int splits, int ctas_per_sm, cudaStream_t stream);
 void set_gemm_debug_buffer(long long* dev_ptr);  // debug hook: phase timestamps of subsequent launches
 // Deferred epilogue for split-K: sums `splits` partials and applies p.epi.
 int launch_splitk_epilogue(const GemmParams& p, int block_n, int splits, cudaStream_t stream);

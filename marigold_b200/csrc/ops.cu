@@ -172,7 +172,26 @@ int run_gemm(GemmParams& p, int block_n, float* splitk_ws, cudaStream_t stream) 
     set_error("GEGLU epilogue needs block_n %% 64 == 0 (got %d)", block_n);
     return MGB_ERR_INVALID;
   }
-  if (block_n > 16) {
+  // Multi-wave grids run two CTAs per SM (gemm_tc.cu, MINB = 2): shallow operand rings of <= 113 KB, the epilogue of
+  // one tile under the K loop of its neighbour. Single-wave grids keep one CTA per SM with a deep ring.
+  static const int two_cta_env = getenv("MGB_GEMM_2CTA") ? atoi(getenv("MGB_GEMM_2CTA")) : 1;
+  int ctas_per_sm = 1;
+  {
+    const long long m_tiles = p.mode == 0 ? (p.M + 127) / 128 : (long long)(p.M / (p.H * p.W)) * p.tiles_x * p.tiles_y;
+    const long long ctas = m_tiles * ((p.N + block_n - 1) / block_n) * splits;
+    if (two_cta_env && block_n >= 64 && p.mode != 2 && ctas > 148) {
+      const int stage_bytes = 16384 + block_n * 128;
+      const int st2 = std::min(p.stages, (113 * 1024 - 1280) / stage_bytes);
+      const int need = 8 * ((p.epi.flags & EPI_GEGLU) ? 9216 : 4608);
+      if (st2 >= 2 && st2 * stage_bytes >= need) { p.stages = st2; ctas_per_sm = 2; }
+    }
+    // experiment switch (MGB_GEMM_2CTA=2): single-wave grids keep their deep ring but run the 96-register binary, so that
+    // small successor kernels launched early (PDL) can become resident beside the tail of this one
+    if (two_cta_env == 2 && ctas_per_sm == 1 && block_n >= 64 && p.mode != 2) ctas_per_sm = -2;
+  }
+  const int kernel_minb = ctas_per_sm == 1 ? 1 : 2;
+  if (ctas_per_sm == -2) ctas_per_sm = 1;
+  if (block_n > 16 && ctas_per_sm == 1) {
     // the drained operand ring doubles as the epilogue's transpose scratch (8 warps x 4.5 KB, x2 for GEGLU): deepen
     // the pipeline until that fits
     const int need = 8 * ((p.epi.flags & EPI_GEGLU) ? 9216 : 4608);
@@ -200,7 +219,7 @@ int run_gemm(GemmParams& p, int block_n, float* splitk_ws, cudaStream_t stream) 
   } else {
     p.partial = nullptr;
   }
-  int e = launch_gemm_tc(p, block_n, splits, stream);
+  int e = launch_gemm_tc(p, block_n, splits, kernel_minb, stream);
   if (e) {
     set_error("gemm_tc launch failed: %s", cudaGetErrorString(cudaError_t(e)));
     return MGB_ERR_CUDA;
