@@ -1,7 +1,10 @@
 """Benchmark of the Marigold denoising hot path (BASELINE.json metric: denoise-steps/sec @768 px).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--config c2|c3|c4|c5]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+--config selects the BASELINE.json configuration (default c2 = configs[1], the headline; the others are the
+LCM / normals / 1024-px cases of configs[2..4], same metric, members sharded round-robin over the ranks).
 
 A "step" is one denoising iteration (cat -> UNet -> scheduler.step, reference
 marigold/marigold_depth_pipeline.py:456-468) of ONE ensemble member at 768x768 (latent 96x96), the
@@ -29,10 +32,68 @@ from pathlib import Path
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
-RES = 768
-SCHEDULE_STEPS = 50                     # configs[1]: 50 DDIM steps
 F_UNET = {384: 0.418e12, 768: 2.138e12, 1024: 4.658e12}    # algorithmic FLOP per member-step
 METRIC = "denoise-steps/sec @768px (UNet forward + scheduler step per ensemble member)"
+# BASELINE.json configs[1..4]. ensemble: None = one member per GPU (weak scaling, the headline); a number = that many
+# members sharded round-robin over the ranks (rank r takes r, r+G, ...: uneven 2/1 splits for E=10 on 8 GPUs).
+CONFIGS = {
+    "c2": dict(name="marigold-depth-v1-1, 768x768, ensemble_size=1 member per GPU, 50-step DDIM (trailing, zero-SNR, v-pred)",
+               res=768, sched="ddim", sched_steps=50, ensemble=None, task="depth", images=1),
+    "c3": dict(name="marigold-depth-lcm-v1-0, 768x768, ensemble_size=8, 4-step LCM", res=768, sched="lcm", sched_steps=4,
+               ensemble=8, task="depth", images=1),
+    "c4": dict(name="marigold-normals-v1-1, 768x768, ensemble_size=10, 10-step DDIM", res=768, sched="ddim",
+               sched_steps=10, ensemble=10, task="normals", images=1),
+    "c5": dict(name="marigold-depth-v1-1, 1024x1024, ensemble_size=10, 50-step DDIM, image batch (bounded sample: 2 of 16 "
+                    "images end to end)", res=1024, sched="ddim", sched_steps=50, ensemble=10, task="depth", images=2),
+}
+RES, SCHEDULE_STEPS = 768, 50           # headline values; run_b200 / run_reference use the selected config
+
+
+def usable_cores() -> int:
+    """Cores this process may actually use (affinity mask and cgroup CPU quota), not os.cpu_count()."""
+    n = os.cpu_count() or 1
+    try:
+        n = min(n, len(os.sched_getaffinity(0)))
+    except Exception:  # noqa: BLE001
+        pass
+    try:
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()
+        if q != "max":
+            n = min(n, max(1, int(float(q) / float(per))))
+    except Exception:  # noqa: BLE001
+        pass
+    return max(1, n)
+
+
+def cpu_model() -> str:
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.lower().startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except Exception:  # noqa: BLE001
+        pass
+    return "unknown"
+
+
+def synthetic_image(S: int, seed: int = 1234):
+    """uint8 [1,3,S,S]: smooth sinusoids + rectangles + pixel noise."""
+    import numpy as np
+    import torch
+
+    rng = np.random.default_rng(seed)
+    yy, xx = np.meshgrid(np.linspace(0, 1, S), np.linspace(0, 1, S), indexing="ij")
+    img = np.zeros((3, S, S))
+    for _ in range(6):
+        fx, fy, ph = rng.uniform(0.5, 4, 2).tolist() + [rng.uniform(0, 6.28)]
+        amp = rng.uniform(20, 50, 3)
+        img += amp[:, None, None] * np.sin(2 * np.pi * (fx * xx + fy * yy) + ph)[None]
+    img += 128
+    for _ in range(5):
+        x0, y0 = rng.integers(0, S - 8, 2)
+        w, h = rng.integers(8, max(9, S // 3), 2)
+        img[:, y0:y0 + h, x0:x0 + w] = rng.uniform(0, 255, 3)[:, None, None]
+    img += rng.normal(0, 4, img.shape)
+    return torch.from_numpy(np.clip(img, 0, 255).astype(np.uint8))[None]
 
 
 def _peaks():
@@ -88,21 +149,45 @@ class ClockSampler:
 
 
 def _build_models(kind="full"):
-    from tests.helpers import oracle_models
+    """Random-init weights of the real architecture (torch default init, seed 0): the oracle modules are only the
+    weight generator here (and the checker of the cpu_baseline / --impl reference legs)."""
+    import torch
 
-    return oracle_models(kind)
+    from oracle.unet import UNet2DConditionOracle, UNetConfig
+    from oracle.vae import AutoencoderKLOracle, VAEConfig
+
+    torch.manual_seed(0)
+    unet = UNet2DConditionOracle(UNetConfig()).eval()
+    vae = AutoencoderKLOracle(VAEConfig()).eval()
+    text = torch.randn(1, 2, 1024, generator=torch.Generator().manual_seed(7))
+    return unet, vae, text
 
 
-def _ddim_tables(total):
-    """Coefficient tables of the 50-step DDIM schedule, cycled to `total` entries."""
+def _engine(unet, vae, text):
+    from marigold_b200.engine import Engine, EngineConfig
+
+    eng = Engine(EngineConfig())
+    eng.load_state_dict("unet", unet.state_dict())
+    eng.load_state_dict("vae", vae.state_dict())
+    eng.finalize()
+    eng.set_text_embedding(text)
+    return eng
+
+
+def _scheduler(cfg):
+    from marigold_b200.schedulers import DDIMScheduler, LCMScheduler
+
+    return LCMScheduler() if cfg["sched"] == "lcm" else DDIMScheduler()
+
+
+def _tables(cfg, total):
+    """Coefficient tables of the configuration's schedule, cycled to `total` entries."""
     import numpy as np
 
-    from marigold_b200.schedulers import DDIMScheduler
-
-    s = DDIMScheduler()
-    s.set_timesteps(SCHEDULE_STEPS)
+    s = _scheduler(cfg)
+    s.set_timesteps(cfg["sched_steps"])
     kx, kv, kz = s.coefficients()
-    idx = np.arange(total) % SCHEDULE_STEPS
+    idx = np.arange(total) % cfg["sched_steps"]
     return s.timesteps[idx], kx[idx], kv[idx], kz[idx]
 
 
@@ -112,10 +197,10 @@ def run_b200(args):
     import torch.distributed as dist
 
     from marigold_b200 import _lib, parallel
-    from marigold_b200.pipeline import MarigoldDepthPipeline
-    from marigold_b200.schedulers import DDIMScheduler
-    from tests.helpers import engine_from_oracle, synthetic_image
+    from marigold_b200.pipeline import MarigoldDepthPipeline, MarigoldNormalsPipeline
 
+    cfg = CONFIGS[args.config]
+    res, n_sched = cfg["res"], cfg["sched_steps"]
     rank = int(os.environ.get("RANK", 0))
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
@@ -125,28 +210,31 @@ def run_b200(args):
     dev = torch.device("cuda", local_rank)
     lib = _lib.load()
 
-    from tests.helpers import usable_cores
-
     torch.set_num_threads(max(1, usable_cores() // max(1, world)))   # N ranks share the box's usable cores
     unet, vae, text = _build_models("full")
-    eng = engine_from_oracle(unet, vae, text)
+    eng = _engine(unet, vae, text)
     del vae                                   # weights live on the device now; only rank 0 keeps the fp32 UNet
-    if rank != 0 or args.no_cpu_baseline:     # (the checker of the cpu_baseline leg)
-        unet = None
+    if rank != 0 or (args.no_cpu_baseline and args.no_library_baseline):
+        unet = None                           # (the checker of the cpu_baseline / library-baseline legs)
     import gc
 
     gc.collect()
     K, W = args.steps, args.warmup
-    ts, kx, kv, kz = _ddim_tables(W + K)
+    ts, kx, kv, kz = _tables(cfg, W + K)
     eng.set_schedule(ts, kx, kv, kz)
 
-    lh = lw = RES // 8
+    E = cfg["ensemble"] if cfg["ensemble"] is not None else world            # c2: one member per GPU
+    mine = parallel.member_indices(E, rank, world)
+    B = len(mine)
+    lh = lw = res // 8
     g = torch.Generator().manual_seed(2024)
-    noise_all = torch.randn(max(world, 1), 4, lh, lw, generator=g)           # member k uses row k on any rank
-    img = synthetic_image(RES)
+    noise_all = torch.randn(E, 4, lh, lw, generator=g)                        # member k uses row k on any rank
+    step_noise_all = torch.randn(W + K, E, 4, lh, lw, generator=g) if cfg["sched"] == "lcm" else None
+    img = synthetic_image(res)
     rgb = (img.float() / 255.0 * 2 - 1).to(dev)
-    rgb_latent = eng.encode(rgb).contiguous()
-    target = noise_all[rank:rank + 1].to(dev).contiguous()
+    rgb_latent = eng.encode(rgb).expand(max(B, 1), -1, -1, -1).contiguous()
+    target = noise_all[mine].to(dev).contiguous() if B else None
+    sn = step_noise_all[:, mine].to(dev).contiguous() if (step_noise_all is not None and B) else None
 
     def sync_all():
         torch.cuda.synchronize()
@@ -155,7 +243,8 @@ def run_b200(args):
             torch.cuda.synchronize()
 
     # ---- device-timed K steps, inputs resident in HBM -------------------------------------------
-    eng.denoise_range_(rgb_latent, target, 0, W)
+    if B:
+        eng.denoise_range_(rgb_latent, target, 0, W, sn)
     sync_all()
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -163,7 +252,8 @@ def run_b200(args):
     l0 = lib.mgb_launch_count()
     t_cpu0 = time.perf_counter()
     e0.record()
-    eng.denoise_range_(rgb_latent, target, W, K)
+    if B:
+        eng.denoise_range_(rgb_latent, target, W, K, sn)
     e1.record()
     t_enqueue = time.perf_counter() - t_cpu0
     sync_all()
@@ -171,54 +261,66 @@ def run_b200(args):
     clocks = sampler.stop()
     ms_local = e0.elapsed_time(e1)
     ms = parallel.barrier_max_ms(ms_local, dev)
-    assert torch.isfinite(target).all(), "non-finite latent after the timed region"
-    value = world * K / (ms / 1e3)
+    if B:
+        assert torch.isfinite(target).all(), "non-finite latent after the timed region"
+    value = E * K / (ms / 1e3)                       # member-steps of ALL ranks / max-over-ranks device time
 
-    # ---- end to end through the public pipeline API: host image in, numpy depth out -------------
-    n_e2e = min(K, SCHEDULE_STEPS)
-    pipe = MarigoldDepthPipeline(eng, DDIMScheduler(), text, default_denoising_steps=n_e2e,
-                                 default_processing_resolution=RES)
+    # ---- end to end through the public pipeline API: host image in, numpy map out --------------
+    n_e2e = min(K, n_sched) if cfg["ensemble"] is None else n_sched
+    sched = _scheduler(cfg)
+    Pipe = MarigoldNormalsPipeline if cfg["task"] == "normals" else MarigoldDepthPipeline
+    pipe = Pipe(eng, sched, text, default_denoising_steps=n_e2e, default_processing_resolution=res)
     img_pinned = img.pin_memory()
     noise_pinned = noise_all.pin_memory()
-    E = world                                                               # 1 member per GPU
+    kw = dict(ensemble_size=E, noise=noise_pinned, show_progress_bar=False)
+    if cfg["task"] == "depth":
+        kw["color_map"] = None
+    if cfg["sched"] == "lcm" and n_e2e > 1:
+        kw["step_noise"] = step_noise_all[: n_e2e - 1].pin_memory()
     import logging
 
     logging.disable(logging.WARNING)
-    pipe(img_pinned, ensemble_size=E, noise=noise_pinned, color_map=None, show_progress_bar=False)   # warm-up
+    pipe(img_pinned, **kw)                                                   # warm-up
     sync_all()
-    reps = 2
+    reps = max(2, cfg["images"])
     t0 = time.perf_counter()
     for _ in range(reps):
-        out = pipe(img_pinned, ensemble_size=E, noise=noise_pinned, color_map=None, show_progress_bar=False)
+        out = pipe(img_pinned, **kw)
     torch.cuda.synchronize()
     t_e2e_local = (time.perf_counter() - t0) / reps
     t_e2e = parallel.barrier_max_ms(t_e2e_local * 1e3, dev) / 1e3
     e2e_value = E * n_e2e / t_e2e
-    h2d = img_pinned.numel() * img_pinned.element_size() + (noise_pinned.numel() // max(world, 1)) * 4
-    d2h = out.depth_np.size * 4
+    h2d = img_pinned.numel() * img_pinned.element_size() + len(mine) * 4 * lh * lw * 4
+    res_np = out.normals_np if cfg["task"] == "normals" else out.depth_np
+    d2h = res_np.size * 4
 
-    # ---- dominant kernel alone (CUDA-graph replay => pure device time) ---------------------------
+    # ---- dominant kernels alone (CUDA-graph replay => pure device time) ---------------------------
     kern = None
     if rank == 0 and not args.no_kernel_roofline:
         kern = _dominant_kernel_roofline(torch)
 
+    # ---- the same graph through torch's library kernels (cuDNN / cuBLAS / SDPA, bf16) on this GPU ----
+    libbase = None
+    if rank == 0 and not args.no_library_baseline:
+        libbase = _library_baseline(unet, text, res, min(K, 10))
+
     # ---- CPU baseline (oracle port) on a bounded sample ------------------------------------------
     cpu = None
     if rank == 0 and not args.no_cpu_baseline:
-        cpu = _cpu_baseline(unet, text, steps=1)
+        cpu = _cpu_baseline(unet, text, steps=1, res=res)
     eng.close()
 
     if rank == 0:
         pk = _peaks()
-        achieved = world * K * F_UNET[RES] / (ms / 1e3) / 1e12
+        achieved = E * K * F_UNET[res] / (ms / 1e3) / 1e12
         peak = pk["tflops_sustained"] * world
         line = {
             "metric": METRIC, "value": value, "unit": "denoise-steps/s", "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": "marigold-depth-v1-1 architecture (SD-2 UNet 865.9M + SD VAE), 768x768, "
-                                   "ensemble_size=1 member per GPU, 50-step DDIM schedule (trailing, zero-SNR, v-pred)",
-                       "members_per_gpu": 1, "latent": [lh, lw], "parallelism": f"members-dp{world}",
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak" if cfg["ensemble"] is None else "strong",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": cfg["name"] + " — SD-2 UNet 865.9M + SD VAE architecture", "id": args.config,
+                       "members_total": E, "members_this_rank": B, "latent": [lh, lw],
+                       "parallelism": f"members-dp{world}",
                        "l2": "inputs > L2: 1.73 GB of bf16 weights stream from HBM every step",
                        "weights": "random init (torch default init, seed 0)"},
             "clocks": clocks,
@@ -226,13 +328,17 @@ def run_b200(args):
             "cpu_enqueue_ms_per_step": t_enqueue * 1e3 / K,
             "e2e": {"value": e2e_value, "unit": "denoise-steps/s", "h2d_bytes_per_step": h2d / n_e2e,
                     "d2h_bytes_per_step": d2h / n_e2e, "seconds_per_image": t_e2e, "steps_per_call": n_e2e,
+                    "images_timed": reps,
                     "includes": "H2D image+noise, resize/normalise, VAE encode, denoise loop, VAE decode, "
-                                + ("all-gather + ensemble, " if world > 1 else "") + "resize, D2H depth"},
+                                + ("all-gather, " if world > 1 else "") + ("ensemble, " if E > 1 else "")
+                                + "resize, D2H result"},
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                          "frac": achieved / peak, "traffic": None,
-                         "what": "whole fused UNet step (all kernels), algorithmic FLOP 2.138e12 per member-step",
+                         "what": f"whole fused UNet step (all kernels), algorithmic FLOP {F_UNET[res]:.4g} per member-step",
                          "peak_source": pk["source"] + ", bf16_tflops_sustained x n_gpus",
-                         "dominant_kernel": kern},
+                         "dominant_kernel": kern[0] if kern else None,
+                         "kernels": kern},
+            "gpu_library_baseline": libbase,
             "cpu_baseline": cpu,
         }
         print(json.dumps(line), flush=True)
@@ -241,26 +347,8 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
-def _dominant_kernel_roofline(torch):
-    """The top-level 3x3 conv (320 -> 320 @ 96x96, 16 per UNet step): algorithmic FLOP / device time,
-    timed alone with a CUDA graph of 20 launches (no host gaps), burst peak as denominator."""
-    from marigold_b200 import ops
-
-    pk = _peaks()
-    NB, H, W_, C = 1, 96, 96, 320
-    x = torch.randn(NB, H, W_, C, device="cuda").to(torch.bfloat16)
-    w = ops.pack_conv_weight((torch.randn(C, C, 3, 3, device="cuda") / (9 * C) ** 0.5).to(torch.bfloat16))
-    b = torch.randn(C, device="cuda")
-    out = torch.empty(NB, H, W_, C, dtype=torch.float32, device="cuda")
-    from marigold_b200 import _lib
-    from marigold_b200._lib import check, ptr, stream_ptr
-
-    lib = _lib.load()
-
-    def launch():
-        check(lib.mgb_op_conv2d(ptr(x), ptr(w), ptr(b), None, ptr(out), None, NB, H, W_, C, C, 0, 0, 0, 0, 0, None,
-                                stream_ptr()), "mgb_op_conv2d")
-
+def _graph_time_us(torch, launch, n=20, reps=5):
+    """Average device time of `launch` from a CUDA graph of n launches (no host gaps)."""
     launch()
     torch.cuda.synchronize()
     s = torch.cuda.Stream()
@@ -268,27 +356,107 @@ def _dominant_kernel_roofline(torch):
         launch()
         gr = torch.cuda.CUDAGraph()
         with torch.cuda.graph(gr, stream=s):
-            for _ in range(20):
+            for _ in range(n):
                 launch()
     torch.cuda.synchronize()
     gr.replay()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(5):
+    for _ in range(reps):
         gr.replay()
     e1.record()
     torch.cuda.synchronize()
-    us = e0.elapsed_time(e1) * 1e3 / 100
-    flop = 2.0 * NB * H * W_ * C * C * 9
+    return e0.elapsed_time(e1) * 1e3 / (n * reps)
+
+
+def _library_baseline(unet, text, res, steps):
+    """Informational GPU yardstick: the oracle graph of one UNet + DDIM step run by torch in bf16 on
+    the same B200 — cuDNN convolutions, cuBLAS linears, SDPA attention, eager launches — i.e. what the reference pipeline
+    executes with torch_dtype=bfloat16. Not part of the product path."""
+    import copy
+
+    import torch
+
+    from oracle.schedulers import DDIMSchedulerOracle
+
+    if unet is None:
+        return None
+    try:
+        m = copy.deepcopy(unet).to("cuda", torch.bfloat16)
+        ctx = text.to("cuda", torch.bfloat16)
+        lh = res // 8
+        g = torch.Generator().manual_seed(1)
+        x = torch.randn(1, 4, lh, lh, generator=g).to("cuda", torch.bfloat16)
+        rgb = torch.randn(1, 4, lh, lh, generator=g).to("cuda", torch.bfloat16)
+        o = DDIMSchedulerOracle()
+        o.set_timesteps(50)
+        with torch.no_grad():
+            for i in range(3):
+                t = o.timesteps[i]
+                x = o.step(m(torch.cat([rgb, x], 1), t, ctx), t, x)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for i in range(steps):
+                t = o.timesteps[3 + i]
+                x = o.step(m(torch.cat([rgb, x], 1), t, ctx), t, x)
+            e1.record()
+            torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        del m
+        torch.cuda.empty_cache()
+        return {"value": 1e3 / ms, "unit": "denoise-steps/s", "ms_per_step": ms, "steps": steps,
+                "what": f"oracle UNet + DDIM graph, torch {torch.__version__} bf16 (cuDNN / cuBLAS / SDPA), eager, 1 member, "
+                        f"{res}x{res}, same GPU"}
+    except Exception as e:  # noqa: BLE001
+        return {"unavailable": repr(e)[:200]}
+
+
+def _dominant_kernel_roofline(torch):
+    """The two kernels that dominate a 768-px UNet step BY TIME, each timed alone from a CUDA graph of 20 launches
+    against the burst peak: (1) flash self-attention over the 9216 latent tokens (5 launches x ~0.2 ms per step),
+    (2) the top-level 3x3 conv 320 -> 320 @ 96x96 (16 launches per step)."""
+    from marigold_b200 import _lib, ops
+    from marigold_b200._lib import check, ptr, stream_ptr
+
+    pk = _peaks()
+    lib = _lib.load()
+    out = []
+    # (1) attention: qkv [9216, 960] bf16, 5 heads of 64; algorithmic FLOP 4 T^2 C
+    T, C = 9216, 320
+    qkv = torch.randn(T, 3 * C, device="cuda").to(torch.bfloat16)
+    us = _graph_time_us(torch, lambda: ops.flash_attn64(qkv, 1, T, C, 0.125))
+    flop = 4.0 * T * T * C
     ach = flop / (us * 1e-6) / 1e12
-    return {"kernel": "gemm_tc_kernel (implicit-GEMM conv3x3 320->320 @96x96)", "us_per_launch": us,
-            "achieved": ach, "peak": pk["tflops_burst"], "unit": "TFLOP/s", "frac": ach / pk["tflops_burst"],
-            "peak_source": pk["source"] + ", bf16_tflops (burst: kernel timed alone)",
-            # one `ncu --set full` capture of this launch (profiles/r01f_ncu_full_summary.txt): dram__bytes_read.sum +
-            # dram__bytes_write.sum. Algorithmic bytes are 19.5e6 (A 5.9e6 bf16, weights 1.8e6, fp32 output 11.8e6): the
-            # operands and the output stay in the 126 MB L2 between kernels, so DRAM sees less than the algorithm moves.
-            "traffic": 7791872, "traffic_source": "ncu r01f, dram read+write bytes per launch"}
+    out.append({"kernel": "flash_attn64_kernel + attn_combine_kernel (self-attention, T=9216, 5 heads x 64)",
+                "us_per_launch": us, "achieved": ach, "peak": pk["tflops_burst"], "unit": "TFLOP/s",
+                "frac": ach / pk["tflops_burst"], "share_of_step": "5 launches/step",
+                "peak_source": pk["source"] + ", bf16_tflops (burst: kernel timed alone)",
+                "traffic": None, "traffic_source": "profiles/r02_kernel_table.md (ncu --set full, dram read+write)"})
+    # (2) conv
+    NB, H, W_, Cc = 1, 96, 96, 320
+    x = torch.randn(NB, H, W_, Cc, device="cuda").to(torch.bfloat16)
+    w = ops.pack_conv_weight((torch.randn(Cc, Cc, 3, 3, device="cuda") / (9 * Cc) ** 0.5).to(torch.bfloat16))
+    b = torch.randn(Cc, device="cuda")
+    o = torch.empty(NB, H, W_, Cc, dtype=torch.float32, device="cuda")
+
+    def launch():
+        check(lib.mgb_op_conv2d(ptr(x), ptr(w), ptr(b), None, ptr(o), None, NB, H, W_, Cc, Cc, 0, 0, 0, 0, 0, None,
+                                stream_ptr()), "mgb_op_conv2d")
+
+    us = _graph_time_us(torch, launch)
+    flop = 2.0 * NB * H * W_ * Cc * Cc * 9
+    ach = flop / (us * 1e-6) / 1e12
+    out.append({"kernel": "gemm_tc_kernel<160> (implicit-GEMM conv3x3 320->320 @96x96)", "us_per_launch": us,
+                "achieved": ach, "peak": pk["tflops_burst"], "unit": "TFLOP/s", "frac": ach / pk["tflops_burst"],
+                "share_of_step": "16 launches/step",
+                "peak_source": pk["source"] + ", bf16_tflops (burst: kernel timed alone)",
+                # one `ncu --set full` capture of this launch: dram__bytes_read.sum + dram__bytes_write.sum. Algorithmic
+                # bytes are 19.5e6 (A 5.9e6 bf16, weights 1.8e6, fp32 output 11.8e6): operands and output stay in the
+                # 126 MB L2 between kernels, so DRAM sees less than the algorithm moves.
+                "traffic": 7791872, "traffic_source": "ncu r01f, dram read+write bytes per launch"})
+    return out
 
 
 def _cpu_baseline(unet, text, steps=1, res=RES):
@@ -296,8 +464,6 @@ def _cpu_baseline(unet, text, steps=1, res=RES):
     import torch
 
     from oracle.schedulers import DDIMSchedulerOracle
-
-    from tests.helpers import usable_cores
 
     torch.set_num_threads(usable_cores())
     lh = res // 8
@@ -312,8 +478,8 @@ def _cpu_baseline(unet, text, steps=1, res=RES):
             t = o.timesteps[i]
             x = o.step(unet(torch.cat([rgb, x], 1), t, text), t, x)
         dt = time.perf_counter() - t0
-    return {"value": steps / dt, "unit": "denoise-steps/s", "cores": torch.get_num_threads(), "kind": "port",
-            "sample": f"{steps} UNet+DDIM step(s), 1 member, {res}x{res}, fp32 torch CPU oracle (oracle/unet.py), "
+    return {"value": steps / dt, "unit": "denoise-steps/s", "cores": torch.get_num_threads(), "cpu": cpu_model(),
+            "kind": "port", "sample": f"{steps} UNet+DDIM step(s), 1 member, {res}x{res}, fp32 torch CPU oracle (oracle/unet.py), "
                       f"{dt:.1f} s"}
 
 
@@ -327,15 +493,15 @@ def run_reference(args):
     import torch
 
     K, W = args.steps, args.warmup
-    from tests.helpers import usable_cores
-
     unet, vae, text = _build_models("full")
     torch.set_num_threads(usable_cores())
     # bounded sample: pick the resolution so that W + K steps fit in ~4 minutes on this host
+    cfg = CONFIGS[args.config]
+    target = cfg["res"]
     probe = _cpu_baseline(unet, text, steps=1, res=384)
     t384 = 1.0 / probe["value"]
     budget = 240.0
-    res = 768 if (W + K) * t384 * (F_UNET[768] / F_UNET[384]) < budget else 384
+    res = target if (W + K) * t384 * (F_UNET[target] / F_UNET[384]) < budget else 384
     lh = res // 8
     from oracle.schedulers import DDIMSchedulerOracle
 
@@ -354,17 +520,19 @@ def run_reference(args):
             t = o.timesteps[i % n_sched]
             x = o.step(unet(torch.cat([rgb, x], 1), t, text), t, x)
         dt = time.perf_counter() - t0
-    scale = F_UNET[res] / F_UNET[768]          # FLOP-equivalent 768-px steps
+    scale = F_UNET[res] / F_UNET[target]          # FLOP-equivalent steps at the configuration's resolution
     value = K * scale / dt
     sample = (f"{K} UNet+DDIM steps at {res}x{res} (1 member), fp32 torch CPU oracle port; "
-              + ("measured at the metric's resolution" if res == 768 else
-                 f"bounded sample: value scaled by F_unet({res})/F_unet(768) = {scale:.4f} to 768-px-equivalent steps"))
-    cpu = {"value": value, "unit": "denoise-steps/s", "cores": torch.get_num_threads(), "kind": "port", "sample": sample}
+              + ("measured at the metric's resolution" if res == target else
+                 f"bounded sample: value scaled by F_unet({res})/F_unet({target}) = {scale:.4f} to {target}-px-equivalent "
+                 f"steps"))
+    cpu = {"value": value, "unit": "denoise-steps/s", "cores": torch.get_num_threads(), "cpu": cpu_model(), "kind": "port",
+           "sample": sample}
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "denoise-steps/s",
             "n_gpus": int(os.environ.get("WORLD_SIZE", args.gpus)), "steps": K, "warmup": W,
             "ms_per_step": dt * 1e3 / K / scale, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "marigold-depth-v1-1 architecture, 768x768, ensemble_size=1, 50-step DDIM schedule",
+            "config": {"workload": cfg["name"] + " — SD-2 UNet 865.9M + SD VAE architecture", "id": args.config,
                        "note": "reference pipeline needs diffusers (absent offline): oracle port on host cores"},
             "cpu_baseline": cpu,
             "e2e": {"value": value, "unit": "denoise-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -377,7 +545,9 @@ if __name__ == "__main__":
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-library-baseline", action="store_true")
     ap.add_argument("--no-kernel-roofline", action="store_true")
     a = ap.parse_args()
     if a.warmup < 3 and a.impl == "b200":

@@ -38,7 +38,7 @@ typedef enum {
 } mgb_status;
 
 typedef enum { MGB_F32 = 0, MGB_BF16 = 1, MGB_F16 = 2 } mgb_dtype;
-typedef enum { MGB_DECODE_DEPTH = 0, MGB_DECODE_NORMALS = 1, MGB_DECODE_RAW3 = 2 } mgb_decode_mode;
+typedef enum { MGB_DECODE_DEPTH = 0, MGB_DECODE_NORMALS = 1, MGB_DECODE_RAW3 = 2, MGB_DECODE_UNIT3 = 3 } mgb_decode_mode;
 
 typedef struct mgb_handle mgb_handle;
 
@@ -46,8 +46,8 @@ typedef struct mgb_handle mgb_handle;
  * Channel counts must be multiples of 64; attention head_dim is 64 (SD-2: "attention_head_dim"
  * there is a head COUNT, C/64). */
 typedef struct {
-  int32_t unet_in_channels;        /* 8  = rgb latent (4) | target latent (4)                       */
-  int32_t unet_out_channels;       /* 4                                                             */
+  int32_t unet_in_channels;        /* 8 = rgb latent (4) | target latent (4); IID with n targets: 4 (n + 1) */
+  int32_t unet_out_channels;       /* 4; IID: 4 n (n <= 4)                                          */
   int32_t unet_block_channels[4];  /* 320, 640, 1280, 1280                                          */
   int32_t unet_layers_per_block;   /* 2                                                             */
   int32_t unet_cross_dim;          /* 1024                                                          */
@@ -89,16 +89,18 @@ int mgb_set_schedule(mgb_handle* h, int32_t n, const int32_t* timesteps, const f
 
 /* ---- the hot path --------------------------------------------------------------------------- */
 /* encode_rgb: vae.encoder + quant_conv, mean half, * latent_scale  (…pipeline.py:479-496).
- * rgb_dev [B,3,H,W] in [-1,1]; latent_dev [B,4,H/8,W/8]. H, W multiples of 64. */
+ * rgb_dev [B,3,H,W] in [-1,1]; latent_dev [B,4,H/8,W/8] (floor). Any H, W >= 8: like the reference, sizes that are not
+ * multiples of 8 lose the remainder rows / columns in the VAE's stride-2 convs. */
 int mgb_encode(mgb_handle* h, const float* rgb_dev, int32_t B, int32_t H, int32_t W, float* latent_dev,
                void* stream);
 /* One denoising iteration i: cat -> unet -> scheduler.step (…pipeline.py:456-468).
- * target_dev [B,4,h,w] is updated in place; noise_dev (or NULL) is this step's z; if
- * model_out_dev != NULL it also receives the raw UNet output [B,4,h,w]. */
+ * target_dev [B,Ct,h,w] (Ct = unet_out_channels: 4, or 4 n for an n-target IID model, marigold_iid_pipeline.py:538-551)
+ * is updated in place; noise_dev (or NULL) is this step's z; if model_out_dev != NULL it also receives the raw UNet
+ * output [B,Ct,h,w]. Any h, w >= 1 (odd sizes follow diffusers' `upsample_size` path). */
 int mgb_unet_step(mgb_handle* h, const float* rgb_latent_dev, float* target_dev, const float* noise_dev,
                   float* model_out_dev, int32_t step_index, int32_t B, int32_t lh, int32_t lw, void* stream);
 /* The whole loop (…pipeline.py:455-468): steps 0..n-1 of the current schedule.
- * step_noise_dev: [n-1, B, 4, h, w] or NULL (required when any kz != 0). */
+ * step_noise_dev: [n-1, B, Ct, h, w] or NULL (required when any kz != 0). */
 int mgb_denoise(mgb_handle* h, const float* rgb_latent_dev, float* target_dev, const float* step_noise_dev,
                 int32_t B, int32_t lh, int32_t lw, void* stream);
 /* Steps [first_step, first_step + num_steps) of the current schedule only (bench.py times K steps of a
@@ -107,7 +109,8 @@ int mgb_denoise_range(mgb_handle* h, const float* rgb_latent_dev, float* target_
                       int32_t first_step, int32_t num_steps, int32_t B, int32_t lh, int32_t lw, void* stream);
 /* decode_depth / decode_normals + the clip / shift / normalise that follow
  * (…depth_pipeline.py:498-516,473-475; …normals_pipeline.py:463-479,438-440).
- * out_dev: DEPTH [B,1,H,W] in [0,1]; NORMALS [B,3,H,W] unit vectors; RAW3 [B,3,H,W]. */
+ * out_dev: DEPTH [B,1,H,W] in [0,1]; NORMALS [B,3,H,W] unit vectors; RAW3 [B,3,H,W]; UNIT3 [B,3,H,W] = (clip(x,-1,1)+1)/2
+ * (one IID target, marigold_iid_pipeline.py:562-565,578-585: the caller loops over the targets' 4-channel slices). */
 int mgb_decode(mgb_handle* h, const float* latent_dev, int32_t B, int32_t lh, int32_t lw, int32_t mode,
                float* out_dev, void* stream);
 
@@ -138,6 +141,11 @@ int mgb_ens_depth_reduce(mgb_handle* h, const float* depth_dev, const double* pa
  * member_idx_dev int32 [HW] or NULL = argmax index. reduction_closest: 1 = "closest", 0 = "mean". */
 int mgb_ens_normals(mgb_handle* h, const float* normals_dev, int32_t E, int64_t HW, int32_t reduction_closest,
                     float* out_dev, float* uncert_dev, int32_t* member_idx_dev, void* stream);
+
+/* ensemble_iid (ensemble.py:252-270): targets_dev [E, N] (N = 3 n H W) -> pred_dev [N] = lower median (or mean) over the
+ * members; uncert_dev [N] or NULL = median absolute deviation (or unbiased std). No alignment, no renormalisation. */
+int mgb_ens_iid(mgb_handle* h, const float* targets_dev, int32_t E, int64_t N, int32_t reduction_median, float* pred_dev,
+                float* uncert_dev, void* stream);
 
 /* ---- capacity ------------------------------------------------------------------------------- */
 /* Bytes of the activation arena the handle holds for images of H x W with B members per batch. */

@@ -5,11 +5,12 @@ pipelines + output dataclasses + ensembling, plus the Engine that stands in for 
 Importing the package does not load the CUDA library; the first Engine()/ensemble call does, and
 fails loudly if it is unavailable (no CPU fallback)."""
 from .engine import Engine, EngineConfig  # noqa: F401
-from .ensemble import ensemble_depth, ensemble_normals  # noqa: F401
+from .ensemble import ensemble_depth, ensemble_iid, ensemble_normals  # noqa: F401
 from .iid import IIDEntry, MarigoldIIDOutput  # noqa: F401
 from .pipeline import (  # noqa: F401
     MarigoldDepthOutput,
     MarigoldDepthPipeline,
+    MarigoldIIDPipeline,
     MarigoldNormalsOutput,
     MarigoldNormalsPipeline,
     MarigoldPipeline,
@@ -18,4 +19,4 @@ from .schedulers import DDIMScheduler, LCMScheduler  # noqa: F401
 
 __all__ = ["Engine", "EngineConfig", "MarigoldDepthPipeline", "MarigoldNormalsPipeline", "MarigoldPipeline",
            "MarigoldDepthOutput", "MarigoldNormalsOutput", "DDIMScheduler", "LCMScheduler", "ensemble_depth",
-           "ensemble_normals", "IIDEntry", "MarigoldIIDOutput"]
+           "ensemble_normals", "ensemble_iid", "IIDEntry", "MarigoldIIDOutput", "MarigoldIIDPipeline"]

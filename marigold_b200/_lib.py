@@ -34,7 +34,7 @@ class mgb_config(C.Structure):
 
 
 # epilogue flags (kernels.h)
-EPI_GEGLU, EPI_SCHED, EPI_DEPTH, EPI_NORMALS, EPI_NCHW, EPI_SILU, EPI_SCALE = 1, 2, 4, 8, 16, 32, 64
+EPI_GEGLU, EPI_SCHED, EPI_DEPTH, EPI_NORMALS, EPI_NCHW, EPI_SILU, EPI_SCALE, EPI_UNIT = 1, 2, 4, 8, 16, 32, 64, 128
 
 _vp, _i32, _i64, _f32, _f64 = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_double
 
@@ -58,6 +58,7 @@ SIGNATURES = {
     "mgb_ens_max_members": (_i32, []),
     "mgb_ens_minmax": (_i32, [_vp, _vp, _i32, _i64, _vp, _vp, _vp]),
     "mgb_ens_depth_reduce": (_i32, [_vp, _vp, _vp, _i32, _i64, _i32, _i32, _i32, _vp, _vp, _vp, _vp]),
+    "mgb_ens_iid": (_i32, [_vp, _vp, _i32, _i64, _i32, _vp, _vp, _vp]),
     "mgb_ens_normals": (_i32, [_vp, _vp, _i32, _i64, _i32, _vp, _vp, _vp, _vp]),
     "mgb_workspace_bytes": (C.c_size_t, [_vp, _i32, _i32, _i32]),
     "mgb_launch_count": (_i64, []),
@@ -71,6 +72,15 @@ SIGNATURES = {
     "mgb_op_space_to_depth": (_i32, [_vp, _vp, _i32, _i32, _i32, _i32, _vp]),
     "mgb_op_upsample2x": (_i32, [_vp, _vp, _i32, _i32, _i32, _i32, _vp]),
 }
+
+
+def _stale() -> bool:
+    try:
+        t = _LIB_PATH.stat().st_mtime
+        srcs = list((_PKG / "csrc").glob("*.cu")) + list((_PKG / "csrc").glob("*.h")) + list((_PKG / "csrc").glob("*.cuh"))
+        return any(p.stat().st_mtime > t for p in srcs)
+    except OSError:
+        return False
 
 
 def lib_path() -> Path:
@@ -88,6 +98,18 @@ def load(build_if_missing: bool = True):
         from . import build as _build
 
         _build.build()
+    elif _stale():
+        # sources newer than the library (a checkout moved on). Not rebuilt implicitly: several ranks may be starting at
+        # once and file times do not survive every copy; MGB_REBUILD_STALE=1 opts in.
+        if os.environ.get("MGB_REBUILD_STALE") == "1" and build_if_missing:
+            from . import build as _build
+
+            _build.build()
+        else:
+            import warnings
+
+            warnings.warn(f"{_LIB_PATH.name} is older than its sources under csrc/; run `python -m marigold_b200.build`",
+                          RuntimeWarning, stacklevel=2)
     lib = C.CDLL(str(_LIB_PATH), mode=os.RTLD_GLOBAL if hasattr(os, "RTLD_GLOBAL") else C.DEFAULT_MODE)
     for name, (res, args) in SIGNATURES.items():
         try:

@@ -104,6 +104,27 @@ def write_safetensors(path, tensors: Dict[str, torch.Tensor], metadata: Optional
             f.write(b)
 
 
+_LEGACY_ATTN = {"query": "to_q", "key": "to_k", "value": "to_v", "proj_attn": "to_out.0"}
+
+
+def _modernise_keys(sd: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+    """SD-era VAE checkpoints name the mid-block attention projections query / key / value / proj_attn (sometimes as
+    1x1 convolutions); diffusers renames them on load (`_convert_deprecated_attention_blocks`). Do the same here."""
+    out = {}
+    for k, v in sd.items():
+        parts = k.split(".")
+        if "attentions" in parts and len(parts) >= 2 and parts[-2] in _LEGACY_ATTN:
+            parts[-2] = _LEGACY_ATTN[parts[-2]]
+            k = ".".join(parts)
+            if parts[-1] == "weight" and v.dim() == 4 and v.shape[-2:] == (1, 1):
+                v = v.reshape(v.shape[0], v.shape[1])
+        elif "attentions" in parts and parts[-1] == "weight" and v.dim() == 4 and v.shape[-2:] == (1, 1) and \
+                any(p.startswith("to_") for p in parts):
+            v = v.reshape(v.shape[0], v.shape[1])
+        out[k] = v
+    return out
+
+
 def read_weights(component_dir, variant: Optional[str] = None) -> Dict[str, torch.Tensor]:
     """diffusers' file naming: diffusion_pytorch_model[.<variant>].safetensors, else the .bin pickle."""
     d = Path(component_dir)
@@ -111,11 +132,11 @@ def read_weights(component_dir, variant: Optional[str] = None) -> Dict[str, torc
     for stem in stems:
         p = d / f"{stem}.safetensors"
         if p.is_file():
-            return read_safetensors(p)
+            return _modernise_keys(read_safetensors(p))
     for stem in stems:
         p = d / f"{stem}.bin"
         if p.is_file():
-            return torch.load(p, map_location="cpu", weights_only=True)
+            return _modernise_keys(torch.load(p, map_location="cpu", weights_only=True))
     raise CheckpointError(f"no diffusion_pytorch_model[.{variant or '<variant>'}].safetensors|.bin under {d}")
 
 
@@ -170,13 +191,29 @@ _SCHED_KEYS = ("num_train_timesteps", "beta_start", "beta_end", "beta_schedule",
                "rescale_betas_zero_snr", "set_alpha_to_one", "steps_offset", "original_inference_steps", "timestep_scaling")
 
 
+_DIFFUSERS_SCHED_DEFAULTS = {
+    "DDIMScheduler": dict(num_train_timesteps=1000, beta_start=0.0001, beta_end=0.02, beta_schedule="linear",
+                          clip_sample=True, set_alpha_to_one=True, steps_offset=0, prediction_type="epsilon",
+                          thresholding=False, timestep_spacing="leading", rescale_betas_zero_snr=False),
+    "LCMScheduler": dict(num_train_timesteps=1000, beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear",
+                         original_inference_steps=50, clip_sample=False, set_alpha_to_one=True, steps_offset=0,
+                         prediction_type="epsilon", thresholding=False, timestep_spacing="leading", timestep_scaling=10.0,
+                         rescale_betas_zero_snr=False),
+}
+
+
 def scheduler_from_config(cfg: dict):
     """scheduler/scheduler_config.json -> host scheduler mirror (marigold_depth_pipeline.py:340-379 accepts exactly
     these two classes)."""
     name = cfg.get("_class_name", "DDIMScheduler")
+    # keys a config omits take DIFFUSERS' constructor defaults (not Marigold's values), as from_pretrained would
+    d = dict(_DIFFUSERS_SCHED_DEFAULTS.get(name, {}))
+    d.update(cfg)
+    cfg = d
     kw = {k: cfg[k] for k in _SCHED_KEYS if k in cfg}
     if cfg.get("clip_sample", False) or cfg.get("thresholding", False):
-        raise CheckpointError("clip_sample / thresholding schedulers are not supported (Marigold ships them disabled)")
+        raise CheckpointError("clip_sample / thresholding schedulers are not supported (Marigold ships them disabled; a "
+                              "config that omits `clip_sample` means diffusers' default, True)")
     if name == "DDIMScheduler":
         kw.pop("original_inference_steps", None)
         kw.pop("timestep_scaling", None)
@@ -189,7 +226,7 @@ def scheduler_from_config(cfg: dict):
 # -------------------------------------------------------------------------------------------------
 # empty-prompt embedding
 # -------------------------------------------------------------------------------------------------
-def empty_text_embedding(root, cross_dim: int) -> torch.Tensor:
+def empty_text_embedding(root, cross_dim: int, variant: Optional[str] = None) -> torch.Tensor:
     """[1, 2, cross_dim] fp32: CLIP hidden states of the empty prompt with padding="do_not_pad" (BOS, EOS)."""
     root = Path(root)
     for name in ("empty_text_embed.safetensors", "empty_text_embed.pt", "empty_text_embed.npy"):
@@ -213,7 +250,11 @@ def empty_text_embedding(root, cross_dim: int) -> torch.Tensor:
             raise CheckpointError(f"transformers is needed to encode the empty prompt ({e}); or provide "
                                   f"{root}/empty_text_embed.safetensors") from None
         tok = CLIPTokenizer.from_pretrained(str(root / "tokenizer"))
-        enc = CLIPTextModel.from_pretrained(str(root / "text_encoder")).eval()
+        try:
+            enc = CLIPTextModel.from_pretrained(str(root / "text_encoder"), variant=variant).eval()
+        except Exception:  # noqa: BLE001  (no weights of that variant: fall back to the default file names)
+            enc = CLIPTextModel.from_pretrained(str(root / "text_encoder")).eval()
+        enc = enc.float()
         ids = tok("", padding="do_not_pad", max_length=tok.model_max_length, truncation=True, return_tensors="pt").input_ids
         with torch.no_grad():
             t = enc(ids)[0].float()
@@ -238,7 +279,7 @@ def inspect_checkpoint(root, variant: Optional[str] = None) -> dict:
         "root": root, "variant": variant, "index": index, "unet_cfg": unet_cfg, "vae_cfg": vae_cfg,
         "engine_config": engine_config_from_diffusers(unet_cfg, vae_cfg), "scheduler": scheduler_from_config(sched_cfg),
         "defaults": {k: index.get(k) for k in ("default_denoising_steps", "default_processing_resolution",
-                                                "scale_invariant", "shift_invariant") if k in index},
+                                                "scale_invariant", "shift_invariant", "target_properties") if k in index},
     }
 
 
@@ -250,7 +291,7 @@ def load_pipeline(cls, root, variant: Optional[str] = None, torch_dtype=None, de
     info = inspect_checkpoint(root, variant)
     cfg = info["engine_config"]
     unet_sd, vae_sd = read_weights(info["root"] / "unet", variant), read_weights(info["root"] / "vae", variant)
-    text = empty_text_embedding(info["root"], cfg.unet_cross_dim)
+    text = empty_text_embedding(info["root"], cfg.unet_cross_dim, variant)
     eng = Engine(cfg, device=device)
     eng.load_state_dict("unet", unet_sd)
     eng.load_state_dict("vae", vae_sd)

@@ -121,6 +121,14 @@ int mgb_ens_depth_reduce(mgb_handle* h, const float* depth, const double* param,
   return rc;
 }
 
+int mgb_ens_iid(mgb_handle* h, const float* targets, int32_t E, int64_t N, int32_t median, float* pred, float* unc,
+                void* stream) {
+  if (!h || !targets || !pred || N <= 0) { set_error("ens_iid: bad argument"); return MGB_ERR_INVALID; }
+  int rc = launch_ens_iid(targets, E, N, median, pred, unc, reinterpret_cast<cudaStream_t>(stream));
+  if (!rc) count_launch(1);
+  return rc;
+}
+
 int mgb_ens_normals(mgb_handle* h, const float* normals, int32_t E, int64_t HW, int32_t closest, float* out,
                     float* unc, int32_t* member_idx, void* stream) {
   if (!h || !normals || !out || HW <= 0) { set_error("ens_normals: bad argument"); return MGB_ERR_INVALID; }

@@ -229,8 +229,12 @@ int mgb_create(const mgb_config* cfg, mgb_handle** out) {
       return MGB_ERR_INVALID;
     }
   }
-  if (cfg->unet_in_channels != 8 || cfg->unet_out_channels != 4 || cfg->vae_latent_channels != 4) {
-    set_error("mgb_create: only in=8 (rgb|target latents), out=4, latent=4 are supported");
+  // depth / normals: in 8 = rgb(4) | target(4), out 4. IID with n targets (marigold_iid_pipeline.py:467-585,
+  // src/trainer/marigold_iid_trainer.py:203-246): in 4 (n + 1), out 4 n; the scheduler epilogue handles <= 16 columns
+  if (cfg->vae_latent_channels != 4 || cfg->unet_out_channels < 4 || cfg->unet_out_channels % 4 || cfg->unet_out_channels > 16 ||
+      cfg->unet_in_channels != 4 + cfg->unet_out_channels) {
+    set_error("mgb_create: need latent=4, out=4n (n <= 4), in=4+out (got in=%d out=%d latent=%d)", cfg->unet_in_channels,
+              cfg->unet_out_channels, cfg->vae_latent_channels);
     return MGB_ERR_UNSUPPORTED;
   }
   if (cfg->norm_groups <= 0 || cfg->unet_cross_dim <= 0 || cfg->unet_layers_per_block <= 0 ||
@@ -556,23 +560,23 @@ static int run_graph(mgb_handle* h, Ctx& c, int op, const float* a0, float* a1, 
   if (op == OP_ENCODE) return vae_encode_forward(h, c, a0, a1, NB, d0, d1);
   if (op == OP_DECODE) return vae_decode_forward(h, c, a0, a1, NB, d0, d1, mode);
   // UNET single step through NCHW <-> NHWC conversions
-  const int HW = d0 * d1;
-  const size_t n = size_t(NB) * HW * 4;
-  float* rgb = reinterpret_cast<float*>(c.arena->alloc(n * 4));
+  const int HW = d0 * d1, Ct = h->cfg.unet_out_channels;
+  const size_t n = size_t(NB) * HW * Ct;
+  float* rgb = reinterpret_cast<float*>(c.arena->alloc(size_t(NB) * HW * 4 * 4));
   float* tgt = reinterpret_cast<float*>(c.arena->alloc(n * 4));
   float* nz = reinterpret_cast<float*>(c.arena->alloc(n * 4));
   float* raw = reinterpret_cast<float*>(c.arena->alloc(n * 4));
   if (!c.dry) {
     TRY(launch_nchw_to_nhwc(a0, rgb, NB, 4, HW, 1.f, c.stream));
-    TRY(launch_nchw_to_nhwc(a1, tgt, NB, 4, HW, 1.f, c.stream));
+    TRY(launch_nchw_to_nhwc(a1, tgt, NB, Ct, HW, 1.f, c.stream));
     count_launch(2);
-    if (a2) { TRY(launch_nchw_to_nhwc(a2, nz, NB, 4, HW, 1.f, c.stream)); count_launch(1); }
+    if (a2) { TRY(launch_nchw_to_nhwc(a2, nz, NB, Ct, HW, 1.f, c.stream)); count_launch(1); }
   }
   TRY(unet_forward(h, c, rgb, tgt, a2 ? nz : nullptr, a3 ? raw : nullptr, step, NB, d0, d1));
   if (!c.dry) {
-    TRY(launch_nhwc_to_nchw(tgt, a1, NB, 4, HW, 1.f, c.stream));
+    TRY(launch_nhwc_to_nchw(tgt, a1, NB, Ct, HW, 1.f, c.stream));
     count_launch(1);
-    if (a3) { TRY(launch_nhwc_to_nchw(raw, a3, NB, 4, HW, 1.f, c.stream)); count_launch(1); }
+    if (a3) { TRY(launch_nhwc_to_nchw(raw, a3, NB, Ct, HW, 1.f, c.stream)); count_launch(1); }
   }
   return MGB_OK;
 }
@@ -644,16 +648,16 @@ int mgb_denoise_range(mgb_handle* h, const float* rgb_latent, float* target, con
     if (h->kz_host[i] != 0.f && !step_noise) { set_error("schedule step %d injects noise but step_noise is NULL", i); return MGB_ERR_INVALID; }
   TRY(ensure_workspace(h, OP_UNET, B, lh, lw));
   Ctx c = make_ctx(h, stream);
-  const int HW = lh * lw;
-  const size_t n = size_t(B) * HW * 4;
+  const int HW = lh * lw, Ct = h->cfg.unet_out_channels;
+  const size_t n = size_t(B) * HW * Ct;
   c.arena->off = 0;
-  float* rgb = reinterpret_cast<float*>(c.arena->alloc(n * 4));
+  float* rgb = reinterpret_cast<float*>(c.arena->alloc(size_t(B) * HW * 4 * 4));
   float* tgt = reinterpret_cast<float*>(c.arena->alloc(n * 4));
   float* nz = reinterpret_cast<float*>(c.arena->alloc(n * 4));
   (void)c.arena->alloc(n * 4);
   const size_t base = c.arena->mark();
   TRY(launch_nchw_to_nhwc(rgb_latent, rgb, B, 4, HW, 1.f, c.stream));
-  TRY(launch_nchw_to_nhwc(target, tgt, B, 4, HW, 1.f, c.stream));
+  TRY(launch_nchw_to_nhwc(target, tgt, B, Ct, HW, 1.f, c.stream));
   count_launch(2);
   const bool any_noise = step_noise != nullptr;
   if (!any_noise) CUDA_TRY(cudaMemsetAsync(nz, 0, n * 4, c.stream));   // kz * 0 must stay finite
@@ -662,7 +666,7 @@ int mgb_denoise_range(mgb_handle* h, const float* rgb_latent, float* target, con
   mgb_handle::StepGraph& G = h->step_graph;
   for (int i = first_step; i < first_step + num_steps; ++i) {
     if (h->kz_host[i] != 0.f) {
-      TRY(launch_nchw_to_nhwc(step_noise + size_t(i) * n, nz, B, 4, HW, 1.f, c.stream));
+      TRY(launch_nchw_to_nhwc(step_noise + size_t(i) * n, nz, B, Ct, HW, 1.f, c.stream));
       count_launch(1);
     }
     const bool graph_ok = graphs && G.exec && G.NB == B && G.lh == lh && G.lw == lw &&
@@ -704,7 +708,7 @@ int mgb_denoise_range(mgb_handle* h, const float* rgb_latent, float* target, con
       }
     }
   }
-  TRY(launch_nhwc_to_nchw(tgt, target, B, 4, HW, 1.f, c.stream));
+  TRY(launch_nhwc_to_nchw(tgt, target, B, Ct, HW, 1.f, c.stream));
   count_launch(1);
   if (h->arena.overflow) { set_error("arena overflow"); return MGB_ERR_NOMEM; }
   return MGB_OK;
@@ -719,7 +723,7 @@ int mgb_denoise(mgb_handle* h, const float* rgb_latent, float* target, const flo
 int mgb_decode(mgb_handle* h, const float* latent, int32_t B, int32_t lh, int32_t lw, int32_t mode, float* out,
                void* stream) {
   TRY(check_ready(h, false));
-  if (!latent || !out || B <= 0 || lh <= 0 || lw <= 0 || mode < 0 || mode > 2) {
+  if (!latent || !out || B <= 0 || lh <= 0 || lw <= 0 || mode < 0 || mode > 3) {
     set_error("mgb_decode: bad argument (latent %d x %d, mode %d)", lh, lw, mode);
     return MGB_ERR_INVALID;
   }

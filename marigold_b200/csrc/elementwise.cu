@@ -115,26 +115,30 @@ int launch_cast_bf16(const float* x, bf16* y, size_t n, cudaStream_t stream) {
   MGB_LAUNCH_CHECK("cast_bf16");
 }
 
-// UNet conv_in operand (reference marigold_depth_pipeline.py:456-458: rgb latent FIRST):
-// out bf16 [M, 64] = [rgb(4) | target(4) | 0 x 56]
+// UNet conv_in operand (reference marigold_depth_pipeline.py:456-458, marigold_iid_pipeline.py:538-540: rgb latent FIRST):
+// out bf16 [M, 64] = [rgb(4) | target(Ct) | zeros], Ct = 4 (depth / normals) or 4 n (IID with n targets), 4 + Ct <= 64
 __global__ void pack_latents_kernel(const float4* __restrict__ rgb, const float4* __restrict__ tgt,
-                                    uint4* __restrict__ out, int M) {
+                                    uint2* __restrict__ out, int M, int Qt) {
   pdl_launch_dependents();
   pdl_wait();
-  const int total = M * 8;  // 8 x 16 B per 64-channel row
+  const int total = M * 16;  // 16 x 8 B (4 bf16) per 64-channel row
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-    const int m = i >> 3, part = i & 7;
-    uint4 o = make_uint4(0, 0, 0, 0);
+    const int m = i >> 4, part = i & 15;
+    uint2 o = make_uint2(0, 0);
     if (part == 0) {
-      const float4 a = __ldg(rgb + m), b = __ldg(tgt + m);
-      o = make_uint4(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w), pack_bf16x2(b.x, b.y), pack_bf16x2(b.z, b.w));
+      const float4 a = __ldg(rgb + m);
+      o = make_uint2(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w));
+    } else if (part <= Qt) {
+      const float4 b = __ldg(tgt + (size_t)m * Qt + (part - 1));
+      o = make_uint2(pack_bf16x2(b.x, b.y), pack_bf16x2(b.z, b.w));
     }
     out[i] = o;
   }
 }
-int launch_pack_latents(const float* rgb, const float* tgt, bf16* out, int M, cudaStream_t stream) {
-  launch_k(pack_latents_kernel, grid_for(size_t(M) * 8, 256), 256, 0, stream, reinterpret_cast<const float4*>(rgb),
-           reinterpret_cast<const float4*>(tgt), reinterpret_cast<uint4*>(out), M);
+int launch_pack_latents(const float* rgb, const float* tgt, bf16* out, int M, int Ct, cudaStream_t stream) {
+  if (Ct < 4 || (Ct & 3) || 4 + Ct > 64) { set_error("pack_latents: target channels %d", Ct); return MGB_ERR_INVALID; }
+  launch_k(pack_latents_kernel, grid_for(size_t(M) * 16, 256), 256, 0, stream, reinterpret_cast<const float4*>(rgb),
+           reinterpret_cast<const float4*>(tgt), reinterpret_cast<uint2*>(out), M, Ct / 4);
   MGB_LAUNCH_CHECK("pack_latents");
 }
 

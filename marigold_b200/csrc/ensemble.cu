@@ -531,6 +531,44 @@ int launch_ens_depth_reduce(const float* depth, const float* st_host, int E, lon
   return MGB_OK;
 }
 
+// ---- ensemble_iid (ensemble.py:252-270): per element, plain median (+ MAD) or mean (+ unbiased std) over E ------------
+__global__ void __launch_bounds__(kEnsThreads)
+    ens_iid_kernel(const float* __restrict__ x, int E, long long N, int median, float* __restrict__ pred,
+                   float* __restrict__ unc) {
+  float a[kEnsDynMaxE], dv[kEnsDynMaxE];
+  for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < N; p += (long long)gridDim.x * blockDim.x) {
+    for (int e = 0; e < E; ++e) a[e] = __ldg(x + (long long)e * N + p);
+    float pr, u = 0.f;
+    if (median) {
+      pr = select_lower_median(a, E, nullptr);            // torch.median: lower median for even E
+      if (unc) {
+        for (int e = 0; e < E; ++e) dv[e] = fabsf(a[e] - pr);
+        u = select_lower_median(dv, E, nullptr);
+      }
+    } else {
+      float sm = 0.f;
+      for (int e = 0; e < E; ++e) sm += a[e];
+      pr = sm / float(E);
+      if (unc) {
+        float q = 0.f;
+        for (int e = 0; e < E; ++e) { const float d = a[e] - pr; q += d * d; }
+        u = sqrtf(q / float(E - 1));
+      }
+    }
+    pred[p] = pr;
+    if (unc) unc[p] = u;
+  }
+}
+
+int launch_ens_iid(const float* x, int E, long long N, int median, float* pred, float* unc, cudaStream_t stream) {
+  if (E < 1 || E > kEnsDynMaxE) { set_error("ensemble size %d outside [1, %d]", E, kEnsDynMaxE); return MGB_ERR_UNSUPPORTED; }
+  const int blocks = int(std::min<long long>((N + kEnsThreads - 1) / kEnsThreads, kEnsMaxBlocks * 4));
+  ens_iid_kernel<<<blocks, kEnsThreads, 0, stream>>>(x, E, N, median, pred, unc);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { set_error("ens iid: %s", cudaGetErrorString(e)); return MGB_ERR_CUDA; }
+  return MGB_OK;
+}
+
 // ---- ensemble_normals -------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kEnsThreads)
     ens_normals_kernel(const float* __restrict__ nrm, int E, long long HW, int closest, float* __restrict__ out,

@@ -137,7 +137,10 @@ __device__ __forceinline__ void epilogue_special(const GemmEpilogue& e, const Ro
     return;
   }
   if (e.flags & EPI_NCHW) {
-    for (int c = 0; c < N; ++c) e.out_f32[(img * N + c) * e.hw + pix] = v[c];
+    // EPI_UNIT: reference marigold_iid_pipeline.py:562-565 (clip to [-1, 1], shift to [0, 1])
+    const bool unit = (e.flags & EPI_UNIT) != 0;
+    for (int c = 0; c < N; ++c)
+      e.out_f32[(img * N + c) * e.hw + pix] = unit ? (fminf(fmaxf(v[c], -1.0f), 1.0f) + 1.0f) / 2.0f : v[c];
     return;
   }
 }

@@ -28,6 +28,7 @@ enum : int {
   EPI_NCHW = 16,        // out_f32 written as NCHW planes [img, c, h*w] (needs hw)
   EPI_SILU = 32,        // out = silu(acc + bias)
   EPI_SCALE = 64,       // acc *= scale before bias (used for attention-score GEMMs)
+  EPI_UNIT = 128,       // with EPI_NCHW: out = (clip(v, -1, 1) + 1) / 2                     (IID decode head)
 };
 
 struct GemmEpilogue {
@@ -125,8 +126,8 @@ int launch_upsample2x(const float* x, bf16* y, int NB, int H, int W, int C, int 
 int launch_concat(const float* a, const float* b, float* out, int M, int Ca, int Cb, cudaStream_t stream);
 // fp32 -> bf16 cast
 int launch_cast_bf16(const float* x, bf16* y, size_t n, cudaStream_t stream);
-// UNet conv_in operand: [rgb(4) | target(4) | zeros(56)] bf16 NHWC-64 from two fp32 NHWC-4 latents
-int launch_pack_latents(const float* rgb, const float* tgt, bf16* out, int M, cudaStream_t stream);
+// UNet conv_in operand: [rgb(4) | target(Ct) | zeros] bf16 NHWC-64 from the fp32 NHWC latents (Ct = 4, or 4 n for IID)
+int launch_pack_latents(const float* rgb, const float* tgt, bf16* out, int M, int Ct, cudaStream_t stream);
 // NCHW fp32 <-> NHWC fp32 (small tensors at the ABI)
 int launch_nchw_to_nhwc(const float* x, float* y, int NB, int C, int HW, float scale, cudaStream_t stream);
 int launch_nhwc_to_nchw(const float* x, float* y, int NB, int C, int HW, float scale, cudaStream_t stream);
@@ -165,6 +166,8 @@ int launch_ens_minmax(const float* depth, int E, long long HW, float* ws, float*
                       cudaStream_t stream);
 int launch_ens_depth_reduce(const float* depth, const float* st_host, int E, long long HW, int shift, int median,
                             int use_min, float* pred, float* unc, int* idx, void* ws, cudaStream_t stream);
+// ensemble_iid: x [E, N] -> pred [N] (median | mean), unc [N] or null (MAD | unbiased std)
+int launch_ens_iid(const float* x, int E, long long N, int median, float* pred, float* unc, cudaStream_t stream);
 int launch_ens_normals(const float* nrm, int E, long long HW, int closest, float* out, float* unc, int* idx,
                        cudaStream_t stream);
 

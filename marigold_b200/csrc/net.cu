@@ -265,8 +265,9 @@ static int vae_attn_forward(Ctx& c, const VaeAttnW& A, Act& x, Act& y, int NB, i
 }
 
 // ---------------------------------------------------------------------------------------------
-// UNet step. rgb / tgt: fp32 NHWC [NB, lh, lw, 4]. tgt is updated in place by the fused
-// conv_out + scheduler epilogue. raw_out (or null): fp32 NHWC [NB, lh, lw, 4] model output.
+// UNet step. rgb: fp32 NHWC [NB, lh, lw, 4]; tgt: fp32 NHWC [NB, lh, lw, Ct] (Ct = unet_out_channels: 4, or 4 n for the
+// n-target IID models), updated in place by the fused conv_out + scheduler epilogue. raw_out (or null): fp32 NHWC
+// [NB, lh, lw, Ct] model output.
 // ---------------------------------------------------------------------------------------------
 static int zero_counters(Ctx& c) {
   // one memset (a memset node under capture) for the grid-barrier counters of every GroupNorm of this forward
@@ -301,7 +302,7 @@ int unet_forward(mgb_handle* hd, Ctx& c, const float* rgb, float* tgt, const flo
                             hd->step_counter, step, c.stream), 1);
   c.cur_bias = hd->cur_bias;
   bf16* x0 = aalloc<bf16>(c, M * 64);
-  LAUNCH(launch_pack_latents(rgb, tgt, x0, int(M), c.stream), 1);
+  LAUNCH(launch_pack_latents(rgb, tgt, x0, int(M), cfg.unet_out_channels, c.stream), 1);
   Act h = act_alloc(c, M, ch[0]);
   {
     Epi e; e.bias = U.conv_in.b; e.out_f32 = h.p;
@@ -494,7 +495,8 @@ int vae_decode_forward(mgb_handle* hd, Ctx& c, const float* latent, float* out, 
   TRY(groupnorm(c, h, nullptr, t, nullptr, V.dec_norm_out, NB, H * W, 1e-6f, 1));
   {
     Epi e; e.bias = V.dec_out.b; e.out_f32 = out;
-    e.flags = mode == MGB_DECODE_DEPTH ? EPI_DEPTH : mode == MGB_DECODE_NORMALS ? EPI_NORMALS : EPI_NCHW;
+    e.flags = mode == MGB_DECODE_DEPTH ? EPI_DEPTH : mode == MGB_DECODE_NORMALS ? EPI_NORMALS
+              : mode == MGB_DECODE_UNIT3 ? (EPI_NCHW | EPI_UNIT) : EPI_NCHW;
     TRY(conv3x3(c, t, NB, H, W, V.dec_out, 0, e));
   }
   c.arena->release(mk0);

@@ -153,8 +153,10 @@ class Engine:
                                              num_steps, B, lh, lw, stream_ptr()), "mgb_denoise_range")
 
     def decode(self, latent, mode: int) -> torch.Tensor:
+        """mode: 0 depth head [B,1,H,W], 1 normals head, 2 raw RGB, 3 (clip + 1) / 2 (one IID target); latent [B,4,h,w]."""
         latent = self._f32(latent)
-        B, _, lh, lw = latent.shape
+        B, c, lh, lw = latent.shape
+        assert c == 4, f"the VAE decodes 4-channel latents, got {c}"
         ch = 1 if mode == 0 else 3
         out = torch.empty(B, ch, lh * 8, lw * 8, dtype=torch.float32, device=self.device)
         with torch.cuda.device(self.device):

@@ -1,5 +1,5 @@
-"""Drop-in `ensemble_depth` / `ensemble_normals` (reference marigold/util/ensemble.py:39-196, 199-249)
-backed by the CUDA kernels in csrc/ensemble.cu.
+"""Drop-in `ensemble_depth` / `ensemble_normals` / `ensemble_iid` (reference marigold/util/ensemble.py:39-196, 199-249,
+252-270) backed by the CUDA kernels in csrc/ensemble.cu.
 
 Same signatures, defaults, error behaviour and return shapes as the reference. The scipy BFGS driver
 stays on the host exactly as in the reference (ensemble.py:165-171); what changes is the objective:
@@ -194,3 +194,30 @@ def ensemble_normals(
     if return_aux:
         return out, unc, {"member_idx": idx}
     return out, unc
+
+
+def ensemble_iid(
+    targets: torch.Tensor,
+    output_uncertainty: bool = False,
+    reduction: str = "median",
+    engine=None,
+) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+    """reference ensemble.py:252-270: per-element (lower) median + MAD, or mean + unbiased std, over the members;
+    no alignment and no renormalisation. targets [E, 3n, H, W] -> ([1, 3n, H, W], uncertainty or None)."""
+    if reduction not in ("mean", "median"):
+        raise ValueError(f"Unrecognized reduction method: {reduction}.")
+    if not targets.is_cuda:
+        raise _lib.MgbError("marigold_b200.ensemble_iid needs a CUDA tensor (no CPU fallback)")
+    eng = _handle(engine)
+    E = targets.shape[0]
+    with torch.cuda.device(targets.device):
+        x = targets.to(torch.float32).contiguous()
+        n = x[0].numel()
+        pred = torch.empty((1,) + tuple(x.shape[1:]), dtype=torch.float32, device=x.device)
+        unc = torch.empty_like(pred) if output_uncertainty else None
+        check(eng.lib.mgb_ens_iid(eng._h, ptr(x), E, n, 1 if reduction == "median" else 0, ptr(pred), ptr(unc),
+                                  stream_ptr()), "mgb_ens_iid")
+    pred = pred.to(targets.dtype)
+    if unc is not None:
+        unc = unc.to(targets.dtype)
+    return pred, unc

@@ -3,8 +3,8 @@
 Mirrors `IIDEntry` / `MarigoldIIDOutput` of the reference (marigold/marigold_iid_pipeline.py:59-160): per target a
 [3,H,W] array in [0,1], an 8-bit visualisation that depends on the target's `prediction_space` ("srgb" and "stack" as
 is; "linear" gamma-encoded with 1/2.2 after an optional rescale to the maximum), and the ensembling uncertainty.
-The pipeline class that fills it needs the engine to accept 4*(n+1) / 4*n latent channels; that is round-2 work
-(DESIGN.md §7), the checker side already exists (oracle.pipeline.OracleIIDPipeline, oracle.ensemble.ensemble_iid).
+Filled by `marigold_b200.pipeline.MarigoldIIDPipeline` (engine with 4 (n + 1) / 4 n latent channels, per-target
+decode, `ensemble_iid`); checker side: oracle.pipeline.OracleIIDPipeline, oracle.ensemble.ensemble_iid.
 """
 from __future__ import annotations
 

@@ -21,7 +21,7 @@ import torch.nn.functional as F
 
 from . import _lib
 from .engine import Engine
-from .ensemble import ensemble_depth, ensemble_normals
+from .ensemble import ensemble_depth, ensemble_iid, ensemble_normals
 from .schedulers import DDIMScheduler, LCMScheduler
 
 try:  # PIL is optional at run time (tensor inputs work without it)
@@ -53,7 +53,7 @@ def get_tv_resample_method(method_str: str) -> str:
     """reference image_util.py:123-134 (returns an interpolate mode string instead of a torchvision enum)."""
     m = _RESAMPLE.get(method_str)
     if m is None:
-        raise ValueError(f"Unknown resampling method: {m}")
+        raise ValueError(f"Unknown resampling method: {method_str}")
     return m
 
 
@@ -81,16 +81,49 @@ _SPECTRAL11 = np.array([
     [230, 245, 152], [171, 221, 164], [102, 194, 165], [50, 136, 189], [94, 79, 162]], dtype=np.float64) / 255.0
 
 
-def colorize_depth_maps(depth: np.ndarray, min_depth: float, max_depth: float, cmap: str = "Spectral") -> np.ndarray:
-    """reference image_util.py:38-76 for the default colour map; returns [3,H,W] float in [0,1]."""
-    if cmap != "Spectral":
-        raise ValueError(f"Only the 'Spectral' colour map is built in (got {cmap!r})")
-    d = (np.asarray(depth, dtype=np.float64) - min_depth) / (max_depth - min_depth)
-    x = np.clip(d, 0, 1) * 10.0
+def _spectral_lut() -> np.ndarray:
+    """matplotlib's 256-entry lookup table of "Spectral" (LinearSegmentedColormap over the 11 evenly spaced ColorBrewer
+    anchors, `_create_lookup_table(256, ...)`): LUT[i] = piecewise-linear interpolation at i / 255."""
+    x = np.arange(256, dtype=np.float64) / 255.0 * 10.0
     i0 = np.clip(np.floor(x).astype(np.int64), 0, 9)
-    w = (x - i0)[..., None]
-    rgb = _SPECTRAL11[i0] * (1 - w) + _SPECTRAL11[i0 + 1] * w
-    return np.moveaxis(rgb, -1, 0)
+    w = (x - i0)[:, None]
+    return np.clip(_SPECTRAL11[i0] * (1 - w) + _SPECTRAL11[i0 + 1] * w, 0.0, 1.0)
+
+
+_SPECTRAL_LUT = _spectral_lut()
+
+
+def colorize_depth_maps(depth, min_depth: float, max_depth: float, cmap: str = "Spectral", valid_mask=None) -> np.ndarray:
+    """reference image_util.py:38-76. Returns [(B,) 3, H, W] float in [0,1]. "Spectral" (the pipeline default) is built
+    in with matplotlib's exact semantics — `cm(x)` indexes a 256-entry table with int(x * 256) (x == 1 -> 255) — any other
+    matplotlib colour map is looked up through matplotlib when it is installed."""
+    depth = np.asarray(depth.detach().cpu().numpy() if isinstance(depth, torch.Tensor) else depth).squeeze()
+    assert depth.ndim >= 2, "Invalid dimension"
+    if depth.ndim < 3:
+        depth = depth[np.newaxis]
+    d = ((depth - min_depth) / (max_depth - min_depth)).clip(0, 1)
+    if cmap == "Spectral":
+        idx = np.minimum((d * 256).astype(np.int64), 255)
+        rgb = _SPECTRAL_LUT[idx]                                          # [B, H, W, 3]
+    else:
+        try:
+            import matplotlib
+        except Exception:  # noqa: BLE001
+            raise ValueError(f"colour map {cmap!r} needs matplotlib (only 'Spectral' is built in)") from None
+        rgb = matplotlib.colormaps[cmap](d, bytes=False)[..., 0:3]
+    out = np.moveaxis(rgb, -1, 1)                                         # [B, 3, H, W]
+    if valid_mask is not None:
+        vm = np.asarray(valid_mask.detach().cpu().numpy() if isinstance(valid_mask, torch.Tensor) else valid_mask).squeeze()
+        vm = vm[np.newaxis, np.newaxis] if vm.ndim < 3 else vm[:, np.newaxis]
+        out = out.copy()
+        out[~np.repeat(vm, 3, axis=1)] = 0
+    return out
+
+
+def _check_ensemble_size(engine, ensemble_size: int) -> None:
+    mx = int(engine.lib.mgb_ens_max_members())
+    if ensemble_size > mx:
+        raise ValueError(f"ensemble_size={ensemble_size} exceeds the {mx} members the ensembling kernels accept")
 
 
 def find_batch_size(ensemble_size: int, input_res: int, dtype: torch.dtype) -> int:
@@ -179,13 +212,14 @@ class _MarigoldBase:
         need_sn = is_lcm and denoising_steps > 1
         rank, G = parallel.world()
         mine = parallel.member_indices(ensemble_size, rank, G)
+        ct = self.engine.cfg.unet_out_channels               # 4, or 4 n for an n-target IID model
         if G > 1:
             # every rank draws (or receives) the FULL noise tensors and takes its rows, so member k's noise
             # does not depend on the partitioning
-            noise = self._draw_noise((ensemble_size, 4, lh, lw), generator, noise)
+            noise = self._draw_noise((ensemble_size, ct, lh, lw), generator, noise)
             if need_sn and step_noise is None:
                 dev = generator.device if generator is not None else self.device
-                step_noise = torch.randn((denoising_steps - 1, ensemble_size, 4, lh, lw), device=dev, dtype=self.dtype,
+                step_noise = torch.randn((denoising_steps - 1, ensemble_size, ct, lh, lw), device=dev, dtype=self.dtype,
                                          generator=generator)
         _bs = batch_size if batch_size > 0 else find_batch_size(len(mine), max(rgb_norm.shape[1:]), self.dtype)
         preds = []
@@ -195,18 +229,25 @@ class _MarigoldBase:
             if G > 1 or noise is not None:
                 z0 = noise[ids].to(self.device, torch.float32).contiguous()
             else:
-                z0 = self._draw_noise((nb, 4, lh, lw), generator, None)
+                z0 = self._draw_noise((nb, ct, lh, lw), generator, None)
             sn = None
             if need_sn:
                 if step_noise is not None:
                     sn = step_noise[:, ids].to(self.device, torch.float32).contiguous()
                 else:
+                    # one randn per step, in step order after z0: the draw sequence of scheduler.step(generator=...)
+                    # inside the reference loop (depth_pipeline.py:466-468), so a seeded generator gives the same stream
                     dev = generator.device if generator is not None else self.device
-                    sn = torch.randn((denoising_steps - 1, nb, 4, lh, lw), device=dev, dtype=self.dtype,
-                                     generator=generator).to(self.device)
+                    sn = torch.stack([torch.randn((nb, ct, lh, lw), device=dev, dtype=self.dtype, generator=generator)
+                                      for _ in range(denoising_steps - 1)]).to(self.device)
             target = self.engine.denoise(rgb_latent1.expand(nb, -1, -1, -1).contiguous(), z0, sn)
-            preds.append(self.engine.decode(target, decode_mode))
-        ch = 1 if decode_mode == 0 else 3
+            if decode_mode == _lib_decode_iid:
+                # marigold_iid_pipeline.py:568-585: one VAE decode per 4-channel target slice, concatenated along channels
+                preds.append(torch.cat([self.engine.decode(target[:, 4 * i:4 * i + 4].contiguous(), _lib_decode_iid)
+                                        for i in range(ct // 4)], dim=1))
+            else:
+                preds.append(self.engine.decode(target, decode_mode))
+        ch = 1 if decode_mode == 0 else (3 * (ct // 4) if decode_mode == _lib_decode_iid else 3)
         local = torch.concat(preds, dim=0) if preds else torch.empty((0, ch, lh * 8, lw * 8), device=self.device)
         return parallel.gather_members(local, ensemble_size)
 
@@ -255,6 +296,7 @@ class MarigoldDepthPipeline(_MarigoldBase):
             processing_res = self.default_processing_resolution
         assert processing_res >= 0
         assert ensemble_size >= 1
+        _check_ensemble_size(self.engine, ensemble_size)          # fail before any inference work is spent
         self._check_inference_step(denoising_steps)
         resample = get_tv_resample_method(resample_method)
         rgb_norm, input_size = self._preprocess(input_image, processing_res, resample)
@@ -275,7 +317,7 @@ class MarigoldDepthPipeline(_MarigoldBase):
         final_pred = final_pred.clip(0, 1)
         depth_colored_img = None
         if color_map is not None:
-            col = (colorize_depth_maps(final_pred, 0, 1, cmap=color_map).squeeze() * 255).astype(np.uint8)
+            col = (colorize_depth_maps(final_pred, 0, 1, cmap=color_map).squeeze() * 255).astype(np.uint8)  # :326-331
             hwc = np.moveaxis(col, 0, -1)
             depth_colored_img = Image.fromarray(hwc) if Image is not None else hwc
         return MarigoldDepthOutput(depth_np=final_pred, depth_colored=depth_colored_img, uncertainty=pred_uncert)
@@ -331,5 +373,71 @@ class MarigoldNormalsPipeline(_MarigoldBase):
         return MarigoldNormalsOutput(normals_np=final_pred, normals_img=normals_img, uncertainty=pred_uncert)
 
 
-_lib_decode_depth, _lib_decode_normals = 0, 1   # mgb_decode_mode
+class MarigoldIIDPipeline(_MarigoldBase):
+    """Intrinsic image decomposition with an arbitrary number of 3-channel targets (reference
+    marigold/marigold_iid_pipeline.py:164-585): ONE UNet whose conv_in takes 4 (n + 1) latent channels and whose
+    conv_out produces 4 n; every target's 4-channel latent is decoded separately; E > 1 goes through `ensemble_iid`."""
+
+    def __init__(self, engine, scheduler, empty_text_embed, target_properties: Optional[Dict] = None,
+                 default_denoising_steps: Optional[int] = None, default_processing_resolution: Optional[int] = None):
+        super().__init__(engine, scheduler, empty_text_embed, default_denoising_steps, default_processing_resolution)
+        self.target_properties = target_properties
+        self.target_names = target_properties["target_names"]          # :228-229 (KeyError / TypeError like the reference)
+        self.n_targets = len(self.target_names)
+        if engine.cfg.unet_out_channels != 4 * self.n_targets:
+            raise ValueError(f"the UNet predicts {engine.cfg.unet_out_channels} latent channels, but target_names "
+                             f"{self.target_names} needs {4 * self.n_targets}")
+
+    def _check_inference_step(self, n_step: int) -> None:
+        """marigold_iid_pipeline.py:413-448: LCM is refused."""
+        assert n_step >= 1
+        if isinstance(self.scheduler, DDIMScheduler):
+            if "trailing" != self.scheduler.config.timestep_spacing:
+                logging.warning(f'The loaded `DDIMScheduler` is configured with `timestep_spacing="'
+                                f'{self.scheduler.config.timestep_spacing}"`; the recommended setting is `"trailing"`.')
+            elif n_step > 10:
+                logging.warning(f"Setting too many denoising steps ({n_step}) may degrade the prediction; consider "
+                                f"relying on the default values.")
+            if not self.scheduler.config.rescale_betas_zero_snr:
+                logging.warning("The loaded `DDIMScheduler` is configured with `rescale_betas_zero_snr=False`; the "
+                                "recommended setting is True.")
+        elif isinstance(self.scheduler, LCMScheduler):
+            raise RuntimeError("This pipeline implementation does not support the LCMScheduler. Please refer to the "
+                               "project README.md for instructions about using LCM.")
+        else:
+            raise RuntimeError(f"Unsupported scheduler type: {type(self.scheduler)}")
+
+    @torch.no_grad()
+    def __call__(self, input_image, denoising_steps: Optional[int] = None, ensemble_size: int = 1,
+                 processing_res: Optional[int] = None, match_input_res: bool = True,
+                 resample_method: str = "bilinear", batch_size: int = 0,
+                 generator: Union[torch.Generator, None] = None, show_progress_bar: bool = True,
+                 ensemble_kwargs: Dict = None, *, noise: Optional[torch.Tensor] = None):
+        from .iid import MarigoldIIDOutput, fill_outputs
+
+        if denoising_steps is None:
+            denoising_steps = self.default_denoising_steps
+        if processing_res is None:
+            processing_res = self.default_processing_resolution
+        assert processing_res >= 0
+        assert ensemble_size >= 1
+        self._check_inference_step(denoising_steps)
+        resample = get_tv_resample_method(resample_method)
+        rgb_norm, input_size = self._preprocess(input_image, processing_res, resample)
+        target_preds = self._infer_members(rgb_norm, ensemble_size, denoising_steps, batch_size, generator, noise,
+                                           None, _lib_decode_iid)
+        assert target_preds.dim() == 4 and target_preds.shape[1] == 3 * self.n_targets      # :367-370
+        if ensemble_size > 1:
+            final_pred, pred_uncert = ensemble_iid(target_preds, engine=self.engine, **(ensemble_kwargs or {}))
+        else:
+            final_pred, pred_uncert = target_preds, None
+        if match_input_res:
+            final_pred = _resize(final_pred, tuple(input_size[-2:]), resample)      # (:386-392; uncertainty is NOT resized)
+        output = MarigoldIIDOutput(target_names=self.target_names)
+        fill_outputs(output, final_pred, pred_uncert, self.target_names, self.target_properties)
+        assert output.is_complete
+        return output
+
+
+_lib_decode_depth, _lib_decode_normals, _lib_decode_iid = 0, 1, 3   # mgb_decode_mode
 MarigoldPipeline = MarigoldDepthPipeline         # alias, reference marigold/__init__.py:41

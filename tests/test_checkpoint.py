@@ -116,6 +116,13 @@ def test_unsupported_architectures_and_schedulers_are_refused(fake_checkpoint):
         ck.scheduler_from_config({**sched_cfg, "_class_name": "EulerDiscreteScheduler"})
     with pytest.raises(ck.CheckpointError):
         ck.scheduler_from_config({**sched_cfg, "clip_sample": True})
+    # a sparse scheduler config means DIFFUSERS' defaults (clip_sample=True -> refused; epsilon / leading / alpha_to_one),
+    # never Marigold's values silently
+    with pytest.raises(ck.CheckpointError):
+        ck.scheduler_from_config({"_class_name": "DDIMScheduler"})
+    sparse = ck.scheduler_from_config({"_class_name": "DDIMScheduler", "clip_sample": False})
+    assert (sparse.config.prediction_type, sparse.config.timestep_spacing, sparse.config.set_alpha_to_one,
+            sparse.config.rescale_betas_zero_snr, sparse.config.beta_schedule) == ("epsilon", "leading", True, False, "linear")
     with pytest.raises(ck.CheckpointError, match="not found"):
         ck.inspect_checkpoint(root / "missing")
     with pytest.raises(ck.CheckpointError):
@@ -149,3 +156,24 @@ def test_from_pretrained_matches_engine_built_from_state_dicts(fake_checkpoint):
     assert nout.normals_np.shape == (3, 64, 64) and np.isfinite(nout.normals_np).all()
     for p in (pipe, pipe16, npipe, ref_pipe):
         p.engine.close()
+
+
+def test_legacy_vae_attention_keys_are_renamed(tmp_path):
+    """SD-era VAE files: mid_block.attentions.0.{query,key,value,proj_attn}, sometimes stored as 1x1 convolutions
+    (diffusers converts them on load)."""
+    sd = {"encoder.mid_block.attentions.0.query.weight": torch.randn(8, 8, 1, 1),
+          "encoder.mid_block.attentions.0.query.bias": torch.randn(8),
+          "encoder.mid_block.attentions.0.proj_attn.weight": torch.randn(8, 8),
+          "decoder.mid_block.attentions.0.to_k.weight": torch.randn(8, 8, 1, 1),
+          "encoder.conv_in.weight": torch.randn(8, 3, 3, 3)}
+    (tmp_path / "vae").mkdir()
+    ck.write_safetensors(tmp_path / "vae" / "diffusion_pytorch_model.safetensors", sd)
+    out = ck.read_weights(tmp_path / "vae")
+    assert set(out) == {"encoder.mid_block.attentions.0.to_q.weight", "encoder.mid_block.attentions.0.to_q.bias",
+                        "encoder.mid_block.attentions.0.to_out.0.weight", "decoder.mid_block.attentions.0.to_k.weight",
+                        "encoder.conv_in.weight"}
+    assert out["encoder.mid_block.attentions.0.to_q.weight"].shape == (8, 8)
+    assert out["decoder.mid_block.attentions.0.to_k.weight"].shape == (8, 8)
+    assert torch.equal(out["encoder.mid_block.attentions.0.to_q.weight"],
+                       sd["encoder.mid_block.attentions.0.query.weight"].reshape(8, 8))
+    assert out["encoder.conv_in.weight"].shape == (8, 3, 3, 3)

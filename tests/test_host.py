@@ -116,9 +116,23 @@ def test_colorize_and_resize_helpers():
     from marigold_b200.pipeline import colorize_depth_maps, get_tv_resample_method, resize_max_res
 
     c = colorize_depth_maps(np.linspace(0, 1, 12).reshape(3, 4), 0, 1)
-    assert c.shape == (3, 3, 4) and c.min() >= 0 and c.max() <= 1
+    assert c.shape == (1, 3, 3, 4) and c.min() >= 0 and c.max() <= 1      # [B, 3, H, W] like image_util.py:38-76
+    c = c.squeeze()
     np.testing.assert_allclose(c[:, 0, 0], np.array([158, 1, 66]) / 255.0)
     np.testing.assert_allclose(c[:, 2, 3], np.array([94, 79, 162]) / 255.0)
+    # matplotlib semantics: cm(x) indexes a 256-entry table with int(x * 256); LUT[i] = interpolation at i / 255
+    from marigold_b200.pipeline import _SPECTRAL_LUT
+
+    assert _SPECTRAL_LUT.shape == (256, 3)
+    np.testing.assert_allclose(_SPECTRAL_LUT[51], np.array([244, 109, 67]) / 255.0, atol=1e-12)     # 51 / 255 = 0.2 = anchor 2
+    w = 127 / 25.5 - 4                                                                            # 127 / 255 lies between anchors 4, 5
+    np.testing.assert_allclose(_SPECTRAL_LUT[127], (np.array([254, 224, 139]) * (1 - w) + np.array([255, 255, 191]) * w) / 255.0,
+                               atol=1e-12)
+    x = np.array([[0.4999, 0.5, 0.50195, 0.50391]])                         # 127.97 -> 127, 128, 128.5 -> 128, 129.0 -> 129
+    idx = [127, 128, 128, 129]
+    np.testing.assert_array_equal(colorize_depth_maps(np.repeat(x, 2, 0), 0, 1).squeeze()[:, 0].T, _SPECTRAL_LUT[idx])
+    m = colorize_depth_maps(np.ones((2, 2)), 0, 1, valid_mask=np.array([[True, False], [True, True]])).squeeze()
+    assert (m[:, 0, 1] == 0).all() and (m[:, 0, 0] > 0).any()
     with pytest.raises(ValueError):
         get_tv_resample_method("lanczos")
     img = torch.randint(0, 256, (1, 3, 90, 130), dtype=torch.uint8)
