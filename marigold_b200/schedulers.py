@@ -22,11 +22,14 @@ class SchedulerOutput:
 
 
 def _alphas_cumprod(cfg) -> np.ndarray:
-    if cfg.beta_schedule != "scaled_linear":
+    # float32 like diffusers (torch.linspace(..., dtype=float32) [** 2]), then cumprod in float32
+    if cfg.beta_schedule == "scaled_linear":
+        betas = np.linspace(np.float32(cfg.beta_start) ** np.float32(0.5), np.float32(cfg.beta_end) ** np.float32(0.5),
+                            cfg.num_train_timesteps, dtype=np.float32) ** 2
+    elif cfg.beta_schedule == "linear":
+        betas = np.linspace(np.float32(cfg.beta_start), np.float32(cfg.beta_end), cfg.num_train_timesteps, dtype=np.float32)
+    else:
         raise RuntimeError(f"Unsupported beta_schedule: {cfg.beta_schedule}")
-    # float32 like diffusers (torch.linspace(..., dtype=float32) ** 2), then cumprod in float32
-    betas = np.linspace(np.float32(cfg.beta_start) ** np.float32(0.5), np.float32(cfg.beta_end) ** np.float32(0.5),
-                        cfg.num_train_timesteps, dtype=np.float32) ** 2
     if cfg.rescale_betas_zero_snr:
         ab_sqrt = np.sqrt(np.cumprod((1.0 - betas).astype(np.float32), dtype=np.float32))
         s0, sT = ab_sqrt[0].copy(), ab_sqrt[-1].copy()
