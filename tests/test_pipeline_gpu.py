@@ -125,7 +125,6 @@ def test_normals_pipeline_and_errors(setup):
     # (the ensembled map can legitimately differ at single pixels: "closest" picks ONE member per pixel and two
     # near-equidistant members swap under bf16 noise.) Channel order and sign are checked on every strong pixel of every
     # MEMBER, before the ensemble:
-    assert record("tiny/pipe_normals_p01_cos", np.quantile(cos, 0.01)) > 0.98
     rgb_norm, _ = pipe._preprocess(img, 128, "bilinear")
     members = pipe._infer_members(rgb_norm, 4, 2, 0, None, z0, None, 1).cpu().numpy()
     _, _, ref_members = ora(img, ensemble_size=4, noise=z0)

@@ -42,7 +42,7 @@ def rows_of(path):
 
 def num(d, u, key):
     v = d.get(key, "")
-    if v in ("", "n/a"):
+    if v in ("", "n/a", "no data") or not v.replace(",", "").replace(".", "").replace("-", "").replace("e", "").replace("+", "").isdigit():
         return None
     unit = u.get(key, "").split("/")[0]
     return float(v.replace(",", "")) * UNIT_SCALE.get(unit, 1)
