@@ -127,6 +127,13 @@ int mgb_ens_depth_cost(mgb_handle* h, const float* depth_dev, const double* para
 int mgb_ens_depth_cost_batch(mgb_handle* h, const float* depth_dev, const double* params_host, int32_t P, int32_t E,
                              int64_t HW, int32_t scale_invariant, int32_t shift_invariant, int32_t reduction_median,
                              double regularizer, double* costs_out_host, void* stream);
+/* One forward-difference gradient of that objective in a single pass (scipy approx_derivative as BFGS calls it,
+ * ensemble.py:165-171): base_host [n] is the current point, pert_host [n] the same vector with EVERY coordinate moved to
+ * its perturbed value x_i + h_i; costs_out_host [1 + n]: [0] = cost(base), [1 + i] = cost(base with coordinate i
+ * perturbed), each bit-identical to mgb_ens_depth_cost of that vector. n = 2E (or E when !shift); E <= 16. */
+int mgb_ens_depth_cost_fd(mgb_handle* h, const float* depth_dev, const double* base_host, const double* pert_host,
+                          int32_t E, int64_t HW, int32_t scale_invariant, int32_t shift_invariant,
+                          int32_t reduction_median, double regularizer, double* costs_out_host, void* stream);
 /* Largest ensemble size the ensembling entry points accept (sizes <= 16 run register-resident kernels). */
 int mgb_ens_max_members(void);
 /* init_param statistics (ensemble.py:91-105): per-member min and max. Synchronises. */

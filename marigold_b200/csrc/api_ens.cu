@@ -76,6 +76,28 @@ int mgb_ens_depth_cost_batch(mgb_handle* h, const float* depth, const double* pa
   return MGB_OK;
 }
 
+int mgb_ens_depth_cost_fd(mgb_handle* h, const float* depth, const double* base, const double* pert, int32_t E, int64_t HW,
+                          int32_t scale_inv, int32_t shift_inv, int32_t median, double reg, double* costs_out, void* stream) {
+  int rc = ens_prepare(h);
+  if (rc) return rc;
+  if (!depth || !base || !pert || !costs_out || HW <= 0) { set_error("ens_depth_cost_fd: bad argument"); return MGB_ERR_INVALID; }
+  if (E < 2 || E > 16) { set_error("ens_depth_cost_fd: ensemble size %d outside [2,16] (use mgb_ens_depth_cost_batch)", E); return MGB_ERR_UNSUPPORTED; }
+  CUDA_TRY(cudaStreamSynchronize(reinterpret_cast<cudaStream_t>(stream)));   // previous user of the staging area
+  float* st = pinned_st(h);
+  rc = make_st(base, E, scale_inv, shift_inv, st);
+  if (rc) return rc;
+  rc = make_st(pert, E, scale_inv, shift_inv, st + 2 * E);
+  if (rc) return rc;
+  int launches = 0;
+  rc = launch_ens_depth_cost_fd(depth, st, E, HW, shift_inv, median, reg, h->ens_ws, h->ens_pinned, &launches,
+                                reinterpret_cast<cudaStream_t>(stream));
+  if (rc) return rc;
+  count_launch(launches);
+  const int n = shift_inv ? 2 * E : E;
+  for (int i = 0; i <= n; ++i) costs_out[i] = h->ens_pinned[3 * i];
+  return MGB_OK;
+}
+
 int mgb_ens_depth_cost(mgb_handle* h, const float* depth, const double* param, int32_t E, int64_t HW,
                        int32_t scale_inv, int32_t shift_inv, int32_t median, double reg, double* cost_out,
                        void* stream) {

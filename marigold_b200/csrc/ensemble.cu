@@ -56,13 +56,37 @@ struct CostPartial {
   float pmin, pmax;
 };
 
+// Block-level reduction of one fp32 accumulator to a double (fixed order: xor tree inside a warp, warps in index order)
+__device__ __forceinline__ double block_sum_double(float v, double* sh /* [kEnsThreads / 32] */) {
+  double d = double(v);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = d;
+  __syncthreads();
+  double tot = 0.0;
+  if (threadIdx.x == 0)
+    for (int w = 0; w < kEnsThreads / 32; ++w) tot += sh[w];
+  __syncthreads();
+  return tot;   // valid in thread 0
+}
+__device__ __forceinline__ void block_minmax(float& pmin, float& pmax, float (*shf)[kEnsThreads / 32]) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    pmin = fminf(pmin, __shfl_xor_sync(0xffffffffu, pmin, o));
+    pmax = fmaxf(pmax, __shfl_xor_sync(0xffffffffu, pmax, o));
+  }
+  if ((threadIdx.x & 31) == 0) { shf[0][threadIdx.x >> 5] = pmin; shf[1][threadIdx.x >> 5] = pmax; }
+  __syncthreads();
+  if (threadIdx.x == 0)
+    for (int w = 1; w < kEnsThreads / 32; ++w) { pmin = fminf(pmin, shf[0][w]); pmax = fmaxf(pmax, shf[1][w]); }
+  __syncthreads();
+}
+
+// One block's share of the objective for ONE parameter set: E (E - 1) / 2 pair sums + min / max of the ensembled map.
 template <int E>
-__global__ void __launch_bounds__(kEnsThreads)
-    ens_cost_kernel(const float* __restrict__ depth, const float* __restrict__ st_all, long long HW, int shift, int median,
-                    CostPartial* __restrict__ partials_all) {
+__device__ __forceinline__ void cost_block(const float* __restrict__ depth, const float* __restrict__ st, long long HW,
+                                           int shift, int median, CostPartial* __restrict__ out) {
   constexpr int NP = E * (E - 1) / 2;
-  const float* st = st_all + size_t(blockIdx.y) * 2 * E;                 // this block row's parameter set
-  CostPartial* partials = partials_all + size_t(blockIdx.y) * gridDim.x;
   float s[E], t[E];
 #pragma unroll
   for (int e = 0; e < E; ++e) { s[e] = st[e]; t[e] = st[E + e]; }
@@ -99,63 +123,211 @@ __global__ void __launch_bounds__(kEnsThreads)
     pmin = fminf(pmin, pred);
     pmax = fmaxf(pmax, pred);
   }
-  // block reduction (double for the pair sums)
   __shared__ double sh[kEnsThreads / 32];
   __shared__ float shf[2][kEnsThreads / 32];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  CostPartial* out = partials + blockIdx.x;
 #pragma unroll 1
   for (int k = 0; k < NP; ++k) {
-    double v = double(acc[k]);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    if (lane == 0) sh[warp] = v;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      double tot = 0.0;
-      for (int w = 0; w < kEnsThreads / 32; ++w) tot += sh[w];
-      out->pair_sum[k] = tot;
-    }
-    __syncthreads();
+    const double tot = block_sum_double(acc[k], sh);
+    if (threadIdx.x == 0) out->pair_sum[k] = tot;
   }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    pmin = fminf(pmin, __shfl_xor_sync(0xffffffffu, pmin, o));
-    pmax = fmaxf(pmax, __shfl_xor_sync(0xffffffffu, pmax, o));
-  }
-  if (lane == 0) { shf[0][warp] = pmin; shf[1][warp] = pmax; }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    for (int w = 1; w < kEnsThreads / 32; ++w) { pmin = fminf(pmin, shf[0][w]); pmax = fmaxf(pmax, shf[1][w]); }
-    out->pmin = pmin; out->pmax = pmax;
-  }
+  block_minmax(pmin, pmax, shf);
+  if (threadIdx.x == 0) { out->pmin = pmin; out->pmax = pmax; }
 }
 
-__global__ void ens_cost_final_kernel(const CostPartial* __restrict__ partials_all, int nblocks, int E, long long HW,
-                                      double reg, double* __restrict__ out_all) {
-  // one block per parameter set; thread k owns pair k
+template <int E>
+__global__ void __launch_bounds__(kEnsThreads)
+    ens_cost_kernel(const float* __restrict__ depth, const float* __restrict__ st_all, long long HW, int shift, int median,
+                    CostPartial* __restrict__ partials_all) {
+  cost_block<E>(depth, st_all + size_t(blockIdx.y) * 2 * E, HW, shift, median,
+                partials_all + size_t(blockIdx.y) * gridDim.x + blockIdx.x);
+}
+
+// ---- one forward-difference gradient in ONE pass: the base point plus the n = 2E (or E) single-coordinate
+// perturbations scipy's approx_derivative evaluates. Perturbing member m only changes the E - 1 pairs (m, j) and moves
+// one element of the per-pixel order statistics, so block row m + 1 recomputes just those (the lower median of the
+// perturbed set is clamp(x', w[r*-1], w[r*]) with w = the sorted base values without member m): ~9x less arithmetic
+// than 2E + 1 independent evaluations. Every sum is formed exactly as cost_block forms it (same pixel-to-thread map, same
+// reduction order), and the final kernel assembles each perturbed objective from base + perturbed pair sums in pair
+// order, so the values equal ens_cost_kernel's bit for bit (tests/test_ensemble_gpu.py).
+struct FdPartial {
+  double pair_sum[2][kEnsMaxE];   // [s' | t'][other member j]
+  float pmin[2], pmax[2];
+};
+
+template <int E>
+__global__ void __launch_bounds__(kEnsThreads)
+    ens_cost_fd_kernel(const float* __restrict__ depth, const float* __restrict__ st /* [2E] base */,
+                       const float* __restrict__ pert /* [2E]: s'_0..s'_{E-1} | t'_0..t'_{E-1} */, long long HW, int shift,
+                       int median, CostPartial* __restrict__ base_part, FdPartial* __restrict__ fd_part) {
+  if (blockIdx.y == 0) {
+    cost_block<E>(depth, st, HW, shift, median, base_part + blockIdx.x);
+    return;
+  }
+  const int m = blockIdx.y - 1;
+  const int nk = shift ? 2 : 1;
+  float s[E], t[E];
+#pragma unroll
+  for (int e = 0; e < E; ++e) { s[e] = st[e]; t[e] = st[E + e]; }
+  const float sp = pert[m], tp = pert[E + m];
+  float acc0[E], acc1[E];
+#pragma unroll
+  for (int e = 0; e < E; ++e) { acc0[e] = 0.f; acc1[e] = 0.f; }
+  float mn0 = FLT_MAX, mx0 = -FLT_MAX, mn1 = FLT_MAX, mx1 = -FLT_MAX;
+  constexpr int R = (E - 1) / 2;   // rank of the lower median
+  for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < HW; p += (long long)gridDim.x * blockDim.x) {
+    float a[E];
+    float dm = 0.f;
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      const float d = __ldg(depth + (long long)e * HW + p);
+      a[e] = align1(d, s[e], t[e], shift);
+      if (e == m) dm = d;
+    }
+    float sm_base = 0.f;
+#pragma unroll
+    for (int e = 0; e < E; ++e) if (e == m) sm_base = s[e];
+    float tm_base = 0.f;
+#pragma unroll
+    for (int e = 0; e < E; ++e) if (e == m) tm_base = t[e];
+    const float x0 = align1(dm, sp, tm_base, shift);      // s_m perturbed
+    const float x1 = align1(dm, sm_base, tp, shift);      // t_m perturbed
+#pragma unroll
+    for (int j = 0; j < E; ++j) {
+      if (j != m) {
+        const float d0 = x0 - a[j], d1 = x1 - a[j];
+        acc0[j] = fmaf(d0, d0, acc0[j]);
+        acc1[j] = fmaf(d1, d1, acc1[j]);
+      }
+    }
+    float p0, p1;
+    if (median) {
+      float v[E];
+      int idx[E];
+#pragma unroll
+      for (int e = 0; e < E; ++e) { v[e] = a[e]; idx[e] = e; }
+      sort_small<E>(v, idx);
+      int r = 0;
+#pragma unroll
+      for (int e = 0; e < E; ++e) if (idx[e] == m) r = e;
+      // w = v without rank r; lo = w[R - 1] (-inf if R == 0), hi = w[R] (+inf if R == E - 1)
+      float lo = -FLT_MAX, hi = FLT_MAX;
+#pragma unroll
+      for (int e = 0; e < E; ++e) {
+        const int wi = e < r ? e : e - 1;            // index in w of v[e] (e != r)
+        if (e != r && wi == R - 1) lo = v[e];
+        if (e != r && wi == R) hi = v[e];
+      }
+      p0 = fminf(fmaxf(x0, lo), hi);
+      p1 = fminf(fmaxf(x1, lo), hi);
+    } else {
+      float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+      for (int e = 0; e < E; ++e) { s0 += (e == m ? x0 : a[e]); s1 += (e == m ? x1 : a[e]); }
+      p0 = s0 / float(E); p1 = s1 / float(E);
+    }
+    mn0 = fminf(mn0, p0); mx0 = fmaxf(mx0, p0);
+    mn1 = fminf(mn1, p1); mx1 = fmaxf(mx1, p1);
+  }
+  __shared__ double sh[kEnsThreads / 32];
+  __shared__ float shf[2][kEnsThreads / 32];
+  FdPartial* out = fd_part + size_t(m) * gridDim.x + blockIdx.x;
+#pragma unroll 1
+  for (int j = 0; j < E; ++j) {
+    float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+    for (int e = 0; e < E; ++e) if (e == j) { a0 = acc0[e]; a1 = acc1[e]; }
+    const double t0 = block_sum_double(a0, sh);
+    const double t1 = nk == 2 ? block_sum_double(a1, sh) : 0.0;
+    if (threadIdx.x == 0) { out->pair_sum[0][j] = t0; out->pair_sum[1][j] = t1; }
+  }
+  block_minmax(mn0, mx0, shf);
+  block_minmax(mn1, mx1, shf);
+  if (threadIdx.x == 0) { out->pmin[0] = mn0; out->pmax[0] = mx0; out->pmin[1] = mn1; out->pmax[1] = mx1; }
+}
+
+// Sum over the blocks' partials of one pair, one warp per call: lane l takes blocks l, l + 32, ...; xor tree. Both final
+// kernels use it, so a pair total has ONE value no matter which kernel produced the partials.
+template <typename F>
+__device__ __forceinline__ double warp_total(int nblocks, F&& get) {
+  double tot = 0.0;
+  for (int b = threadIdx.x & 31; b < nblocks; b += 32) tot += get(b);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+  return tot;
+}
+
+__global__ void __launch_bounds__(256) ens_cost_final_kernel(const CostPartial* __restrict__ partials_all, int nblocks, int E,
+                                                             long long HW, double reg, double* __restrict__ out_all) {
+  // one block per parameter set; one warp per pair (warps stride over the pairs)
   const CostPartial* partials = partials_all + size_t(blockIdx.x) * nblocks;
   double* out = out_all + 3 * blockIdx.x;
   const int NP = E * (E - 1) / 2;
-  __shared__ double sh[128];
-  double c = 0.0;
-  for (int k = threadIdx.x; k < NP; k += blockDim.x) {
-    double tot = 0.0;
-    for (int b = 0; b < nblocks; ++b) tot += partials[b].pair_sum[k];
+  __shared__ double c[kEnsMaxE * (kEnsMaxE - 1) / 2];
+  for (int k = threadIdx.x >> 5; k < NP; k += blockDim.x >> 5) {
+    const double tot = warp_total(nblocks, [&](int b) { return partials[b].pair_sum[k]; });
     // reference: (diff**2).mean().sqrt() evaluated in fp32
-    c += double(sqrtf(float(tot / double(HW))));
+    if ((threadIdx.x & 31) == 0) c[k] = double(sqrtf(float(tot / double(HW))));
   }
-  sh[threadIdx.x] = c;
   __syncthreads();
-  if (threadIdx.x == 0) {
-    double cost = 0.0;
-    for (int i = 0; i < int(blockDim.x); ++i) cost += sh[i];
+  if (threadIdx.x < 32) {
     float pmin = FLT_MAX, pmax = -FLT_MAX;
-    for (int b = 0; b < nblocks; ++b) { pmin = fminf(pmin, partials[b].pmin); pmax = fmaxf(pmax, partials[b].pmax); }
-    if (reg > 0.0) cost += (double(fabsf(0.0f - pmin)) + double(fabsf(1.0f - pmax))) * reg;
-    out[0] = cost;
-    out[1] = double(pmin);
-    out[2] = double(pmax);
+    for (int b = threadIdx.x; b < nblocks; b += 32) { pmin = fminf(pmin, partials[b].pmin); pmax = fmaxf(pmax, partials[b].pmax); }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      pmin = fminf(pmin, __shfl_xor_sync(0xffffffffu, pmin, o));
+      pmax = fmaxf(pmax, __shfl_xor_sync(0xffffffffu, pmax, o));
+    }
+    if (threadIdx.x == 0) {
+      double cost = 0.0;
+      for (int k = 0; k < NP; ++k) cost += c[k];          // pair order, like the reference's Python loop
+      if (reg > 0.0) cost += (double(fabsf(0.0f - pmin)) + double(fabsf(1.0f - pmax))) * reg;
+      out[0] = cost;
+      out[1] = double(pmin);
+      out[2] = double(pmax);
+    }
+  }
+}
+
+// set q: 0 = the base point; q >= 1: coordinate i = q - 1 perturbed (i < E: s_i, else t_{i-E})
+__global__ void __launch_bounds__(256) ens_cost_fd_final_kernel(const CostPartial* __restrict__ base_part,
+                                                                const FdPartial* __restrict__ fd_part, int nblocks, int E,
+                                                                long long HW, double reg, double* __restrict__ out_all) {
+  const int q = blockIdx.x;
+  const int m = q == 0 ? -1 : (q - 1) % E, kk = q == 0 ? 0 : (q - 1) / E;
+  const FdPartial* fp = q == 0 ? nullptr : fd_part + size_t(m) * nblocks;
+  double* out = out_all + 3 * q;
+  const int NP = E * (E - 1) / 2;
+  __shared__ double c[kEnsMaxE * (kEnsMaxE - 1) / 2];
+  for (int k = threadIdx.x >> 5; k < NP; k += blockDim.x >> 5) {
+    int i = 0, r = k;                                       // pair index -> (i, j), torch.combinations order
+    while (r >= E - 1 - i) { r -= E - 1 - i; ++i; }
+    const int j = i + 1 + r;
+    double tot;
+    if (i == m) tot = warp_total(nblocks, [&](int b) { return fp[b].pair_sum[kk][j]; });
+    else if (j == m) tot = warp_total(nblocks, [&](int b) { return fp[b].pair_sum[kk][i]; });
+    else tot = warp_total(nblocks, [&](int b) { return base_part[b].pair_sum[k]; });
+    if ((threadIdx.x & 31) == 0) c[k] = double(sqrtf(float(tot / double(HW))));
+  }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float pmin = FLT_MAX, pmax = -FLT_MAX;
+    for (int b = threadIdx.x; b < nblocks; b += 32) {
+      pmin = fminf(pmin, q == 0 ? base_part[b].pmin : fp[b].pmin[kk]);
+      pmax = fmaxf(pmax, q == 0 ? base_part[b].pmax : fp[b].pmax[kk]);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      pmin = fminf(pmin, __shfl_xor_sync(0xffffffffu, pmin, o));
+      pmax = fmaxf(pmax, __shfl_xor_sync(0xffffffffu, pmax, o));
+    }
+    if (threadIdx.x == 0) {
+      double cost = 0.0;
+      for (int k = 0; k < NP; ++k) cost += c[k];
+      if (reg > 0.0) cost += (double(fabsf(0.0f - pmin)) + double(fabsf(1.0f - pmax))) * reg;
+      out[0] = cost;
+      out[1] = double(pmin);
+      out[2] = double(pmax);
+    }
   }
 }
 
@@ -287,7 +459,8 @@ __global__ void ens_cost_dyn_final_kernel(const double* __restrict__ pair_part, 
 // ws layout: [partials: max(CostPartial x kEnsCostBlocks x (2 kEnsMaxE + 1), kDynPartialBytes + min/max)]
 //            [st: kEnsMaxP x 2 kEnsDynMaxE floats][out: kEnsMaxP x 3 doubles]
 static size_t ens_partial_bytes() {
-  const size_t t = sizeof(CostPartial) * kEnsCostBlocks * (2 * kEnsMaxE + 1);
+  const size_t t = std::max(sizeof(CostPartial) * kEnsCostBlocks * (2 * kEnsMaxE + 1),
+                            sizeof(CostPartial) * kEnsCostBlocks + sizeof(FdPartial) * kEnsCostBlocks * kEnsMaxE);
   const size_t d = kDynPartialBytes + size_t(kEnsMaxP) * kDynBlocks * 2 * sizeof(float);
   return ((t > d ? t : d) + 255) & ~size_t(255);
 }
@@ -319,7 +492,7 @@ int launch_ens_depth_cost(const float* depth, const float* st_host, int P, int E
       CASE(15) CASE(16)
 #undef CASE
     }
-    ens_cost_final_kernel<<<P, 128, 0, stream>>>(partials, blocks, E, HW, reg, out);
+    ens_cost_final_kernel<<<P, 256, 0, stream>>>(partials, blocks, E, HW, reg, out);
     *launches = 2;
   } else {
     const int NP = E * (E - 1) / 2, chunks = (NP + kDynPairs - 1) / kDynPairs;
@@ -339,6 +512,34 @@ int launch_ens_depth_cost(const float* depth, const float* st_host, int P, int E
   if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
   if (e == cudaSuccess) e = cudaGetLastError();
   if (e != cudaSuccess) { set_error("ens cost: %s", cudaGetErrorString(e)); return MGB_ERR_CUDA; }
+  return MGB_OK;
+}
+
+// st_host (pinned): float [4E] = base {s | t} then perturbed {s' | t'}; out_host_pinned: double [1 + n][3] with n = 2E
+// (shift) or E: set 0 = base, set 1 + i = coordinate i perturbed. One launch pair, one synchronisation.
+int launch_ens_depth_cost_fd(const float* depth, const float* st_host, int E, long long HW, int shift, int median,
+                             double reg, void* ws, double* out_host_pinned, int* launches, cudaStream_t stream) {
+  if (E < 2 || E > kEnsMaxE) { set_error("ens cost fd: ensemble size %d outside [2, %d]", E, kEnsMaxE); return MGB_ERR_UNSUPPORTED; }
+  float* st = ens_ws_st(ws);
+  double* out = ens_ws_out(ws);
+  cudaError_t e = cudaMemcpyAsync(st, st_host, sizeof(float) * 4 * E, cudaMemcpyHostToDevice, stream);
+  if (e != cudaSuccess) { set_error("ens cost fd H2D: %s", cudaGetErrorString(e)); return MGB_ERR_CUDA; }
+  CostPartial* base_part = reinterpret_cast<CostPartial*>(ws);
+  FdPartial* fd_part = reinterpret_cast<FdPartial*>(base_part + kEnsCostBlocks);
+  const int blocks = int(std::min<long long>((HW + kEnsThreads - 1) / kEnsThreads, kEnsCostBlocks));
+  const int n = shift ? 2 * E : E;
+  switch (E) {
+#define CASE(k) case k: ens_cost_fd_kernel<k><<<dim3(blocks, E + 1), kEnsThreads, 0, stream>>>(depth, st, st + 2 * E, HW, shift, median, base_part, fd_part); break;
+    CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8) CASE(9) CASE(10) CASE(11) CASE(12) CASE(13) CASE(14)
+    CASE(15) CASE(16)
+#undef CASE
+  }
+  ens_cost_fd_final_kernel<<<1 + n, 256, 0, stream>>>(base_part, fd_part, blocks, E, HW, reg, out);
+  *launches = 2;
+  e = cudaMemcpyAsync(out_host_pinned, out, size_t(1 + n) * 3 * sizeof(double), cudaMemcpyDeviceToHost, stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+  if (e == cudaSuccess) e = cudaGetLastError();
+  if (e != cudaSuccess) { set_error("ens cost fd: %s", cudaGetErrorString(e)); return MGB_ERR_CUDA; }
   return MGB_OK;
 }
 
@@ -445,12 +646,16 @@ __global__ void __launch_bounds__(kEnsThreads)
     ens_renorm_kernel(float* __restrict__ pred, float* __restrict__ unc, long long HW, const float* __restrict__ bmm,
                       int nblocks, int use_min) {
   __shared__ float s_min, s_rng;
-  if (threadIdx.x == 0) {
+  __shared__ float shf[2][kEnsThreads / 32];
+  {
     float mn = FLT_MAX, mx = -FLT_MAX;
-    for (int b = 0; b < nblocks; ++b) { mn = fminf(mn, bmm[2 * b]); mx = fmaxf(mx, bmm[2 * b + 1]); }
-    if (!use_min) mn = 0.f;                       // scale-only alignment: depth_min = 0 (ensemble.py:187-188)
-    s_min = mn;
-    s_rng = fmaxf(mx - mn, 1e-6f);                // .clamp(min=1e-6)
+    for (int b = threadIdx.x; b < nblocks; b += blockDim.x) { mn = fminf(mn, bmm[2 * b]); mx = fmaxf(mx, bmm[2 * b + 1]); }
+    block_minmax(mn, mx, shf);
+    if (threadIdx.x == 0) {
+      if (!use_min) mn = 0.f;                     // scale-only alignment: depth_min = 0 (ensemble.py:187-188)
+      s_min = mn;
+      s_rng = fmaxf(mx - mn, 1e-6f);              // .clamp(min=1e-6)
+    }
   }
   __syncthreads();
   const float mn = s_min, rng = s_rng;

@@ -45,7 +45,7 @@ def _resize_max_res_nearest_exact(img: torch.Tensor, max_edge: int) -> torch.Ten
 _EPS = float(np.sqrt(np.finfo(np.float64).eps))   # scipy.optimize._optimize._epsilon (BFGS default `eps`)
 
 
-def _fd_jac(cost_fn, cost_batch):
+def _fd_jac(cost_fn, cost_batch, cost_fd=None):
     """scipy's 2-point forward difference with an absolute step (approx_derivative as BFGS calls it with jac=None:
     `abs_step=eps`, f0 = f(x)) restated for scipy versions without the `workers=` hook; the 2E points are one batch."""
     def jac(x):
@@ -56,12 +56,15 @@ def _fd_jac(cost_fn, cost_batch):
         h = np.where(dx == 0, _EPS * sign * np.maximum(1.0, np.abs(x)), h)
         xs = np.repeat(x[None], x.size, 0)
         xs[np.arange(x.size), np.arange(x.size)] = x + h
-        f = cost_batch(np.concatenate([x[None], xs]))
-        return (f[1:] - f[0]) / ((x + h) - x)
+        f0 = cost_fn(x)
+        f = cost_fd(xs) if cost_fd is not None else None
+        if f is None:
+            f = cost_batch(xs)
+        return (f - f0) / ((x + h) - x)
     return jac
 
 
-def _bfgs(cost_fn, cost_batch, fd_map, param0, tol, max_iter):
+def _bfgs(cost_fn, cost_batch, fd_map, param0, tol, max_iter, cost_fd=None):
     """scipy.optimize.minimize(..., method="BFGS", tol=tol, options={"maxiter": max_iter}) exactly as the reference
     calls it (ensemble.py:165-171), with the finite-difference points evaluated as one device batch."""
     import scipy.optimize
@@ -71,7 +74,7 @@ def _bfgs(cost_fn, cost_batch, fd_map, param0, tol, max_iter):
     if ver >= (1, 16):
         res = scipy.optimize.minimize(cost_fn, param0, method="BFGS", tol=tol, options={**opts, "workers": fd_map})
     else:
-        res = scipy.optimize.minimize(cost_fn, param0, jac=_fd_jac(cost_fn, cost_batch), method="BFGS", tol=tol,
+        res = scipy.optimize.minimize(cost_fn, param0, jac=_fd_jac(cost_fn, cost_batch, cost_fd), method="BFGS", tol=tol,
                                       options=opts)
     return res.x, res.nit
 
@@ -143,13 +146,39 @@ def ensemble_depth(
         def cost_fn(param: np.ndarray) -> float:
             return float(cost_batch(param)[0])
 
+        def cost_fd(xs: np.ndarray) -> Optional[np.ndarray]:
+            """xs [n, n]: row i = a common base point with coordinate i perturbed (what scipy's 2-point scheme
+            evaluates). One structured pass on the device (`mgb_ens_depth_cost_fd`); None if xs is not of that form."""
+            n = xs.shape[1]
+            if E > 16 or xs.shape[0] != n or n < 2:
+                return None
+            base = xs[1].copy()
+            base[1] = xs[0][1]                                  # row 0 is unperturbed at coordinate 1
+            pert = np.ascontiguousarray(np.diagonal(xs))
+            chk = np.repeat(base[None], n, 0)
+            chk[np.arange(n), np.arange(n)] = pert
+            if not np.array_equal(chk, xs):
+                return None
+            out = np.empty(n + 1, dtype=np.float64)
+            check(lib.mgb_ens_depth_cost_fd(h, ptr(d_align), base.ctypes.data_as(C.c_void_p),
+                                            pert.ctypes.data_as(C.c_void_p), E, hw_a, sc, sh, median,
+                                            float(regularizer_strength), out.ctypes.data_as(C.c_void_p), stream_ptr()),
+                  "mgb_ens_depth_cost_fd")
+            n_eval[0] += n
+            n_eval[1] += 1
+            return out[1:]
+
         def fd_map(fun, xs):
             """scipy's finite-difference hook (`workers=`, scipy >= 1.16): all perturbed points in one call."""
-            return [np.atleast_1d(c) for c in cost_batch(list(xs))]
+            X = np.ascontiguousarray(np.asarray(list(xs), dtype=np.float64))
+            costs = cost_fd(X)
+            if costs is None:
+                costs = cost_batch(X)
+            return [np.atleast_1d(c) for c in costs]
 
         nit = 0
         if param is None:
-            param, nit = _bfgs(cost_fn, cost_batch, fd_map, param0, tol, max_iter)
+            param, nit = _bfgs(cost_fn, cost_batch, fd_map, param0, tol, max_iter, cost_fd)
         param = np.ascontiguousarray(param, dtype=np.float64)   # (tests may inject the alignment)
 
         pred = torch.empty(1, 1, H, W, dtype=torch.float32, device=depth.device)
@@ -162,7 +191,7 @@ def ensemble_depth(
         unc = unc.to(depth.dtype)
     if return_aux:
         return pred, unc, {"param": param, "param0": param0, "member_idx": idx, "nit": nit, "nfev": n_eval[0],
-                            "round_trips": n_eval[1], "cost_fn": cost_fn, "cost_batch": cost_batch}
+                            "round_trips": n_eval[1], "cost_fn": cost_fn, "cost_batch": cost_batch, "cost_fd": cost_fd}
     return pred, unc
 
 

@@ -159,6 +159,18 @@ def test_cost_batch_is_one_round_trip_and_bit_identical():
     batch = aux["cost_batch"](P)
     single = np.array([aux["cost_fn"](p) for p in P])
     np.testing.assert_array_equal(batch, single)
+    # the structured forward-difference pass (base + one perturbed coordinate per row) gives the same bits again
+    for red, shift in (("median", True), ("mean", True), ("median", False)):
+        kw = dict(reduction=red, shift_invariant=shift)
+        n = 2 * E if shift else E
+        b = p0[:n] + rng.normal(0, 1e-2, n)
+        _, _, ax = ensemble_depth(d, return_aux=True, param=b, **kw)
+        X = np.repeat(b[None], n, 0)
+        X[np.arange(n), np.arange(n)] += rng.choice([1.5e-8, 1e-3], n)
+        fd = ax["cost_fd"](X)
+        assert fd is not None
+        np.testing.assert_array_equal(fd, np.array([ax["cost_fn"](x) for x in X]))
+        assert ax["cost_fd"](X[::-1].copy()) is None               # not of the single-coordinate form: generic batch
     # end to end: round trips = objective calls + gradient calls, far fewer than evaluated points
     _, _, aux2 = ensemble_depth(d, return_aux=True)
     assert aux2["nfev"] >= aux2["round_trips"]
