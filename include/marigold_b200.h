@@ -154,6 +154,25 @@ int mgb_ens_normals(mgb_handle* h, const float* normals_dev, int32_t E, int64_t 
 int mgb_ens_iid(mgb_handle* h, const float* targets_dev, int32_t E, int64_t N, int32_t reduction_median, float* pred_dev,
                 float* uncert_dev, void* stream);
 
+/* ---- pre / post-processing bookends and the evaluation step ------------------------------------ */
+/* torchvision resize(antialias=True) as resize_max_res calls it (marigold/util/image_util.py:90-120) and for the final
+ * prediction (marigold_depth_pipeline.py:306-312). src_dev [NC,H,W] uint8 (src_is_u8) or fp32 -> dst_dev fp32 [NC,h,w].
+ * mode 0 bilinear, 1 bicubic (both antialiased), 2 nearest-exact. post 0: none; 1: round + clamp to [0,255] (a uint8
+ * image stays uint8-valued); 2: that, then x / 255 * 2 - 1 (marigold_depth_pipeline.py:252). tmp_dev: NC*H*w floats. */
+int mgb_resize(const void* src_dev, int32_t src_is_u8, int32_t NC, int32_t H, int32_t W, float* dst_dev, int32_t h, int32_t w,
+               int32_t mode, int32_t post, float* tmp_dev, void* stream);
+/* colorize_depth_maps + chw2hwc + uint8 (image_util.py:38-76, marigold_depth_pipeline.py:326-331): depth_dev fp32 [HW] ->
+ * out_hwc_dev uint8 [HW,3]; lut_dev uint8 [256,3] = the colour map's 256-entry table * 255, truncated. */
+int mgb_colorize(const float* depth_dev, int64_t HW, float dmin, float dmax, const uint8_t* lut_dev, uint8_t* out_hwc_dev,
+                 void* stream);
+/* Least-squares scale / shift alignment to the ground truth over the valid pixels (src/util/alignment.py:35-82), the
+ * clips of script/depth/eval.py:201-207 and the masked depth metrics of src/util/metric.py:64-191 in two passes and ONE
+ * synchronisation. mask_dev uint8 [HW] or NULL; aligned_out_dev fp32 [HW] or NULL; ws_dev: mgb_eval_ws_bytes() bytes.
+ * out_host[13] = {scale, shift, n_valid, abs_rel, sq_rel, rmse, rmse_log, log10, delta1, delta2, delta3, i_rmse, silog}. */
+size_t mgb_eval_ws_bytes(void);
+int mgb_eval_depth(const float* pred_dev, const float* gt_dev, const uint8_t* mask_dev, int64_t HW, int32_t least_squares,
+                   float dmin, float dmax, float* aligned_out_dev, void* ws_dev, double* out_host, void* stream);
+
 /* ---- capacity ------------------------------------------------------------------------------- */
 /* Bytes of the activation arena the handle holds for images of H x W with B members per batch. */
 size_t mgb_workspace_bytes(mgb_handle* h, int32_t B, int32_t H, int32_t W);

@@ -119,6 +119,37 @@ int mgb_op_layernorm(const float* x, void* y, const float* gamma, const float* b
   return rc;
 }
 
+/* ---- pre / post-processing and evaluation (image.cu, eval.cu) ---- */
+int mgb_resize(const void* src, int32_t src_is_u8, int32_t NC, int32_t H, int32_t W, float* dst, int32_t h, int32_t w,
+               int32_t mode, int32_t post, float* tmp, void* stream) {
+  if (!src || !dst || !tmp) { set_error("mgb_resize: null pointer"); return MGB_ERR_INVALID; }
+  int rc = launch_resize(src, src_is_u8, NC, H, W, dst, h, w, mode, post, tmp, reinterpret_cast<cudaStream_t>(stream));
+  if (!rc) count_launch(2);
+  return rc;
+}
+
+int mgb_colorize(const float* depth, int64_t HW, float dmin, float dmax, const uint8_t* lut, uint8_t* out_hwc, void* stream) {
+  int rc = launch_colorize(depth, HW, dmin, dmax, lut, out_hwc, reinterpret_cast<cudaStream_t>(stream));
+  if (!rc) count_launch(1);
+  return rc;
+}
+
+size_t mgb_eval_ws_bytes(void) { return eval_ws_bytes() + 16 * sizeof(double); }
+
+int mgb_eval_depth(const float* pred, const float* gt, const uint8_t* mask, int64_t HW, int32_t least_squares, float dmin,
+                   float dmax, float* aligned_out, void* ws, double* out_host, void* stream) {
+  if (!pred || !gt || !ws || !out_host || HW <= 0) { set_error("mgb_eval_depth: bad argument"); return MGB_ERR_INVALID; }
+  double* out_dev = reinterpret_cast<double*>(static_cast<char*>(ws) + eval_ws_bytes());
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  int rc = launch_eval_depth(pred, gt, mask, HW, least_squares, dmin, dmax, aligned_out, ws, out_dev, s);
+  if (rc) return rc;
+  count_launch(4);
+  cudaError_t e = cudaMemcpyAsync(out_host, out_dev, 13 * sizeof(double), cudaMemcpyDeviceToHost, s);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+  if (e != cudaSuccess) { set_error("mgb_eval_depth: %s", cudaGetErrorString(e)); return MGB_ERR_CUDA; }
+  return MGB_OK;
+}
+
 int mgb_op_space_to_depth(const float* x, void* y, int32_t NB, int32_t H, int32_t W, int32_t C, void* stream) {
   int rc = launch_space_to_depth(x, reinterpret_cast<bf16*>(y), NB, H, W, C, reinterpret_cast<cudaStream_t>(stream));
   if (!rc) count_launch(1);

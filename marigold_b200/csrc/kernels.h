@@ -153,6 +153,19 @@ int launch_softmax_rows(const float* s, bf16* p, int M, int n, int ld, cudaStrea
 int launch_transpose_bf16(const bf16* x, bf16* y, int M, int N, int ld, cudaStream_t stream);
 
 // ---------------------------------------------------------------------------------------------
+// Pre / post-processing bookends (image.cu) and the evaluation step (eval.cu)
+// ---------------------------------------------------------------------------------------------
+// src [NC, H, W] (u8 or f32) -> dst f32 [NC, h, w]; tmp: NC * H * w floats. mode 0 bilinear-aa, 1 bicubic-aa, 2 nearest-exact;
+// post 0 none, 1 round + clamp to [0, 255], 2 that and then x / 255 * 2 - 1
+int launch_resize(const void* src, int src_is_u8, int NC, int H, int W, float* dst, int h, int w, int mode, int post, float* tmp,
+                  cudaStream_t stream);
+int launch_colorize(const float* depth, long long HW, float dmin, float dmax, const uint8_t* lut, uint8_t* out,
+                    cudaStream_t stream);
+size_t eval_ws_bytes();
+int launch_eval_depth(const float* pred, const float* gt, const uint8_t* mask, long long HW, int do_align, float dmin, float dmax,
+                      float* aligned_out, void* ws, double* out_dev, cudaStream_t stream);
+
+// ---------------------------------------------------------------------------------------------
 // Ensemble kernels (ensemble.cu)
 // ---------------------------------------------------------------------------------------------
 size_t ens_ws_bytes();

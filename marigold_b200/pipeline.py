@@ -58,7 +58,14 @@ def get_tv_resample_method(method_str: str) -> str:
 
 
 def _resize(img: torch.Tensor, size, mode: str) -> torch.Tensor:
-    """torchvision.transforms.functional.resize(img, size, interpolation, antialias=True) semantics."""
+    """torchvision.transforms.functional.resize(img, size, interpolation, antialias=True) semantics. CUDA tensors (the
+    pipelines' path) go through the library's own kernels (csrc/image.cu); CPU tensors (host-side helpers in the tests)
+    through torch."""
+    if img.is_cuda:
+        from . import imageops
+
+        out = imageops.resize(img, size, mode, post=1 if img.dtype == torch.uint8 else 0)
+        return out.to(img.dtype)
     if mode == "nearest-exact":
         return F.interpolate(img.float(), size=size, mode=mode).to(img.dtype)
     out = F.interpolate(img.float(), size=size, mode=mode, antialias=True, align_corners=False)
@@ -179,9 +186,18 @@ class _MarigoldBase:
         input_size = rgb.shape
         assert 4 == rgb.dim() and 3 == input_size[-3], f"Wrong input shape {input_size}, expected [1, rgb, H, W]"
         rgb = rgb.to(self.device)
-        if processing_res > 0:
-            rgb = resize_max_res(rgb, max_edge_resolution=processing_res, resample_method=resample_method)
-        rgb_norm = (rgb / 255.0 * 2.0 - 1.0).to(self.dtype)
+        if processing_res > 0 and rgb.dtype == torch.uint8:
+            # resize_max_res (image_util.py:90-120) with the uint8 rounding and the [-1, 1] normalisation (:252-254) fused
+            # into the second pass of the device resize
+            from . import imageops
+
+            h0, w0 = rgb.shape[-2:]
+            f = min(processing_res / w0, processing_res / h0)
+            rgb_norm = imageops.resize(rgb, (int(h0 * f), int(w0 * f)), resample_method, post=2).to(self.dtype)
+        else:
+            if processing_res > 0:
+                rgb = resize_max_res(rgb, max_edge_resolution=processing_res, resample_method=resample_method)
+            rgb_norm = (rgb / 255.0 * 2.0 - 1.0).to(self.dtype)
         assert rgb_norm.min() >= -1.0 and rgb_norm.max() <= 1.0
         return rgb_norm, input_size
 
@@ -317,8 +333,14 @@ class MarigoldDepthPipeline(_MarigoldBase):
         final_pred = final_pred.clip(0, 1)
         depth_colored_img = None
         if color_map is not None:
-            col = (colorize_depth_maps(final_pred, 0, 1, cmap=color_map).squeeze() * 255).astype(np.uint8)  # :326-331
-            hwc = np.moveaxis(col, 0, -1)
+            if color_map == "Spectral":
+                from . import imageops
+
+                hwc = imageops.colorize_u8(torch.from_numpy(np.ascontiguousarray(final_pred)).to(self.device), 0, 1,
+                                           imageops.spectral_lut_u8()).cpu().numpy()            # :326-331 on the device
+            else:
+                col = (colorize_depth_maps(final_pred, 0, 1, cmap=color_map).squeeze() * 255).astype(np.uint8)
+                hwc = np.moveaxis(col, 0, -1)
             depth_colored_img = Image.fromarray(hwc) if Image is not None else hwc
         return MarigoldDepthOutput(depth_np=final_pred, depth_colored=depth_colored_img, uncertainty=pred_uncert)
 

@@ -19,13 +19,15 @@ raw.mgb_debug_gemm_timing.argtypes = [C.c_void_p]
 def run(M, N, K, bn, stages, out_dtype="f32", flags=0):
     a = torch.randn(M, K, device="cuda").to(torch.bfloat16)
     w = (torch.randn(N, K, device="cuda") / K ** 0.5).to(torch.bfloat16)
-    of = torch.empty(M, N, device="cuda") if out_dtype == "f32" else None
-    ob = torch.empty(M, N, device="cuda", dtype=torch.bfloat16) if out_dtype == "bf16" else None
+    n_out = N // 2 if flags & 1 else N
+    of = torch.empty(M, n_out, device="cuda") if out_dtype == "f32" else None
+    ob = torch.empty(M, n_out, device="cuda", dtype=torch.bfloat16) if out_dtype == "bf16" else None
+    bias = torch.randn(N, device="cuda")
     ctas = ((M + 127) // 128) * ((N + bn - 1) // bn)
     dbg = torch.zeros(ctas, 8, dtype=torch.int64, device="cuda")
 
     def fn():
-        check(lib.mgb_op_linear(ptr(a), ptr(w), None, None, ptr(of), ptr(ob), M, N, K, flags, bn, 1, stages, None, stream_ptr()), "lin")
+        check(lib.mgb_op_linear(ptr(a), ptr(w), ptr(bias), None, ptr(of), ptr(ob), M, N, K, flags, bn, 1, stages, None, stream_ptr()), "lin")
     for _ in range(3):
         fn()
     torch.cuda.synchronize()
@@ -51,3 +53,6 @@ if __name__ == "__main__":
     run(9216, 320, 320, 160, 5, "bf16")
     run(9216, 320, 2880, 160, 5)
     run(9216, 2560, 320, 256, 4, "bf16")
+    run(9216, 2560, 320, 256, 2, "bf16", flags=1)        # FF-in + GEGLU as the network launches it
+    run(9216, 960, 320, 256, 2, "bf16")                  # fused QKV
+    run(2304, 5120, 640, 256, 2, "bf16", flags=1)
