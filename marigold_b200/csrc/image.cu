@@ -51,16 +51,19 @@ __global__ void __launch_bounds__(256)
       const float center = scale * (o + 0.5f);
       const int xmin = max(int(center - support + 0.5f), 0);
       const int xsize = min(int(center + support + 0.5f), in_len) - xmin;
-      float total_w = 0.f, acc = 0.f;
+      // weights normalised first, then accumulated in tap order (the order torch's antialias kernels use)
+      float total_w = 0.f;
+      for (int j = 0; j < xsize; ++j) total_w += aa_filter((j + xmin - center + 0.5f) * invscale, mode == 1);
+      const float inv_total = total_w != 0.f ? 1.f / total_w : 0.f;
+      float acc = 0.f;
       for (int j = 0; j < xsize; ++j) {
-        const float w = aa_filter((j + xmin - center + 0.5f) * invscale, mode == 1);
-        total_w += w;
-        acc = fmaf(w, float(base[(xmin + j) * s_axis]), acc);
+        const float w = aa_filter((j + xmin - center + 0.5f) * invscale, mode == 1) * inv_total;
+        acc = fmaf(float(base[(xmin + j) * s_axis]), w, acc);
       }
-      v = total_w != 0.f ? acc / total_w : 0.f;
+      v = acc;
     }
     if (post >= 1) v = fminf(fmaxf(rintf(v), 0.f), 255.f);           // the resized image is uint8 in the reference
-    if (post == 2) v = v / 255.0f * 2.0f - 1.0f;                    // marigold_depth_pipeline.py:252
+    if (post == 2) v = __fsub_rn(__fmul_rn(__fdiv_rn(v, 255.0f), 2.0f), 1.0f);   // rgb / 255.0 * 2.0 - 1.0 (depth_pipeline.py:252), un-fused
     dst[i] = v;
   }
 }

@@ -45,22 +45,29 @@ def _resize_max_res_nearest_exact(img: torch.Tensor, max_edge: int) -> torch.Ten
 _EPS = float(np.sqrt(np.finfo(np.float64).eps))   # scipy.optimize._optimize._epsilon (BFGS default `eps`)
 
 
+def _scipy_fd_points(x: np.ndarray) -> np.ndarray:
+    """x + h with scipy's forward-difference step for BFGS(jac=None): approx_derivative(..., abs_step=eps): h = eps, or
+    eps * sign(x) * max(1, |x|) where x + eps == x."""
+    h = np.full_like(x, _EPS)
+    dx = (x + h) - x
+    sign = (x >= 0).astype(np.float64) * 2 - 1
+    h = np.where(dx == 0, _EPS * sign * np.maximum(1.0, np.abs(x)), h)
+    return x + h
+
+
 def _fd_jac(cost_fn, cost_batch, cost_fd=None):
     """scipy's 2-point forward difference with an absolute step (approx_derivative as BFGS calls it with jac=None:
     `abs_step=eps`, f0 = f(x)) restated for scipy versions without the `workers=` hook; the 2E points are one batch."""
     def jac(x):
         x = np.asarray(x, dtype=np.float64)
-        h = np.full_like(x, _EPS)
-        dx = (x + h) - x
-        sign = (x >= 0).astype(np.float64) * 2 - 1
-        h = np.where(dx == 0, _EPS * sign * np.maximum(1.0, np.abs(x)), h)
+        xp = _scipy_fd_points(x)
         xs = np.repeat(x[None], x.size, 0)
-        xs[np.arange(x.size), np.arange(x.size)] = x + h
+        xs[np.arange(x.size), np.arange(x.size)] = xp
         f0 = cost_fn(x)
         f = cost_fd(xs) if cost_fd is not None else None
         if f is None:
             f = cost_batch(xs)
-        return (f - f0) / ((x + h) - x)
+        return (f - f0) / (xp - x)
     return jac
 
 
@@ -92,6 +99,7 @@ def ensemble_depth(
     engine=None,
     return_aux: bool = False,
     param: Optional[np.ndarray] = None,
+    speculate: bool = True,
 ) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
     if depth.dim() != 4 or depth.shape[1] != 1:
         raise ValueError(f"Expecting 4D tensor of shape [B,1,H,W]; got {depth.shape}.")
@@ -143,8 +151,29 @@ def ensemble_depth(
             n_eval[1] += 1
             return out
 
+        spec = {"x": None, "pert": None, "costs": None}   # last speculative (f, forward-difference points) evaluation
+
+        def _fd_call(base: np.ndarray, pert: np.ndarray) -> np.ndarray:
+            out = np.empty(base.size + 1, dtype=np.float64)
+            check(lib.mgb_ens_depth_cost_fd(h, ptr(d_align), base.ctypes.data_as(C.c_void_p),
+                                            pert.ctypes.data_as(C.c_void_p), E, hw_a, sc, sh, median,
+                                            float(regularizer_strength), out.ctypes.data_as(C.c_void_p), stream_ptr()),
+                  "mgb_ens_depth_cost_fd")
+            n_eval[0] += base.size + 1
+            n_eval[1] += 1
+            return out
+
         def cost_fn(param: np.ndarray) -> float:
-            return float(cost_batch(param)[0])
+            """The objective at `param`. BFGS asks for the gradient at (almost) every point it evaluates, so the 2E
+            forward-difference points scipy will request next (x + h e_i with its default absolute step) ride along in
+            the same pass and the same synchronisation; `fd_map` serves them from here when the request matches."""
+            x = np.ascontiguousarray(param, dtype=np.float64)
+            if speculate and E <= 16 and x.size >= 2:
+                pert = _scipy_fd_points(x)
+                out = _fd_call(x, pert)
+                spec.update(x=x.copy(), pert=pert, costs=out[1:])
+                return float(out[0])
+            return float(cost_batch(x)[0])
 
         def cost_fd(xs: np.ndarray) -> Optional[np.ndarray]:
             """xs [n, n]: row i = a common base point with coordinate i perturbed (what scipy's 2-point scheme
@@ -159,14 +188,9 @@ def ensemble_depth(
             chk[np.arange(n), np.arange(n)] = pert
             if not np.array_equal(chk, xs):
                 return None
-            out = np.empty(n + 1, dtype=np.float64)
-            check(lib.mgb_ens_depth_cost_fd(h, ptr(d_align), base.ctypes.data_as(C.c_void_p),
-                                            pert.ctypes.data_as(C.c_void_p), E, hw_a, sc, sh, median,
-                                            float(regularizer_strength), out.ctypes.data_as(C.c_void_p), stream_ptr()),
-                  "mgb_ens_depth_cost_fd")
-            n_eval[0] += n
-            n_eval[1] += 1
-            return out[1:]
+            if spec["x"] is not None and np.array_equal(spec["x"], base) and np.array_equal(spec["pert"], pert):
+                return spec["costs"]                            # already evaluated together with f(base)
+            return _fd_call(base, pert)[1:]
 
         def fd_map(fun, xs):
             """scipy's finite-difference hook (`workers=`, scipy >= 1.16): all perturbed points in one call."""
