@@ -43,12 +43,10 @@ __host__ __device__ constexpr int a_stage_bytes() { return BLOCK_M * BLOCK_K * 2
 __host__ __device__ constexpr int b_stage_bytes(int block_n) { return block_n * BLOCK_K * 2; }
 __host__ __device__ constexpr int tmem_cols_for(int n) { return n <= 32 ? 32 : n <= 64 ? 64 : n <= 128 ? 128 : 256; }
 
-constexpr int kBarrierBytes = 256;   // full / empty / tmem / halo barriers + the TMEM base address
-constexpr int kBiasBytes = 1024;     // this tile's BLOCK_N bias values, staged while the K loop runs
 size_t gemm_smem_bytes(int block_n, int stages, int a_ring_bytes) {
-  // 1024 B alignment slack + A ring + B ring + barriers + bias staging
+  // 1024 B alignment slack + A ring + B ring + barriers
   const size_t a = a_ring_bytes >= 0 ? size_t(a_ring_bytes) : size_t(stages) * a_stage_bytes();
-  return 1024 + a + size_t(stages) * b_stage_bytes(block_n) + kBarrierBytes + kBiasBytes;
+  return 1024 + a + size_t(stages) * b_stage_bytes(block_n) + 256;
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -223,7 +221,6 @@ __global__ void __launch_bounds__(kGemmThreads, MINB) gemm_tc_kernel(const __gri
   uint64_t* a_full = tmem_full_bar + 1;     // mode 2: halo ring barriers (up to 4 slots)
   uint64_t* a_empty = a_full + 4;
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(a_empty + 4);
-  float* s_bias = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full_bar) + kBarrierBytes);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -436,20 +433,12 @@ __global__ void __launch_bounds__(kGemmThreads, MINB) gemm_tc_kernel(const __gri
     tg.mode = p.mode; tg.m_base = (long long)m_tile * BLOCK_M; tg.M = p.M;
     tg.img = img; tg.ty = ty; tg.tx = tx; tg.H = p.H; tg.W = p.W;
     tg.tile_w_shift = p.tile_w_shift; tg.tile_w_mask = p.tile_w - 1; tg.tile_h = p.tile_h;
-    const GemmEpilogue& e = p.epi;
-    const int n0 = n_tile * BLOCK_N;
-    if constexpr (BLOCK_N > 16) {
-      // Stage this tile's bias in shared memory while the K loop runs: read per chunk from global memory it cost one
-      // exposed L2 round trip (~700 cycles) per 32-column chunk (r02 phase stamps: 1550 cycles per chunk, 5.5 k per tile)
-      const float* bsrc = p.partial != nullptr ? nullptr : e.bias;
-      for (int i = threadIdx.x - 64; i < BLOCK_N; i += 32 * kEpiWarps)
-        s_bias[i] = (bsrc && n0 + i < p.N) ? __ldg(bsrc + n0 + i) : 0.f;
-      asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
-    }
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
     if (dbg && threadIdx.x == 64) dbg[3] = clock64();
     const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16);
+    const GemmEpilogue& e = p.epi;
+    const int n0 = n_tile * BLOCK_N;
 
     const int ehalf = (warp - 2) >> 2;   // which of the two warps of this lane quarter
     if constexpr (BLOCK_N == 16) {
@@ -494,6 +483,7 @@ __global__ void __launch_bounds__(kGemmThreads, MINB) gemm_tc_kernel(const __gri
       float* out_f32 = raw ? p.partial + (long long)split * p.M * p.N : e.out_f32;
       bf16* out_bf16 = raw ? nullptr : e.out_bf16;
       const float* residual = raw ? nullptr : e.residual;
+      const float* bias = raw ? nullptr : e.bias;
       const int ldo = raw ? p.N : e.ldo;
       const int n_out = geglu ? p.N / 2 : p.N;               // output columns
       const int half = BLOCK_N / 2;
@@ -534,9 +524,15 @@ __global__ void __launch_bounds__(kGemmThreads, MINB) gemm_tc_kernel(const __gri
         const int acc_col = n0 + j * 32 + c4;                                   // accumulator column (bias index)
         const int col = geglu ? n_tile * half + j * 32 + c4 : acc_col;          // output column
         const int nv = n_out - col;
-        // bias of this lane's 4 columns from the staged copy (zero beyond N and in raw split-K mode)
-        const float4 b4 = *reinterpret_cast<const float4*>(s_bias + j * 32 + c4);
-        const float4 g4 = geglu ? *reinterpret_cast<const float4*>(s_bias + half + j * 32 + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f), g4 = b4;
+        if (bias && nv >= 4) {
+          b4 = __ldg(reinterpret_cast<const float4*>(bias + acc_col));
+          if (geglu) g4 = __ldg(reinterpret_cast<const float4*>(bias + acc_col + half));
+        } else if (bias && nv > 0) {
+          b4.x = __ldg(bias + acc_col);
+          if (nv > 1) b4.y = __ldg(bias + acc_col + 1);
+          if (nv > 2) b4.z = __ldg(bias + acc_col + 2);
+        }
         // warp-uniform: the whole 32-column chunk is inside the matrix (the fast path uses full-mask shuffles)
         const int chunk_nv = n_out - (col - c4);
         if (chunk_nv <= 0) { __syncwarp(); continue; }
@@ -583,43 +579,8 @@ __global__ void __launch_bounds__(kGemmThreads, MINB) gemm_tc_kernel(const __gri
               }
             }
           }
-        } else if (geglu && ld_vec && chunk_nv >= 32) {
-          // GEGLU fast path: RG rows (4 RG gate activations) in flight per lane. The rolled general path below ran one row
-          // at a time: ~120 dependent instructions per row on 2 warps per scheduler = 880 cycles per row, 15.7 k cycles per
-          // tile against a 2.7 k K loop (r02 phase stamps).
-          constexpr int RG = 2;
-#pragma unroll
-          for (int r0 = 0; r0 < 8; r0 += RG) {
-            float4 x[RG], gt[RG];
-            long long ob[RG];
-            uint32_t vm = 0;
-#pragma unroll
-            for (int it = 0; it < RG; ++it) {
-              long long m;
-              const bool ok = tile_row_index(tg, q * 32 + (r0 + it) * 4 + sub, &m);
-              ob[it] = m * (long long)ldo + col;
-              vm |= uint32_t(ok) << it;
-              x[it] = *reinterpret_cast<const float4*>(s_rd + (r0 + it) * (4 * kEpiPitch));
-              gt[it] = *reinterpret_cast<const float4*>(s_rd + 32 * kEpiPitch + (r0 + it) * (4 * kEpiPitch));
-            }
-#pragma unroll
-            for (int it = 0; it < RG; ++it) {
-              float4 v;
-              v.x = (x[it].x + b4.x) * gelu_erf_f(gt[it].x + g4.x); v.y = (x[it].y + b4.y) * gelu_erf_f(gt[it].y + g4.y);
-              v.z = (x[it].z + b4.z) * gelu_erf_f(gt[it].z + g4.z); v.w = (x[it].w + b4.w) * gelu_erf_f(gt[it].w + g4.w);
-              if ((vm >> it) & 1u) {
-                if (residual) {
-                  const float4 rr = __ldg(reinterpret_cast<const float4*>(residual + ob[it]));
-                  v.x += rr.x; v.y += rr.y; v.z += rr.z; v.w += rr.w;
-                }
-                if (out_f32) *reinterpret_cast<float4*>(out_f32 + ob[it]) = v;
-                if (out_bf16)
-                  *reinterpret_cast<uint2*>(out_bf16 + ob[it]) = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
-              }
-            }
-          }
         } else {
-          // general path (SiLU, ragged / unaligned tails, GEGLU tails): rolled to stay small
+          // general path (GEGLU's erf polynomial, SiLU, ragged / unaligned tails): rolled to stay small
 #pragma unroll 1
           for (int it = 0; it < 8; ++it) {
             long long m;

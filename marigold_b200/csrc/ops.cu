@@ -181,7 +181,7 @@ int run_gemm(GemmParams& p, int block_n, float* splitk_ws, cudaStream_t stream) 
     const long long ctas = m_tiles * ((p.N + block_n - 1) / block_n) * splits;
     if (two_cta_env && block_n >= 64 && p.mode != 2 && ctas > 148) {
       const int stage_bytes = 16384 + block_n * 128;
-      const int st2 = std::min(p.stages, (113 * 1024 - 2304) / stage_bytes);
+      const int st2 = std::min(p.stages, (113 * 1024 - 1280) / stage_bytes);
       const int need = 8 * ((p.epi.flags & EPI_GEGLU) ? 9216 : 4608);
       if (st2 >= 2 && st2 * stage_bytes >= need) { p.stages = st2; ctas_per_sm = 2; }
     }

@@ -52,8 +52,9 @@ def test_fused_normalisation_and_colorize():
 
     img = torch.randint(0, 256, (1, 3, 300, 500), dtype=torch.uint8, generator=torch.Generator().manual_seed(1)).cuda()
     a = imageops.resize(img, (230, 384), "bilinear", post=2)
-    b = imageops.resize(img, (230, 384), "bilinear", post=1) / 255.0 * 2.0 - 1.0
-    assert torch.equal(a, b) and float(a.min()) >= -1 and float(a.max()) <= 1
+    # the reference normalises on the HOST (true division; torch's CUDA div-by-scalar multiplies by the reciprocal instead)
+    b = imageops.resize(img, (230, 384), "bilinear", post=1).cpu() / 255.0 * 2.0 - 1.0
+    assert torch.equal(a.cpu(), b) and float(a.min()) >= -1 and float(a.max()) <= 1
     d = torch.rand(123, 77, generator=torch.Generator().manual_seed(2))
     d[0, 0], d[0, 1], d[0, 2] = 0.0, 1.0, 0.5
     got = imageops.colorize_u8(d.cuda(), 0, 1, imageops.spectral_lut_u8()).cpu().numpy()
