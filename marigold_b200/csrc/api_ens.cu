@@ -88,8 +88,14 @@ int mgb_ens_depth_cost_fd(mgb_handle* h, const float* depth, const double* base,
   if (rc) return rc;
   rc = make_st(pert, E, scale_inv, shift_inv, st + 2 * E);
   if (rc) return rc;
+  if (size_t(HW) * 3 * sizeof(float) > h->ens_v3_bytes) {     // per-pixel order statistics of the base point
+    if (h->ens_v3) CUDA_TRY(cudaFree(h->ens_v3));
+    h->ens_v3 = nullptr; h->ens_v3_bytes = 0;
+    CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&h->ens_v3), size_t(HW) * 3 * sizeof(float)));
+    h->ens_v3_bytes = size_t(HW) * 3 * sizeof(float);
+  }
   int launches = 0;
-  rc = launch_ens_depth_cost_fd(depth, st, E, HW, shift_inv, median, reg, h->ens_ws, h->ens_pinned, &launches,
+  rc = launch_ens_depth_cost_fd(depth, st, E, HW, shift_inv, median, reg, h->ens_ws, h->ens_v3, h->ens_pinned, &launches,
                                 reinterpret_cast<cudaStream_t>(stream));
   if (rc) return rc;
   count_launch(launches);

@@ -268,6 +268,7 @@ void mgb_destroy(mgb_handle* h) {
   if (h->capture_stream) cudaStreamDestroy(h->capture_stream);
   if (h->ens_ws) cudaFree(h->ens_ws);
   if (h->ens_pinned) cudaFreeHost(h->ens_pinned);
+  if (h->ens_v3) cudaFree(h->ens_v3);
   delete h;
 }
 

@@ -37,9 +37,13 @@ constexpr int kKvBytes = 64 * 128;       // 64 rows x 64 bf16
 constexpr int kPBytes = 128 * 128;       // 128 rows x 64 bf16
 constexpr int kKvStages = 3;
 constexpr float kRescaleThreshold = 8.0f;  // log2 units
+constexpr int kAttnDefaultVariant = 0;
 // P (bf16) goes back to tensor memory and feeds the PV MMA as a TMEM A-operand: no smem round trip and no
 // generic->async proxy fence in the softmax loop.
-constexpr bool kAluPack = false;   // bf16 pack on the integer ALU instead of F2FP: measured neutral (r01)
+// The softmax is bound by the XU pipe (ncu r02: sm__inst_executed_pipe_xu 102 % of peak): MUFU.EX2 and the F2FP bf16
+// conversions share it, 1.5 XU operations per score at 16 lanes / clock / SM = 768 cycles per 128 x 64 block against 256
+// cycles of tensor work. Variants move work off it: ALU_PACK converts with integer adds + PRMT; POLY of every 4
+// exponentials are evaluated by ex2_poly on the FMA pipe (relative error 2.2e-4, below the bf16 rounding of P).
 
 struct AttnParams {
   CUtensorMap tmap_q;   // 3D {3C, T, NB}, box {64, 128, 1}
@@ -65,6 +69,7 @@ __device__ __forceinline__ void quarter_barrier(int q) {
   }
 }
 
+template <bool ALU_PACK, int POLY>
 __global__ void __launch_bounds__(kAttnThreads, 2) flash_attn64_kernel(const __grid_constant__ AttnParams p) {
   pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
@@ -251,13 +256,15 @@ __global__ void __launch_bounds__(kAttnThreads, 2) flash_attn64_kernel(const __g
       const float nm = -m_ref;
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        const float a0 = ex2_approx(fmaf(__uint_as_float(r[4 * i]), p.scale_log2, nm));
-        const float a1 = ex2_approx(fmaf(__uint_as_float(r[4 * i + 1]), p.scale_log2, nm));
-        const float a2 = ex2_approx(fmaf(__uint_as_float(r[4 * i + 2]), p.scale_log2, nm));
-        const float a3 = ex2_approx(fmaf(__uint_as_float(r[4 * i + 3]), p.scale_log2, nm));
+        const float e0 = fmaf(__uint_as_float(r[4 * i]), p.scale_log2, nm), e1 = fmaf(__uint_as_float(r[4 * i + 1]), p.scale_log2, nm),
+                    e2 = fmaf(__uint_as_float(r[4 * i + 2]), p.scale_log2, nm), e3 = fmaf(__uint_as_float(r[4 * i + 3]), p.scale_log2, nm);
+        const float a0 = POLY >= 1 ? ex2_poly(e0) : ex2_approx(e0);
+        const float a1 = ex2_approx(e1);
+        const float a2 = POLY >= 2 ? ex2_poly(e2) : ex2_approx(e2);
+        const float a3 = ex2_approx(e3);
         ls0 += a0; ls1 += a1; ls2 += a2; ls3 += a3;
-        pk[2 * i] = kAluPack ? pack_bf16x2_pos_alu(a0, a1) : pack_bf16x2(a0, a1);
-        pk[2 * i + 1] = kAluPack ? pack_bf16x2_pos_alu(a2, a3) : pack_bf16x2(a2, a3);
+        pk[2 * i] = ALU_PACK ? pack_bf16x2_pos_alu(a0, a1) : pack_bf16x2(a0, a1);
+        pk[2 * i + 1] = ALU_PACK ? pack_bf16x2_pos_alu(a2, a3) : pack_bf16x2(a2, a3);
       }
       l_run += (ls0 + ls1) + (ls2 + ls3);
       // P buffer b was last read by PV(j-2)
@@ -385,14 +392,18 @@ int launch_flash_attn64(const bf16* qkv, bf16* out, int NB, int T, int C, float 
   }
   static const size_t dbg_pad = getenv("MGB_ATTN_SMEM_PAD") ? size_t(atoi(getenv("MGB_ATTN_SMEM_PAD"))) : 0;   // debug: force 1 CTA/SM
   const size_t smem = 1024 + kQBytes + 2 * kKvStages * kKvBytes + 256 + 2048 + dbg_pad;
+  // variant: 0 = F2FP + MUFU only, 1 = ALU pack, 2 = ALU pack + 1/4 polynomial, 3 = ALU pack + 1/2 polynomial
+  static const int variant = getenv("MGB_ATTN_VARIANT") ? atoi(getenv("MGB_ATTN_VARIANT")) : kAttnDefaultVariant;
+  void (*kern)(AttnParams) = variant == 0 ? flash_attn64_kernel<false, 0> : variant == 1 ? flash_attn64_kernel<true, 0>
+                             : variant == 2 ? flash_attn64_kernel<true, 1> : flash_attn64_kernel<true, 2>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(flash_attn64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
     if (e != cudaSuccess) { set_error("flash_attn64 attr: %s", cudaGetErrorString(e)); return MGB_ERR_CUDA; }
     attr_set = true;
   }
   dim3 grid((T + 127) / 128, C / 64, NB * p.splits);
-  cudaError_t e = launch_k(flash_attn64_kernel, grid, kAttnThreads, smem, stream, p);
+  cudaError_t e = launch_k(kern, grid, kAttnThreads, smem, stream, p);
   if (e == cudaSuccess) e = cudaGetLastError();
   if (e != cudaSuccess) { set_error("flash_attn64 launch: %s", cudaGetErrorString(e)); return MGB_ERR_CUDA; }
   if (p.splits > 1) {

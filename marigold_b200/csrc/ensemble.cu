@@ -83,9 +83,12 @@ __device__ __forceinline__ void block_minmax(float& pmin, float& pmax, float (*s
 }
 
 // One block's share of the objective for ONE parameter set: E (E - 1) / 2 pair sums + min / max of the ensembled map.
+// v3_out (optional, median only): per pixel the order statistics v[R-1], v[R], v[R+1] of the aligned values around the
+// lower-median rank R (-FLT_MAX / FLT_MAX where they do not exist), for the forward-difference rows.
 template <int E>
 __device__ __forceinline__ void cost_block(const float* __restrict__ depth, const float* __restrict__ st, long long HW,
-                                           int shift, int median, CostPartial* __restrict__ out) {
+                                           int shift, int median, CostPartial* __restrict__ out,
+                                           float* __restrict__ v3_out = nullptr) {
   constexpr int NP = E * (E - 1) / 2;
   float s[E], t[E];
 #pragma unroll
@@ -113,7 +116,13 @@ __device__ __forceinline__ void cost_block(const float* __restrict__ depth, cons
 #pragma unroll
       for (int e = 0; e < E; ++e) idx[e] = e;
       sort_small<E>(a, idx);
-      pred = a[(E - 1) / 2];
+      constexpr int R = (E - 1) / 2;
+      pred = a[R];
+      if (v3_out) {
+        v3_out[3 * p + 0] = R > 0 ? a[R > 0 ? R - 1 : 0] : -FLT_MAX;
+        v3_out[3 * p + 1] = a[R];
+        v3_out[3 * p + 2] = R + 1 < E ? a[R + 1 < E ? R + 1 : R] : FLT_MAX;
+      }
     } else {
       float sm = 0.f;
 #pragma unroll
@@ -142,11 +151,11 @@ __global__ void __launch_bounds__(kEnsThreads)
                 partials_all + size_t(blockIdx.y) * gridDim.x + blockIdx.x);
 }
 
-// ---- one forward-difference gradient in ONE pass: the base point plus the n = 2E (or E) single-coordinate
+// ---- one forward-difference gradient in ONE round trip: the base point plus the n = 2E (or E) single-coordinate
 // perturbations scipy's approx_derivative evaluates. Perturbing member m only changes the E - 1 pairs (m, j) and moves
-// one element of the per-pixel order statistics, so block row m + 1 recomputes just those (the lower median of the
-// perturbed set is clamp(x', w[r*-1], w[r*]) with w = the sorted base values without member m): ~9x less arithmetic
-// than 2E + 1 independent evaluations. Every sum is formed exactly as cost_block forms it (same pixel-to-thread map, same
+// one element of the per-pixel order statistics, so after the base pass (which also stores three order statistics per
+// pixel) block row m of the second kernel recomputes just those, without sorting: ~5x less arithmetic than 2E + 1
+// independent evaluations. Every sum is formed exactly as cost_block forms it (same pixel-to-thread map, same
 // reduction order), and the final kernel assembles each perturbed objective from base + perturbed pair sums in pair
 // order, so the values equal ens_cost_kernel's bit for bit (tests/test_ensemble_gpu.py).
 struct FdPartial {
@@ -156,67 +165,55 @@ struct FdPartial {
 
 template <int E>
 __global__ void __launch_bounds__(kEnsThreads)
-    ens_cost_fd_kernel(const float* __restrict__ depth, const float* __restrict__ st /* [2E] base */,
-                       const float* __restrict__ pert /* [2E]: s'_0..s'_{E-1} | t'_0..t'_{E-1} */, long long HW, int shift,
-                       int median, CostPartial* __restrict__ base_part, FdPartial* __restrict__ fd_part) {
-  if (blockIdx.y == 0) {
-    cost_block<E>(depth, st, HW, shift, median, base_part + blockIdx.x);
-    return;
-  }
-  const int m = blockIdx.y - 1;
+    ens_cost_fd_base_kernel(const float* __restrict__ depth, const float* __restrict__ st, long long HW, int shift, int median,
+                            CostPartial* __restrict__ base_part, float* __restrict__ v3) {
+  cost_block<E>(depth, st, HW, shift, median, base_part + blockIdx.x, median ? v3 : nullptr);
+}
+
+// block row m: member m perturbed (s_m -> s', and t_m -> t' when shift): the E - 1 pair sums with the other members, and
+// min / max of the re-ensembled map. No sort here: with v = the sorted base values (from ens_cost_fd_base_kernel) and w = v
+// without one instance of a_m, the perturbed lower median is clamp(x', w[R-1], w[R]), where
+//   a_m <= v[R-1]          : w[R-1] = v[R],   w[R] = v[R+1]
+//   v[R-1] < a_m <= v[R]   : w[R-1] = v[R-1], w[R] = v[R+1]      (a_m is v[R])
+//   a_m > v[R]             : w[R-1] = v[R-1], w[R] = v[R]
+template <int E>
+__global__ void __launch_bounds__(kEnsThreads)
+    ens_cost_fd_pert_kernel(const float* __restrict__ depth, const float* __restrict__ st /* [2E] base */,
+                            const float* __restrict__ pert /* [2E]: s'_0..s'_{E-1} | t'_0..t'_{E-1} */, long long HW, int shift,
+                            int median, const float* __restrict__ v3, FdPartial* __restrict__ fd_part) {
+  const int m = blockIdx.y;
   const int nk = shift ? 2 : 1;
   float s[E], t[E];
 #pragma unroll
   for (int e = 0; e < E; ++e) { s[e] = st[e]; t[e] = st[E + e]; }
   const float sp = pert[m], tp = pert[E + m];
+  const float sm_base = st[m], tm_base = st[E + m];
   float acc0[E], acc1[E];
 #pragma unroll
   for (int e = 0; e < E; ++e) { acc0[e] = 0.f; acc1[e] = 0.f; }
   float mn0 = FLT_MAX, mx0 = -FLT_MAX, mn1 = FLT_MAX, mx1 = -FLT_MAX;
-  constexpr int R = (E - 1) / 2;   // rank of the lower median
   for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < HW; p += (long long)gridDim.x * blockDim.x) {
     float a[E];
-    float dm = 0.f;
 #pragma unroll
-    for (int e = 0; e < E; ++e) {
-      const float d = __ldg(depth + (long long)e * HW + p);
-      a[e] = align1(d, s[e], t[e], shift);
-      if (e == m) dm = d;
-    }
-    float sm_base = 0.f;
-#pragma unroll
-    for (int e = 0; e < E; ++e) if (e == m) sm_base = s[e];
-    float tm_base = 0.f;
-#pragma unroll
-    for (int e = 0; e < E; ++e) if (e == m) tm_base = t[e];
+    for (int e = 0; e < E; ++e) a[e] = align1(__ldg(depth + (long long)e * HW + p), s[e], t[e], shift);
+    const float dm = __ldg(depth + (long long)m * HW + p);
+    const float am = align1(dm, sm_base, tm_base, shift);
     const float x0 = align1(dm, sp, tm_base, shift);      // s_m perturbed
     const float x1 = align1(dm, sm_base, tp, shift);      // t_m perturbed
 #pragma unroll
     for (int j = 0; j < E; ++j) {
-      if (j != m) {
-        const float d0 = x0 - a[j], d1 = x1 - a[j];
-        acc0[j] = fmaf(d0, d0, acc0[j]);
-        acc1[j] = fmaf(d1, d1, acc1[j]);
-      }
+      // (the j == m slot accumulates (x' - a_m)^2 and is never read)
+      const float d0 = x0 - a[j], d1 = x1 - a[j];
+      acc0[j] = fmaf(d0, d0, acc0[j]);
+      acc1[j] = fmaf(d1, d1, acc1[j]);
     }
     float p0, p1;
     if (median) {
-      float v[E];
-      int idx[E];
-#pragma unroll
-      for (int e = 0; e < E; ++e) { v[e] = a[e]; idx[e] = e; }
-      sort_small<E>(v, idx);
-      int r = 0;
-#pragma unroll
-      for (int e = 0; e < E; ++e) if (idx[e] == m) r = e;
-      // w = v without rank r; lo = w[R - 1] (-inf if R == 0), hi = w[R] (+inf if R == E - 1)
-      float lo = -FLT_MAX, hi = FLT_MAX;
-#pragma unroll
-      for (int e = 0; e < E; ++e) {
-        const int wi = e < r ? e : e - 1;            // index in w of v[e] (e != r)
-        if (e != r && wi == R - 1) lo = v[e];
-        if (e != r && wi == R) hi = v[e];
-      }
+      const float vlo = __ldg(v3 + 3 * p), vmid = __ldg(v3 + 3 * p + 1), vhi = __ldg(v3 + 3 * p + 2);
+      float lo, hi;
+      if (am <= vlo) { lo = vmid; hi = vhi; }
+      else if (am <= vmid) { lo = vlo; hi = vhi; }
+      else { lo = vlo; hi = vmid; }
       p0 = fminf(fmaxf(x0, lo), hi);
       p1 = fminf(fmaxf(x1, lo), hi);
     } else {
@@ -231,13 +228,10 @@ __global__ void __launch_bounds__(kEnsThreads)
   __shared__ double sh[kEnsThreads / 32];
   __shared__ float shf[2][kEnsThreads / 32];
   FdPartial* out = fd_part + size_t(m) * gridDim.x + blockIdx.x;
-#pragma unroll 1
-  for (int j = 0; j < E; ++j) {
-    float a0 = 0.f, a1 = 0.f;
 #pragma unroll
-    for (int e = 0; e < E; ++e) if (e == j) { a0 = acc0[e]; a1 = acc1[e]; }
-    const double t0 = block_sum_double(a0, sh);
-    const double t1 = nk == 2 ? block_sum_double(a1, sh) : 0.0;
+  for (int j = 0; j < E; ++j) {
+    const double t0 = block_sum_double(acc0[j], sh);
+    const double t1 = nk == 2 ? block_sum_double(acc1[j], sh) : 0.0;
     if (threadIdx.x == 0) { out->pair_sum[0][j] = t0; out->pair_sum[1][j] = t1; }
   }
   block_minmax(mn0, mx0, shf);
@@ -518,7 +512,8 @@ int launch_ens_depth_cost(const float* depth, const float* st_host, int P, int E
 // st_host (pinned): float [4E] = base {s | t} then perturbed {s' | t'}; out_host_pinned: double [1 + n][3] with n = 2E
 // (shift) or E: set 0 = base, set 1 + i = coordinate i perturbed. One launch pair, one synchronisation.
 int launch_ens_depth_cost_fd(const float* depth, const float* st_host, int E, long long HW, int shift, int median,
-                             double reg, void* ws, double* out_host_pinned, int* launches, cudaStream_t stream) {
+                             double reg, void* ws, float* v3 /* 3 HW floats of scratch */, double* out_host_pinned,
+                             int* launches, cudaStream_t stream) {
   if (E < 2 || E > kEnsMaxE) { set_error("ens cost fd: ensemble size %d outside [2, %d]", E, kEnsMaxE); return MGB_ERR_UNSUPPORTED; }
   float* st = ens_ws_st(ws);
   double* out = ens_ws_out(ws);
@@ -529,13 +524,15 @@ int launch_ens_depth_cost_fd(const float* depth, const float* st_host, int E, lo
   const int blocks = int(std::min<long long>((HW + kEnsThreads - 1) / kEnsThreads, kEnsCostBlocks));
   const int n = shift ? 2 * E : E;
   switch (E) {
-#define CASE(k) case k: ens_cost_fd_kernel<k><<<dim3(blocks, E + 1), kEnsThreads, 0, stream>>>(depth, st, st + 2 * E, HW, shift, median, base_part, fd_part); break;
+#define CASE(k) case k: \
+      ens_cost_fd_base_kernel<k><<<blocks, kEnsThreads, 0, stream>>>(depth, st, HW, shift, median, base_part, v3); \
+      ens_cost_fd_pert_kernel<k><<<dim3(blocks, E), kEnsThreads, 0, stream>>>(depth, st, st + 2 * E, HW, shift, median, v3, fd_part); break;
     CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8) CASE(9) CASE(10) CASE(11) CASE(12) CASE(13) CASE(14)
     CASE(15) CASE(16)
 #undef CASE
   }
   ens_cost_fd_final_kernel<<<1 + n, 256, 0, stream>>>(base_part, fd_part, blocks, E, HW, reg, out);
-  *launches = 2;
+  *launches = 3;
   e = cudaMemcpyAsync(out_host_pinned, out, size_t(1 + n) * 3 * sizeof(double), cudaMemcpyDeviceToHost, stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
   if (e == cudaSuccess) e = cudaGetLastError();

@@ -177,7 +177,7 @@ int launch_ens_depth_cost(const float* depth, const float* st_host, int P, int E
                           double reg, void* ws, double* out_host_pinned, int* launches, cudaStream_t stream);
 // One forward-difference gradient: st_host (pinned) float [4E] = base {s | t}, perturbed {s' | t'}; out double [1 + n][3]
 int launch_ens_depth_cost_fd(const float* depth, const float* st_host, int E, long long HW, int shift, int median,
-                             double reg, void* ws, double* out_host_pinned, int* launches, cudaStream_t stream);
+                             double reg, void* ws, float* v3, double* out_host_pinned, int* launches, cudaStream_t stream);
 int launch_ens_minmax(const float* depth, int E, long long HW, float* ws, float* host_pinned, int* blocks_out,
                       cudaStream_t stream);
 int launch_ens_depth_reduce(const float* depth, const float* st_host, int E, long long HW, int shift, int median,

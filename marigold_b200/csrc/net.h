@@ -159,4 +159,6 @@ struct mgb_handle {
   // ensemble scratch
   void* ens_ws = nullptr;
   double* ens_pinned = nullptr;  // pinned host staging (api_ens.cu)
+  float* ens_v3 = nullptr;       // per-pixel order statistics for the forward-difference objective
+  size_t ens_v3_bytes = 0;
 };
