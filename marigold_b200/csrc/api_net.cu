@@ -184,12 +184,18 @@ struct Loader {
       x.qkv.n = 3 * C; x.qkv.k = C; x.qkv.w = up_bf16(w);
     }
     x.o1 = lin(t + ".attn1.to_out.0", C, C, true);
-    x.q2 = lin(t + ".attn2.to_q", C, C, false);
+    {
+      const HostTensor *q2 = get(t + ".attn2.to_q.weight"), *o2 = get(t + ".attn2.to_out.0.weight"),
+                       *ob = get(t + ".attn2.to_out.0.bias");
+      if (shape_is(q2, {C, C}, t + ".attn2.to_q.weight") && shape_is(o2, {C, C}, t + ".attn2.to_out.0.weight") &&
+          shape_is(ob, {C}, t + ".attn2.to_out.0.bias")) {
+        x.q2w = up_f32(q2->data); x.o2w = up_f32(o2->data); x.o2b = up_f32(ob->data);
+      }
+    }
     const HostTensor *k2 = get(t + ".attn2.to_k.weight"), *v2 = get(t + ".attn2.to_v.weight");
     if (shape_is(k2, {C, ctx}, t + ".attn2.to_k.weight") && shape_is(v2, {C, ctx}, t + ".attn2.to_v.weight")) {
       x.k2w = up_f32(k2->data); x.v2w = up_f32(v2->data);
     }
-    x.o2 = lin(t + ".attn2.to_out.0", C, C, true);
     // GEGLU: interleave [value | gate] per 256-column accumulator tile
     const HostTensor *fw = get(t + ".ff.net.0.proj.weight"), *fb = get(t + ".ff.net.0.proj.bias");
     if (shape_is(fw, {8 * C, C}, t + ".ff.net.0.proj.weight") && shape_is(fb, {8 * C}, t + ".ff.net.0.proj.bias")) {
@@ -435,7 +441,15 @@ int mgb_set_text_embedding(mgb_handle* h, const float* embed_host, int32_t n_tok
     }
     TRY(launch_linear_small(d_ctx, x.k2w, nullptr, x.kv, n_tokens, x.C, ctx, 0, 0, nullptr));
     TRY(launch_linear_small(d_ctx, x.v2w, nullptr, x.kv + size_t(n_tokens) * x.C, n_tokens, x.C, ctx, 0, 0, nullptr));
-    count_launch(2);
+    if (!x.xG) {
+      const int H = x.C / 64;
+      void* g = nullptr;
+      CUDA_TRY(cudaMalloc(&g, (size_t(2) * H + 1) * x.C * 4));
+      h->dev_allocs.push_back(g);
+      x.xG = static_cast<float*>(g); x.xU = x.xG + size_t(H) * x.C; x.xc1 = x.xU + size_t(H) * x.C;
+    }
+    TRY(launch_xattn2_fold(x.q2w, x.o2w, x.o2b, x.kv, x.xG, x.xU, x.xc1, x.C, nullptr));
+    count_launch(3);
   }
   CUDA_TRY(cudaDeviceSynchronize());
   CUDA_TRY(cudaFree(d_ctx));

@@ -324,7 +324,8 @@ __device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)
 // instead of erff's ~35 instructions; this epilogue runs 11.8 M times per 96 x 96 feed-forward.
 __device__ __forceinline__ float gelu_erf_f(float x) {
   const float z = fabsf(x) * 0.70710678118654752f;
-  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+  float t;                                                        // 1 / (1 + p z) in (0, 1]: one MUFU.RCP (the IEEE
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));   // __frcp_rn adds a refinement + a branchy slow path)
   float poly = fmaf(1.061405429f, t, -1.453152027f);
   poly = fmaf(poly, t, 1.421413741f);
   poly = fmaf(poly, t, -0.284496736f);

@@ -1,7 +1,6 @@
 // Streaming (HBM-bound) helpers around the tensor-core kernels: layout changes that feed TMA
 // (space-to-depth parity planes for stride-2 convs, nearest x2 upsampling, channel concat, latent
-// packing), the ABI's NCHW<->NHWC conversions, the tiny dense layers (time MLP, text K/V), the 2-key
-// cross attention and a row softmax. All use 128-bit accesses where the layout allows.
+// packing), the ABI's NCHW<->NHWC conversions, the tiny dense layers (time MLP, text K/V) and a row softmax. All use 128-bit accesses where the layout allows.
 #include "common.cuh"
 #include "kernels.h"
 #include "launch.h"
@@ -193,46 +192,6 @@ int launch_pack_rgb(const float* rgb_nchw, bf16* out, int NB, int HW, cudaStream
   pack_rgb_kernel<<<grid_for((size_t)NB * HW * 8, 256), 256, 0, stream>>>(rgb_nchw, reinterpret_cast<uint4*>(out), NB,
                                                                          size_t(HW));
   MGB_LAUNCH_CHECK("pack_rgb");
-}
-
-// Cross attention against n_ctx == 2 pre-projected keys/values (the empty-prompt BOS/EOS tokens,
-// reference marigold_depth_pipeline.py:381-394). One warp per (token, head): 64-dim dots, 2-way softmax.
-// q bf16 [M, C]; kv fp32 [2 (k|v), 2 (ctx token), C]; out bf16 [M, C]
-__global__ void __launch_bounds__(256) cross_attn2_kernel(const bf16* __restrict__ q, const float* __restrict__ kv,
-                                                          bf16* __restrict__ out, int M, int C, float scale) {
-  pdl_launch_dependents();
-  pdl_wait();
-  const int heads = C / 64;
-  const long long gw = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (gw >= (long long)M * heads) return;
-  const long long m = gw / heads;
-  const int h = int(gw - m * heads);
-  const int c = h * 64 + lane * 2;
-  const __nv_bfloat162 q2 = *reinterpret_cast<const __nv_bfloat162*>(q + m * C + c);
-  const float qa = __bfloat162float(q2.x), qb = __bfloat162float(q2.y);
-  const float2 k0 = *reinterpret_cast<const float2*>(kv + c), k1 = *reinterpret_cast<const float2*>(kv + C + c);
-  float s0 = qa * k0.x + qb * k0.y, s1 = qa * k1.x + qb * k1.y;
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    s0 += __shfl_xor_sync(0xffffffffu, s0, o);
-    s1 += __shfl_xor_sync(0xffffffffu, s1, o);
-  }
-  s0 *= scale; s1 *= scale;
-  const float mx = fmaxf(s0, s1);
-  const float e0 = __expf(s0 - mx), e1 = __expf(s1 - mx);
-  const float inv = 1.f / (e0 + e1);
-  const float2 v0 = *reinterpret_cast<const float2*>(kv + 2 * C + c),
-               v1 = *reinterpret_cast<const float2*>(kv + 3 * C + c);
-  const float oa = (e0 * v0.x + e1 * v1.x) * inv, ob = (e0 * v0.y + e1 * v1.y) * inv;
-  *reinterpret_cast<__nv_bfloat162*>(out + m * C + c) = __floats2bfloat162_rn(oa, ob);
-}
-int launch_cross_attn2(const bf16* q, const float* kv, bf16* out, int M, int C, float scale, cudaStream_t stream) {
-  if (C % 64) { set_error("cross_attn2: C %% 64 != 0"); return MGB_ERR_INVALID; }
-  const long long warps = (long long)M * (C / 64);
-  const int blocks = int((warps + 7) / 8);
-  launch_k(cross_attn2_kernel, blocks, 256, 0, stream, q, kv, out, M, C, scale);
-  MGB_LAUNCH_CHECK("cross_attn2");
 }
 
 // y[M, N] = act_out(act_in(x)[M, K] W[N, K]^T + b); fp32 everywhere; one warp per output element.

@@ -117,6 +117,13 @@ int launch_gn_fused(const float* xa, int Ca, const float* xb, int Cb, bf16* y, b
 // LayerNorm over the channel dim: x_f32 [M, C] -> y_bf16 [M, C]
 int launch_layernorm(const float* x, bf16* y, const float* gamma, const float* beta, int M, int C, float eps,
                      cudaStream_t stream);
+// Collapsed cross attention against the fixed 2-token context, fused with norm2 and norm3 (norm.cu):
+//   y = x + c1 + sum_h sigmoid(scale * LN2(x) . G_h) U_h ;  a_out = bf16(LN3(y))
+int launch_xattn2_fused(const float* x, float* y, bf16* a_out, const float* g2, const float* b2, const float* g3,
+                        const float* b3, const float* G, const float* U, const float* c1, int M, int C, int H, float scale,
+                        float eps, cudaStream_t stream);
+int launch_xattn2_fold(const float* wq, const float* wo, const float* bo, const float* kv, float* G, float* U, float* c1,
+                       int C, cudaStream_t stream);
 // y[NB, 4, ceil(H/2), ceil(W/2), C] (parity planes p = (h&1)*2 + (w&1), zero where the source pixel does not exist) from
 // x fp32 [NB, H, W, C]
 int launch_space_to_depth(const float* x, bf16* y, int NB, int H, int W, int C, cudaStream_t stream);
@@ -140,8 +147,6 @@ int launch_pack_decoder_latent(const float* latent_nchw, const float* w, const f
 int launch_select_step(const float* bias_table, int bias_total, const float* sched_k, float* cur_bias, float* cur_k,
                        const int* counter, int step, cudaStream_t stream);
 int launch_advance_counter(int* counter, cudaStream_t stream);
-// 2-key cross attention with pre-projected K/V: q bf16 [M, C]; kv fp32 [2(k|v), 2(tokens), C]; out bf16 [M, C]
-int launch_cross_attn2(const bf16* q, const float* kv, bf16* out, int M, int C, float scale, cudaStream_t stream);
 // Tiny dense layer for M <= 16 rows (time MLP, text K/V): y[M,N] = act(x[M,K]) W[N,K]^T + b ; fp32
 int launch_linear_small(const float* x, const float* w, const float* b, float* y, int M, int N, int K,
                         int silu_in, int silu_out, cudaStream_t stream);

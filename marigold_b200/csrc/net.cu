@@ -212,13 +212,13 @@ static int xfmr_forward(Ctx& c, const XfmrW& X, Act& x, Act& y, int NB, int T) {
   { Epi e; e.out_bf16 = qkv; TRY(linear(c, a, int(M), X.qkv, e)); }
   if (!no_attn) LAUNCH(launch_flash_attn64(qkv, o, NB, T, C, 0.125f, attn_ws, attn_ws_bytes, c.stream), attn_ws ? 2 : 1);
   { Epi e; e.bias = X.o1.b; e.residual = hs0; e.out_f32 = hs1; TRY(linear(c, o, int(M), X.o1, e)); }
-  // cross attention against the folded empty-prompt K/V
-  if (!no_ln) LAUNCH(launch_layernorm(hs1, a, X.ln2.g, X.ln2.b, int(M), C, 1e-5f, c.stream), 1);
-  { Epi e; e.out_bf16 = qkv; TRY(linear(c, a, int(M), X.q2, e)); }  // q in the first M*C elements of qkv
-  if (!no_x) LAUNCH(launch_cross_attn2(qkv, X.kv, o, int(M), C, 0.125f, c.stream), 1);
-  { Epi e; e.bias = X.o2.b; e.residual = hs1; e.out_f32 = hs0; TRY(linear(c, o, int(M), X.o2, e)); }
+  // cross attention against the empty-prompt context, collapsed (norm.cu: xattn2_fused_kernel): LN2, to_q, the 2-key
+  // softmax, to_out + residual and LN3 are one launch; hs0 = trunk after attn2, a = LN3(hs0) for the feed-forward
+  if (!no_x) {
+    LAUNCH(launch_xattn2_fused(hs1, hs0, a, X.ln2.g, X.ln2.b, X.ln3.g, X.ln3.b, X.xG, X.xU, X.xc1, int(M), C, C / 64, 0.125f,
+                               1e-5f, c.stream), 1);
+  }
   // GEGLU feed-forward
-  if (!no_ln) LAUNCH(launch_layernorm(hs0, a, X.ln3.g, X.ln3.b, int(M), C, 1e-5f, c.stream), 1);
   { Epi e; e.bias = X.ff1.b; e.out_bf16 = ffm; e.flags = EPI_GEGLU; TRY(linear(c, a, int(M), X.ff1, e)); }
   { Epi e; e.bias = X.ff2.b; e.residual = hs0; e.out_bf16 = hsb; TRY(linear(c, ffm, int(M), X.ff2, e)); }
   {

@@ -50,10 +50,17 @@ struct ResnetW {
 struct XfmrW {
   int C = 0;
   NormW gn, ln1, ln2, ln3;
-  LinW proj_in, qkv, o1, q2, o2, ff1, ff2, proj_out;
-  float* k2w = nullptr;  // fp32 [C, ctx]
-  float* v2w = nullptr;
-  float* kv = nullptr;   // fp32 [2 (k|v), n_ctx, C], folded at set_text_embedding
+  LinW proj_in, qkv, o1, ff1, ff2, proj_out;
+  // cross attention (attn2): fp32 masters, folded against the empty-prompt context at set_text_embedding
+  float* q2w = nullptr;  // to_q   fp32 [C, C]
+  float* o2w = nullptr;  // to_out fp32 [C, C]
+  float* o2b = nullptr;  // to_out bias [C]
+  float* k2w = nullptr;  // to_k   fp32 [C, ctx]
+  float* v2w = nullptr;  // to_v
+  float* kv = nullptr;   // fp32 [2 (k|v), n_ctx, C]
+  float* xG = nullptr;   // [H, C]  G_h = Wq[h-block]^T (k0 - k1)_h
+  float* xU = nullptr;   // [H, C]  U_h = Wo[:, h-block] (v0 - v1)_h
+  float* xc1 = nullptr;  // [C]     Wo v1 + bo
 };
 struct VaeAttnW {
   int C = 0;

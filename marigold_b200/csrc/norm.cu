@@ -354,6 +354,171 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
   }
 }
 
+// -------------------------------------------------------------------------------------------------
+// Cross attention against the FIXED two-token empty-prompt context, collapsed algebraically, fused with the LayerNorm
+// before it (norm2) and the one after it (norm3) — one launch instead of LayerNorm + to_q GEMM + attention + to_out GEMM
+// + LayerNorm (reference: attn2 of diffusers' BasicTransformerBlock, reached from marigold_depth_pipeline.py:461-463; the
+// context is always CLIP(""), :381-394,438-442).
+//   softmax over 2 keys: w0 = sigmoid((q . (k0 - k1)) / sqrt(64)) per head, w1 = 1 - w0, and with q = Wq z:
+//       q_h . dk_h = z . G_h,            G_h = Wq[h-block, :]^T dk_h                    (G: [H, C])
+//   attention output per head = v1_h + w0_h (v0_h - v1_h), and through to_out:
+//       Wo a + bo = c1 + sum_h w0_h U_h, c1 = Wo v1 + bo,  U_h = Wo[:, h-block] (v0 - v1)_h   (U: [H, C])
+//   so the block is   y = x + c1 + sum_h sigmoid(scale * LN2(x) . G_h) U_h   — exact, C (2 H) MACs per token instead of
+//   2 C^2, all in fp32 (the two GEMMs it replaces rounded z, q, a to bf16).
+// x fp32 [M, C] -> y fp32 [M, C] (residual trunk) and a_out bf16 [M, C] = LN3(y) (operand of the feed-forward GEMM).
+// -------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+    xattn2_fused_kernel(const float* __restrict__ x, float* __restrict__ y, bf16* __restrict__ a_out,
+                        const float* __restrict__ g2, const float* __restrict__ b2, const float* __restrict__ g3,
+                        const float* __restrict__ b3, const float* __restrict__ G, const float* __restrict__ U,
+                        const float* __restrict__ c1, int M, int C, int H, float scale, float eps) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= M) return;
+  const int Q = C / 4;
+  const float4* xr = reinterpret_cast<const float4*>(x + (size_t)warp * C);
+  float4 v[kLnMaxQ];
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < kLnMaxQ; ++k) {
+    const int q = lane + 32 * k;
+    if (q < Q) { v[k] = __ldg(xr + q); s += v[k].x + v[k].y + v[k].z + v[k].w; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  float mean = s / C, ss = 0.f;
+#pragma unroll
+  for (int k = 0; k < kLnMaxQ; ++k) {
+    const int q = lane + 32 * k;
+    if (q < Q) {
+      const float a = v[k].x - mean, b = v[k].y - mean, c = v[k].z - mean, d = v[k].w - mean;
+      ss += a * a + b * b + c * c + d * d;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  float rstd = rsqrtf(ss / C + eps);
+  // z = LN2(x) (kept in registers), y starts as x + c1
+  float4 z[kLnMaxQ], acc[kLnMaxQ];
+#pragma unroll
+  for (int k = 0; k < kLnMaxQ; ++k) {
+    const int q = lane + 32 * k;
+    if (q < Q) {
+      const float4 ga = __ldg(reinterpret_cast<const float4*>(g2) + q), be = __ldg(reinterpret_cast<const float4*>(b2) + q);
+      const float4 cc = __ldg(reinterpret_cast<const float4*>(c1) + q);
+      z[k] = make_float4((v[k].x - mean) * rstd * ga.x + be.x, (v[k].y - mean) * rstd * ga.y + be.y,
+                         (v[k].z - mean) * rstd * ga.z + be.z, (v[k].w - mean) * rstd * ga.w + be.w);
+      acc[k] = make_float4(v[k].x + cc.x, v[k].y + cc.y, v[k].z + cc.z, v[k].w + cc.w);
+    }
+  }
+#pragma unroll 1
+  for (int h = 0; h < H; ++h) {
+    const float4* Gh = reinterpret_cast<const float4*>(G + (size_t)h * C);
+    float d = 0.f;
+#pragma unroll
+    for (int k = 0; k < kLnMaxQ; ++k) {
+      const int q = lane + 32 * k;
+      if (q < Q) {
+        const float4 g = __ldg(Gh + q);
+        d += z[k].x * g.x + z[k].y * g.y + z[k].z * g.z + z[k].w * g.w;
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+    const float w0 = 1.0f / (1.0f + __expf(-d * scale));
+    const float4* Uh = reinterpret_cast<const float4*>(U + (size_t)h * C);
+#pragma unroll
+    for (int k = 0; k < kLnMaxQ; ++k) {
+      const int q = lane + 32 * k;
+      if (q < Q) {
+        const float4 u = __ldg(Uh + q);
+        acc[k].x = fmaf(w0, u.x, acc[k].x); acc[k].y = fmaf(w0, u.y, acc[k].y);
+        acc[k].z = fmaf(w0, u.z, acc[k].z); acc[k].w = fmaf(w0, u.w, acc[k].w);
+      }
+    }
+  }
+  // store the trunk, then LN3 of the same row
+  float4* yr = reinterpret_cast<float4*>(y + (size_t)warp * C);
+  s = 0.f;
+#pragma unroll
+  for (int k = 0; k < kLnMaxQ; ++k) {
+    const int q = lane + 32 * k;
+    if (q < Q) { yr[q] = acc[k]; s += acc[k].x + acc[k].y + acc[k].z + acc[k].w; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  mean = s / C; ss = 0.f;
+#pragma unroll
+  for (int k = 0; k < kLnMaxQ; ++k) {
+    const int q = lane + 32 * k;
+    if (q < Q) {
+      const float a = acc[k].x - mean, b = acc[k].y - mean, c = acc[k].z - mean, d = acc[k].w - mean;
+      ss += a * a + b * b + c * c + d * d;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  rstd = rsqrtf(ss / C + eps);
+  uint2* ar = reinterpret_cast<uint2*>(a_out + (size_t)warp * C);
+#pragma unroll
+  for (int k = 0; k < kLnMaxQ; ++k) {
+    const int q = lane + 32 * k;
+    if (q < Q) {
+      const float4 ga = __ldg(reinterpret_cast<const float4*>(g3) + q), be = __ldg(reinterpret_cast<const float4*>(b3) + q);
+      const float o0 = (acc[k].x - mean) * rstd * ga.x + be.x, o1 = (acc[k].y - mean) * rstd * ga.y + be.y;
+      const float o2 = (acc[k].z - mean) * rstd * ga.z + be.z, o3 = (acc[k].w - mean) * rstd * ga.w + be.w;
+      ar[q] = make_uint2(pack_bf16x2(o0, o1), pack_bf16x2(o2, o3));
+    }
+  }
+}
+
+int launch_xattn2_fused(const float* x, float* y, bf16* a_out, const float* g2, const float* b2, const float* g3,
+                        const float* b3, const float* G, const float* U, const float* c1, int M, int C, int H, float scale,
+                        float eps, cudaStream_t stream) {
+  if (C % 4 != 0 || C / 4 > 32 * kLnMaxQ || H < 1) { set_error("xattn2: unsupported C=%d H=%d", C, H); return MGB_ERR_INVALID; }
+  const int warps_per_block = 8;
+  const int blocks = (M + warps_per_block - 1) / warps_per_block;
+  launch_k(xattn2_fused_kernel, blocks, 256, 0, stream, x, y, a_out, g2, b2, g3, b3, G, U, c1, M, C, H, scale, eps);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { set_error("xattn2 launch: %s", cudaGetErrorString(e)); return MGB_ERR_CUDA; }
+  return MGB_OK;
+}
+
+// One-time folding of the empty-prompt context into G [H, C], U [H, C], c1 [C] (see above). wq, wo fp32 [C, C] in the
+// PyTorch [out, in] layout; kv fp32 [2 (k | v), 2 tokens, C]; bo fp32 [C].
+__global__ void xattn2_fold_kernel(const float* __restrict__ wq, const float* __restrict__ wo, const float* __restrict__ bo,
+                                   const float* __restrict__ kv, float* __restrict__ G, float* __restrict__ U,
+                                   float* __restrict__ c1, int C, int H) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= C * (H + 1)) return;
+  const int c = i % C, h = i / C;
+  const float* k0 = kv; const float* k1 = kv + C; const float* v0 = kv + 2 * C; const float* v1 = kv + 3 * C;
+  if (h < H) {
+    float g = 0.f, u = 0.f;
+    for (int d = 0; d < 64; ++d) {
+      const int j = h * 64 + d;
+      g = fmaf(wq[(size_t)j * C + c], k0[j] - k1[j], g);
+      u = fmaf(wo[(size_t)c * C + j], v0[j] - v1[j], u);
+    }
+    G[(size_t)h * C + c] = g;
+    U[(size_t)h * C + c] = u;
+  } else {
+    float a = bo ? bo[c] : 0.f;
+    for (int j = 0; j < C; ++j) a = fmaf(wo[(size_t)c * C + j], v1[j], a);
+    c1[c] = a;
+  }
+}
+int launch_xattn2_fold(const float* wq, const float* wo, const float* bo, const float* kv, float* G, float* U, float* c1,
+                       int C, cudaStream_t stream) {
+  const int H = C / 64, n = C * (H + 1);
+  xattn2_fold_kernel<<<(n + 255) / 256, 256, 0, stream>>>(wq, wo, bo, kv, G, U, c1, C, H);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { set_error("xattn2 fold launch: %s", cudaGetErrorString(e)); return MGB_ERR_CUDA; }
+  return MGB_OK;
+}
+
 int launch_layernorm(const float* x, bf16* y, const float* gamma, const float* beta, int M, int C, float eps,
                      cudaStream_t stream) {
   if (C % 4 != 0 || C / 4 > 32 * kLnMaxQ) {
