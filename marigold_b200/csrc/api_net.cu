@@ -441,14 +441,16 @@ int mgb_set_text_embedding(mgb_handle* h, const float* embed_host, int32_t n_tok
     }
     TRY(launch_linear_small(d_ctx, x.k2w, nullptr, x.kv, n_tokens, x.C, ctx, 0, 0, nullptr));
     TRY(launch_linear_small(d_ctx, x.v2w, nullptr, x.kv + size_t(n_tokens) * x.C, n_tokens, x.C, ctx, 0, 0, nullptr));
-    if (!x.xG) {
+    if (!x.xGU) {
       const int H = x.C / 64;
-      void* g = nullptr;
-      CUDA_TRY(cudaMalloc(&g, (size_t(2) * H + 1) * x.C * 4));
+      void *g = nullptr, *c1 = nullptr;
+      CUDA_TRY(cudaMalloc(&g, size_t(2) * H * x.C * 2));
       h->dev_allocs.push_back(g);
-      x.xG = static_cast<float*>(g); x.xU = x.xG + size_t(H) * x.C; x.xc1 = x.xU + size_t(H) * x.C;
+      CUDA_TRY(cudaMalloc(&c1, size_t(x.C) * 4));
+      h->dev_allocs.push_back(c1);
+      x.xGU = static_cast<bf16*>(g); x.xc1 = static_cast<float*>(c1);
     }
-    TRY(launch_xattn2_fold(x.q2w, x.o2w, x.o2b, x.kv, x.xG, x.xU, x.xc1, x.C, nullptr));
+    TRY(launch_xattn2_fold(x.q2w, x.o2w, x.o2b, x.kv, x.xGU, x.xc1, x.C, nullptr));
     count_launch(3);
   }
   CUDA_TRY(cudaDeviceSynchronize());

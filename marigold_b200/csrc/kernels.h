@@ -120,10 +120,10 @@ int launch_layernorm(const float* x, bf16* y, const float* gamma, const float* b
 // Collapsed cross attention against the fixed 2-token context, fused with norm2 and norm3 (norm.cu):
 //   y = x + c1 + sum_h sigmoid(scale * LN2(x) . G_h) U_h ;  a_out = bf16(LN3(y))
 int launch_xattn2_fused(const float* x, float* y, bf16* a_out, const float* g2, const float* b2, const float* g3,
-                        const float* b3, const float* G, const float* U, const float* c1, int M, int C, int H, float scale,
-                        float eps, cudaStream_t stream);
-int launch_xattn2_fold(const float* wq, const float* wo, const float* bo, const float* kv, float* G, float* U, float* c1,
-                       int C, cudaStream_t stream);
+                        const float* b3, const bf16* GU, const float* c1, int M, int C, int H, float scale, float eps,
+                        cudaStream_t stream);
+int launch_xattn2_fold(const float* wq, const float* wo, const float* bo, const float* kv, bf16* GU, float* c1, int C,
+                       cudaStream_t stream);
 // y[NB, 4, ceil(H/2), ceil(W/2), C] (parity planes p = (h&1)*2 + (w&1), zero where the source pixel does not exist) from
 // x fp32 [NB, H, W, C]
 int launch_space_to_depth(const float* x, bf16* y, int NB, int H, int W, int C, cudaStream_t stream);

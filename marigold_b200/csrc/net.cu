@@ -215,7 +215,7 @@ static int xfmr_forward(Ctx& c, const XfmrW& X, Act& x, Act& y, int NB, int T) {
   // cross attention against the empty-prompt context, collapsed (norm.cu: xattn2_fused_kernel): LN2, to_q, the 2-key
   // softmax, to_out + residual and LN3 are one launch; hs0 = trunk after attn2, a = LN3(hs0) for the feed-forward
   if (!no_x) {
-    LAUNCH(launch_xattn2_fused(hs1, hs0, a, X.ln2.g, X.ln2.b, X.ln3.g, X.ln3.b, X.xG, X.xU, X.xc1, int(M), C, C / 64, 0.125f,
+    LAUNCH(launch_xattn2_fused(hs1, hs0, a, X.ln2.g, X.ln2.b, X.ln3.g, X.ln3.b, X.xGU, X.xc1, int(M), C, C / 64, 0.125f,
                                1e-5f, c.stream), 1);
   }
   // GEGLU feed-forward

@@ -58,9 +58,8 @@ struct XfmrW {
   float* k2w = nullptr;  // to_k   fp32 [C, ctx]
   float* v2w = nullptr;  // to_v
   float* kv = nullptr;   // fp32 [2 (k|v), n_ctx, C]
-  float* xG = nullptr;   // [H, C]  G_h = Wq[h-block]^T (k0 - k1)_h
-  float* xU = nullptr;   // [H, C]  U_h = Wo[:, h-block] (v0 - v1)_h
-  float* xc1 = nullptr;  // [C]     Wo v1 + bo
+  bf16* xGU = nullptr;   // [2][H, C]  G_h = Wq[h-block]^T (k0 - k1)_h ; U_h = Wo[:, h-block] (v0 - v1)_h
+  float* xc1 = nullptr;  // [C]        Wo v1 + bo
 };
 struct VaeAttnW {
   int C = 0;

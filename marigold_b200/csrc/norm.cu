@@ -367,149 +367,173 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
 //   2 C^2, all in fp32 (the two GEMMs it replaces rounded z, q, a to bf16).
 // x fp32 [M, C] -> y fp32 [M, C] (residual trunk) and a_out bf16 [M, C] = LN3(y) (operand of the feed-forward GEMM).
 // -------------------------------------------------------------------------------------------------
-// HT: number of heads when it is one of the SD-2 values (5, 10, 20: loops fully unrolled so that the G / U loads of all
-// heads are independent and in flight together), 0 = generic (rolled). The first version walked the heads with a
-// dependent load -> dot -> shuffle -> sigmoid -> load -> accumulate chain per head: 28-56 us per launch, 1.85 ms per step.
-template <int HT>
+// Persistent blocks with the folded tables in shared memory (G, U as bf16 [H][C]; c1 and the two LayerNorm affines fp32):
+// the first versions re-read G and U from L1 / L2 for every token (13-205 KB per token against 1-5 KB of activations)
+// and ran at 28-60 us per launch; from shared memory the tables cost one conflict-free LDS.64 per quad and head.
+// One warp per token, tokens strided over the grid.
+__device__ __forceinline__ float4 bf16x4_to_f4(uint2 v) {
+  const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&v.x), b = *reinterpret_cast<const __nv_bfloat162*>(&v.y);
+  return make_float4(__bfloat162float(a.x), __bfloat162float(a.y), __bfloat162float(b.x), __bfloat162float(b.y));
+}
+
 __global__ void __launch_bounds__(256)
     xattn2_fused_kernel(const float* __restrict__ x, float* __restrict__ y, bf16* __restrict__ a_out,
                         const float* __restrict__ g2, const float* __restrict__ b2, const float* __restrict__ g3,
-                        const float* __restrict__ b3, const float* __restrict__ G, const float* __restrict__ U,
+                        const float* __restrict__ b3, const bf16* __restrict__ GU /* [2][H][C] */,
                         const float* __restrict__ c1, int M, int C, int H, float scale, float eps) {
+  extern __shared__ __align__(16) uint8_t xs_raw[];
   pdl_launch_dependents();
-  pdl_wait();
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (warp >= M) return;
   const int Q = C / 4;
-  const float4* xr = reinterpret_cast<const float4*>(x + (size_t)warp * C);
-  float4 z[kLnMaxQ], acc[kLnMaxQ];
-  float s = 0.f;
+  uint2* sG = reinterpret_cast<uint2*>(xs_raw);                       // [H][Q] bf16x4
+  uint2* sU = sG + (size_t)H * Q;
+  float4* sP = reinterpret_cast<float4*>(sU + (size_t)H * Q);         // [5][Q]: c1, g2, b2, g3, b3
+  {
+    // static weights: may be read before the predecessor kernel has finished
+    const uint2* src = reinterpret_cast<const uint2*>(GU);
+    for (int i = threadIdx.x; i < 2 * H * Q; i += blockDim.x) sG[i] = __ldg(src + i);
+    const float* ps[5] = {c1, g2, b2, g3, b3};
 #pragma unroll
-  for (int k = 0; k < kLnMaxQ; ++k) {
-    const int q = lane + 32 * k;
-    if (q < Q) { acc[k] = __ldg(xr + q); s += acc[k].x + acc[k].y + acc[k].z + acc[k].w; }
+    for (int k = 0; k < 5; ++k)
+      for (int i = threadIdx.x; i < Q; i += blockDim.x) sP[k * Q + i] = __ldg(reinterpret_cast<const float4*>(ps[k]) + i);
   }
+  __syncthreads();
+  pdl_wait();
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  for (int tok = blockIdx.x * wpb + (threadIdx.x >> 5); tok < M; tok += gridDim.x * wpb) {
+    const float4* xr = reinterpret_cast<const float4*>(x + (size_t)tok * C);
+    float4 z[kLnMaxQ], acc[kLnMaxQ];
+    float s = 0.f;
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-  float mean = s / C, ss = 0.f;
-#pragma unroll
-  for (int k = 0; k < kLnMaxQ; ++k) {
-    const int q = lane + 32 * k;
-    if (q < Q) {
-      const float a = acc[k].x - mean, b = acc[k].y - mean, c = acc[k].z - mean, d = acc[k].w - mean;
-      ss += a * a + b * b + c * c + d * d;
+    for (int k = 0; k < kLnMaxQ; ++k) {
+      const int q = lane + 32 * k;
+      if (q < Q) { acc[k] = __ldg(xr + q); s += acc[k].x + acc[k].y + acc[k].z + acc[k].w; }
     }
-  }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-  float rstd = rsqrtf(ss / C + eps);
-  // z = LN2(x); acc becomes x + c1
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    float mean = s / C, ss = 0.f;
 #pragma unroll
-  for (int k = 0; k < kLnMaxQ; ++k) {
-    const int q = lane + 32 * k;
-    if (q < Q) {
-      const float4 ga = __ldg(reinterpret_cast<const float4*>(g2) + q), be = __ldg(reinterpret_cast<const float4*>(b2) + q);
-      const float4 cc = __ldg(reinterpret_cast<const float4*>(c1) + q);
-      z[k] = make_float4((acc[k].x - mean) * rstd * ga.x + be.x, (acc[k].y - mean) * rstd * ga.y + be.y,
-                         (acc[k].z - mean) * rstd * ga.z + be.z, (acc[k].w - mean) * rstd * ga.w + be.w);
-      acc[k] = make_float4(acc[k].x + cc.x, acc[k].y + cc.y, acc[k].z + cc.z, acc[k].w + cc.w);
+    for (int k = 0; k < kLnMaxQ; ++k) {
+      const int q = lane + 32 * k;
+      if (q < Q) {
+        const float a = acc[k].x - mean, b = acc[k].y - mean, c = acc[k].z - mean, d = acc[k].w - mean;
+        ss += a * a + b * b + c * c + d * d;
+      }
     }
-  }
-  constexpr int HB = HT > 0 ? HT : 4;       // heads per batch (all of them when HT is known)
-  for (int h0 = 0; h0 < H; h0 += HB) {
-    float d[HB];
 #pragma unroll
-    for (int j = 0; j < HB; ++j) {
-      d[j] = 0.f;
-      if (h0 + j < H) {
-        const float4* Gh = reinterpret_cast<const float4*>(G + (size_t)(h0 + j) * C);
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    float rstd = rsqrtf(ss / C + eps);
+    // z = LN2(x); acc becomes x + c1
 #pragma unroll
-        for (int k = 0; k < kLnMaxQ; ++k) {
-          const int q = lane + 32 * k;
-          if (q < Q) {
-            const float4 g = __ldg(Gh + q);
-            d[j] += z[k].x * g.x + z[k].y * g.y + z[k].z * g.z + z[k].w * g.w;
+    for (int k = 0; k < kLnMaxQ; ++k) {
+      const int q = lane + 32 * k;
+      if (q < Q) {
+        const float4 cc = sP[q], ga = sP[Q + q], be = sP[2 * Q + q];
+        z[k] = make_float4((acc[k].x - mean) * rstd * ga.x + be.x, (acc[k].y - mean) * rstd * ga.y + be.y,
+                           (acc[k].z - mean) * rstd * ga.z + be.z, (acc[k].w - mean) * rstd * ga.w + be.w);
+        acc[k] = make_float4(acc[k].x + cc.x, acc[k].y + cc.y, acc[k].z + cc.z, acc[k].w + cc.w);
+      }
+    }
+    for (int h0 = 0; h0 < H; h0 += 4) {
+      float d[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        d[j] = 0.f;
+        if (h0 + j < H) {
+          const uint2* Gh = sG + (size_t)(h0 + j) * Q;
+#pragma unroll
+          for (int k = 0; k < kLnMaxQ; ++k) {
+            const int q = lane + 32 * k;
+            if (q < Q) {
+              const float4 g = bf16x4_to_f4(Gh[q]);
+              d[j] += z[k].x * g.x + z[k].y * g.y + z[k].z * g.z + z[k].w * g.w;
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) d[j] += __shfl_xor_sync(0xffffffffu, d[j], o);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (h0 + j < H) {
+          const float w0 = 1.0f / (1.0f + __expf(-d[j] * scale));
+          const uint2* Uh = sU + (size_t)(h0 + j) * Q;
+#pragma unroll
+          for (int k = 0; k < kLnMaxQ; ++k) {
+            const int q = lane + 32 * k;
+            if (q < Q) {
+              const float4 u = bf16x4_to_f4(Uh[q]);
+              acc[k].x = fmaf(w0, u.x, acc[k].x); acc[k].y = fmaf(w0, u.y, acc[k].y);
+              acc[k].z = fmaf(w0, u.z, acc[k].z); acc[k].w = fmaf(w0, u.w, acc[k].w);
+            }
           }
         }
       }
     }
+    // store the trunk, then LN3 of the same row
+    float4* yr = reinterpret_cast<float4*>(y + (size_t)tok * C);
+    s = 0.f;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1)
+    for (int k = 0; k < kLnMaxQ; ++k) {
+      const int q = lane + 32 * k;
+      if (q < Q) { yr[q] = acc[k]; s += acc[k].x + acc[k].y + acc[k].z + acc[k].w; }
+    }
 #pragma unroll
-      for (int j = 0; j < HB; ++j) d[j] += __shfl_xor_sync(0xffffffffu, d[j], o);
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    mean = s / C; ss = 0.f;
 #pragma unroll
-    for (int j = 0; j < HB; ++j) {
-      if (h0 + j < H) {
-        const float w0 = 1.0f / (1.0f + __expf(-d[j] * scale));
-        const float4* Uh = reinterpret_cast<const float4*>(U + (size_t)(h0 + j) * C);
-#pragma unroll
-        for (int k = 0; k < kLnMaxQ; ++k) {
-          const int q = lane + 32 * k;
-          if (q < Q) {
-            const float4 u = __ldg(Uh + q);
-            acc[k].x = fmaf(w0, u.x, acc[k].x); acc[k].y = fmaf(w0, u.y, acc[k].y);
-            acc[k].z = fmaf(w0, u.z, acc[k].z); acc[k].w = fmaf(w0, u.w, acc[k].w);
-          }
-        }
+    for (int k = 0; k < kLnMaxQ; ++k) {
+      const int q = lane + 32 * k;
+      if (q < Q) {
+        const float a = acc[k].x - mean, b = acc[k].y - mean, c = acc[k].z - mean, d2 = acc[k].w - mean;
+        ss += a * a + b * b + c * c + d2 * d2;
       }
     }
-  }
-  // store the trunk, then LN3 of the same row
-  float4* yr = reinterpret_cast<float4*>(y + (size_t)warp * C);
-  s = 0.f;
 #pragma unroll
-  for (int k = 0; k < kLnMaxQ; ++k) {
-    const int q = lane + 32 * k;
-    if (q < Q) { yr[q] = acc[k]; s += acc[k].x + acc[k].y + acc[k].z + acc[k].w; }
-  }
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    rstd = rsqrtf(ss / C + eps);
+    uint2* ar = reinterpret_cast<uint2*>(a_out + (size_t)tok * C);
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-  mean = s / C; ss = 0.f;
-#pragma unroll
-  for (int k = 0; k < kLnMaxQ; ++k) {
-    const int q = lane + 32 * k;
-    if (q < Q) {
-      const float a = acc[k].x - mean, b = acc[k].y - mean, c = acc[k].z - mean, d2 = acc[k].w - mean;
-      ss += a * a + b * b + c * c + d2 * d2;
-    }
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-  rstd = rsqrtf(ss / C + eps);
-  uint2* ar = reinterpret_cast<uint2*>(a_out + (size_t)warp * C);
-#pragma unroll
-  for (int k = 0; k < kLnMaxQ; ++k) {
-    const int q = lane + 32 * k;
-    if (q < Q) {
-      const float4 ga = __ldg(reinterpret_cast<const float4*>(g3) + q), be = __ldg(reinterpret_cast<const float4*>(b3) + q);
-      const float o0 = (acc[k].x - mean) * rstd * ga.x + be.x, o1 = (acc[k].y - mean) * rstd * ga.y + be.y;
-      const float o2 = (acc[k].z - mean) * rstd * ga.z + be.z, o3 = (acc[k].w - mean) * rstd * ga.w + be.w;
-      ar[q] = make_uint2(pack_bf16x2(o0, o1), pack_bf16x2(o2, o3));
+    for (int k = 0; k < kLnMaxQ; ++k) {
+      const int q = lane + 32 * k;
+      if (q < Q) {
+        const float4 ga = sP[3 * Q + q], be = sP[4 * Q + q];
+        const float o0 = (acc[k].x - mean) * rstd * ga.x + be.x, o1 = (acc[k].y - mean) * rstd * ga.y + be.y;
+        const float o2 = (acc[k].z - mean) * rstd * ga.z + be.z, o3 = (acc[k].w - mean) * rstd * ga.w + be.w;
+        ar[q] = make_uint2(pack_bf16x2(o0, o1), pack_bf16x2(o2, o3));
+      }
     }
   }
 }
 
 int launch_xattn2_fused(const float* x, float* y, bf16* a_out, const float* g2, const float* b2, const float* g3,
-                        const float* b3, const float* G, const float* U, const float* c1, int M, int C, int H, float scale,
-                        float eps, cudaStream_t stream) {
+                        const float* b3, const bf16* GU, const float* c1, int M, int C, int H, float scale, float eps,
+                        cudaStream_t stream) {
   if (C % 4 != 0 || C / 4 > 32 * kLnMaxQ || H < 1) { set_error("xattn2: unsupported C=%d H=%d", C, H); return MGB_ERR_INVALID; }
+  const size_t smem = size_t(2) * H * C * 2 + size_t(5) * C * 4;
+  if (smem > 200 * 1024) { set_error("xattn2: C=%d H=%d needs %zu B of shared memory", C, H, smem); return MGB_ERR_INVALID; }
+  static size_t attr_bytes = 0;
+  if (smem > attr_bytes) {
+    cudaError_t e = cudaFuncSetAttribute(xattn2_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) { set_error("xattn2 attr: %s", cudaGetErrorString(e)); return MGB_ERR_CUDA; }
+    attr_bytes = 200 * 1024;
+  }
   const int warps_per_block = 8;
-  const int blocks = (M + warps_per_block - 1) / warps_per_block;
-  cudaError_t e;
-  if (H == 5) e = launch_k(xattn2_fused_kernel<5>, blocks, 256, 0, stream, x, y, a_out, g2, b2, g3, b3, G, U, c1, M, C, H, scale, eps);
-  else if (H == 10) e = launch_k(xattn2_fused_kernel<10>, blocks, 256, 0, stream, x, y, a_out, g2, b2, g3, b3, G, U, c1, M, C, H, scale, eps);
-  else if (H == 20) e = launch_k(xattn2_fused_kernel<20>, blocks, 256, 0, stream, x, y, a_out, g2, b2, g3, b3, G, U, c1, M, C, H, scale, eps);
-  else e = launch_k(xattn2_fused_kernel<0>, blocks, 256, 0, stream, x, y, a_out, g2, b2, g3, b3, G, U, c1, M, C, H, scale, eps);
+  int per_sm = int(std::min<size_t>(4, (220 * 1024) / (smem + 1024)));
+  if (per_sm < 1) per_sm = 1;
+  const int blocks = std::max(1, std::min((M + warps_per_block - 1) / warps_per_block, 148 * per_sm));
+  cudaError_t e = launch_k(xattn2_fused_kernel, blocks, 256, smem, stream, x, y, a_out, g2, b2, g3, b3, GU, c1, M, C, H, scale, eps);
   if (e == cudaSuccess) e = cudaGetLastError();
   if (e != cudaSuccess) { set_error("xattn2 launch: %s", cudaGetErrorString(e)); return MGB_ERR_CUDA; }
   return MGB_OK;
 }
 
-// One-time folding of the empty-prompt context into G [H, C], U [H, C], c1 [C] (see above). wq, wo fp32 [C, C] in the
+// One-time folding of the empty-prompt context into the bf16 tables GU = [G | U] ([2][H][C]) and c1 [C] (see above). wq, wo fp32 [C, C] in the
 // PyTorch [out, in] layout; kv fp32 [2 (k | v), 2 tokens, C]; bo fp32 [C].
 __global__ void xattn2_fold_kernel(const float* __restrict__ wq, const float* __restrict__ wo, const float* __restrict__ bo,
-                                   const float* __restrict__ kv, float* __restrict__ G, float* __restrict__ U,
+                                   const float* __restrict__ kv, bf16* __restrict__ GU /* [2][H][C] */,
                                    float* __restrict__ c1, int C, int H) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= C * (H + 1)) return;
@@ -522,18 +546,18 @@ __global__ void xattn2_fold_kernel(const float* __restrict__ wq, const float* __
       g = fmaf(wq[(size_t)j * C + c], k0[j] - k1[j], g);
       u = fmaf(wo[(size_t)c * C + j], v0[j] - v1[j], u);
     }
-    G[(size_t)h * C + c] = g;
-    U[(size_t)h * C + c] = u;
+    GU[(size_t)h * C + c] = __float2bfloat16(g);
+    GU[((size_t)H + h) * C + c] = __float2bfloat16(u);
   } else {
     float a = bo ? bo[c] : 0.f;
     for (int j = 0; j < C; ++j) a = fmaf(wo[(size_t)c * C + j], v1[j], a);
     c1[c] = a;
   }
 }
-int launch_xattn2_fold(const float* wq, const float* wo, const float* bo, const float* kv, float* G, float* U, float* c1,
-                       int C, cudaStream_t stream) {
+int launch_xattn2_fold(const float* wq, const float* wo, const float* bo, const float* kv, bf16* GU, float* c1, int C,
+                       cudaStream_t stream) {
   const int H = C / 64, n = C * (H + 1);
-  xattn2_fold_kernel<<<(n + 255) / 256, 256, 0, stream>>>(wq, wo, bo, kv, G, U, c1, C, H);
+  xattn2_fold_kernel<<<(n + 255) / 256, 256, 0, stream>>>(wq, wo, bo, kv, GU, c1, C, H);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { set_error("xattn2 fold launch: %s", cudaGetErrorString(e)); return MGB_ERR_CUDA; }
   return MGB_OK;
