@@ -124,6 +124,13 @@ __device__ __forceinline__ void tma_load_5d_a(uint32_t dst, const CUtensorMap* m
       : "memory");
 }
 
+// 1-D bulk copy global -> shared (size a multiple of 16 B, both addresses 16 B aligned), completion on an mbarrier
+__device__ __forceinline__ void bulk_copy_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst_smem)), "l"(reinterpret_cast<uint64_t>(src_gmem)), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
 // explicit shared-space 128-bit accesses (pointer arithmetic on the aligned dynamic-smem base decays to
 // generic addressing otherwise)
 __device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
