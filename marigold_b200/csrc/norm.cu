@@ -376,7 +376,10 @@ __device__ __forceinline__ float4 bf16x4_to_f4(uint2 v) {
   return make_float4(__bfloat162float(a.x), __bfloat162float(a.y), __bfloat162float(b.x), __bfloat162float(b.y));
 }
 
-__global__ void __launch_bounds__(256)
+// QL: quads per lane (ceil(C / 128)): 3 / 5 / 10 for C = 320 / 640 / 1280 — sized exactly so that the small-C levels run at
+// 4 blocks per SM (the generic 10-slot version needed 128 registers: 16 warps per SM for a latency-bound kernel)
+template <int QL>
+__global__ void __launch_bounds__(256, QL <= 3 ? 4 : QL <= 5 ? 3 : 1)
     xattn2_fused_kernel(const float* __restrict__ x, float* __restrict__ y, bf16* __restrict__ a_out,
                         const float* __restrict__ g2, const float* __restrict__ b2, const float* __restrict__ g3,
                         const float* __restrict__ b3, const bf16* __restrict__ GU /* [2][H][C] */,
@@ -409,10 +412,10 @@ __global__ void __launch_bounds__(256)
   const int wpb = blockDim.x >> 5;
   for (int tok = blockIdx.x * wpb + (threadIdx.x >> 5); tok < M; tok += gridDim.x * wpb) {
     const float4* xr = reinterpret_cast<const float4*>(x + (size_t)tok * C);
-    float4 z[kLnMaxQ], acc[kLnMaxQ];
+    float4 z[QL], acc[QL];
     float s = 0.f;
 #pragma unroll
-    for (int k = 0; k < kLnMaxQ; ++k) {
+    for (int k = 0; k < QL; ++k) {
       const int q = lane + 32 * k;
       if (q < Q) { acc[k] = __ldg(xr + q); s += acc[k].x + acc[k].y + acc[k].z + acc[k].w; }
     }
@@ -420,7 +423,7 @@ __global__ void __launch_bounds__(256)
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     float mean = s / C, ss = 0.f;
 #pragma unroll
-    for (int k = 0; k < kLnMaxQ; ++k) {
+    for (int k = 0; k < QL; ++k) {
       const int q = lane + 32 * k;
       if (q < Q) {
         const float a = acc[k].x - mean, b = acc[k].y - mean, c = acc[k].z - mean, d = acc[k].w - mean;
@@ -432,7 +435,7 @@ __global__ void __launch_bounds__(256)
     float rstd = rsqrtf(ss / C + eps);
     // z = LN2(x); acc becomes x + c1
 #pragma unroll
-    for (int k = 0; k < kLnMaxQ; ++k) {
+    for (int k = 0; k < QL; ++k) {
       const int q = lane + 32 * k;
       if (q < Q) {
         const float4 cc = sP[q], ga = sP[Q + q], be = sP[2 * Q + q];
@@ -449,7 +452,7 @@ __global__ void __launch_bounds__(256)
         if (h0 + j < H) {
           const uint2* Gh = sG + (size_t)(h0 + j) * Q;
 #pragma unroll
-          for (int k = 0; k < kLnMaxQ; ++k) {
+          for (int k = 0; k < QL; ++k) {
             const int q = lane + 32 * k;
             if (q < Q) {
               const float4 g = bf16x4_to_f4(Gh[q]);
@@ -468,7 +471,7 @@ __global__ void __launch_bounds__(256)
           const float w0 = 1.0f / (1.0f + __expf(-d[j] * scale));
           const uint2* Uh = sU + (size_t)(h0 + j) * Q;
 #pragma unroll
-          for (int k = 0; k < kLnMaxQ; ++k) {
+          for (int k = 0; k < QL; ++k) {
             const int q = lane + 32 * k;
             if (q < Q) {
               const float4 u = bf16x4_to_f4(Uh[q]);
@@ -483,7 +486,7 @@ __global__ void __launch_bounds__(256)
     float4* yr = reinterpret_cast<float4*>(y + (size_t)tok * C);
     s = 0.f;
 #pragma unroll
-    for (int k = 0; k < kLnMaxQ; ++k) {
+    for (int k = 0; k < QL; ++k) {
       const int q = lane + 32 * k;
       if (q < Q) { yr[q] = acc[k]; s += acc[k].x + acc[k].y + acc[k].z + acc[k].w; }
     }
@@ -491,7 +494,7 @@ __global__ void __launch_bounds__(256)
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     mean = s / C; ss = 0.f;
 #pragma unroll
-    for (int k = 0; k < kLnMaxQ; ++k) {
+    for (int k = 0; k < QL; ++k) {
       const int q = lane + 32 * k;
       if (q < Q) {
         const float a = acc[k].x - mean, b = acc[k].y - mean, c = acc[k].z - mean, d2 = acc[k].w - mean;
@@ -503,7 +506,7 @@ __global__ void __launch_bounds__(256)
     rstd = rsqrtf(ss / C + eps);
     uint2* ar = reinterpret_cast<uint2*>(a_out + (size_t)tok * C);
 #pragma unroll
-    for (int k = 0; k < kLnMaxQ; ++k) {
+    for (int k = 0; k < QL; ++k) {
       const int q = lane + 32 * k;
       if (q < Q) {
         const float4 ga = sP[3 * Q + q], be = sP[4 * Q + q];
@@ -521,17 +524,23 @@ int launch_xattn2_fused(const float* x, float* y, bf16* a_out, const float* g2, 
   if (C % 4 != 0 || C / 4 > 32 * kLnMaxQ || H < 1) { set_error("xattn2: unsupported C=%d H=%d", C, H); return MGB_ERR_INVALID; }
   const size_t smem = size_t(2) * H * C * 2 + size_t(5) * C * 4;
   if (smem > 200 * 1024) { set_error("xattn2: C=%d H=%d needs %zu B of shared memory", C, H, smem); return MGB_ERR_INVALID; }
-  static size_t attr_bytes = 0;
-  if (smem > attr_bytes) {
-    cudaError_t e = cudaFuncSetAttribute(xattn2_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  const int ql = (C / 4 + 31) / 32;
+  void (*kern)(const float*, float*, bf16*, const float*, const float*, const float*, const float*, const bf16*, const float*,
+               int, int, int, float, float) =
+      ql <= 3 ? xattn2_fused_kernel<3> : ql <= 5 ? xattn2_fused_kernel<5> : xattn2_fused_kernel<10>;
+  static bool attr_set[3] = {false, false, false};
+  const int vi = ql <= 3 ? 0 : ql <= 5 ? 1 : 2;
+  if (!attr_set[vi]) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) { set_error("xattn2 attr: %s", cudaGetErrorString(e)); return MGB_ERR_CUDA; }
-    attr_bytes = 200 * 1024;
+    attr_set[vi] = true;
   }
   const int warps_per_block = 8;
-  // one wave of resident blocks (128 registers x 256 threads: two per SM), each loading the tables once
-  const int per_sm = smem + 1024 <= 110 * 1024 ? 2 : 1;
+  // one wave of resident blocks, each loading the tables once
+  const int by_regs = ql <= 3 ? 4 : ql <= 5 ? 3 : 1;
+  const int per_sm = std::max(1, std::min<int>(by_regs, int((220 * 1024) / (smem + 1024))));
   const int blocks = std::max(1, std::min((M + warps_per_block - 1) / warps_per_block, 148 * per_sm));
-  cudaError_t e = launch_k(xattn2_fused_kernel, blocks, 256, smem, stream, x, y, a_out, g2, b2, g3, b3, GU, c1, M, C, H, scale, eps);
+  cudaError_t e = launch_k(kern, blocks, 256, smem, stream, x, y, a_out, g2, b2, g3, b3, GU, c1, M, C, H, scale, eps);
   if (e == cudaSuccess) e = cudaGetLastError();
   if (e != cudaSuccess) { set_error("xattn2 launch: %s", cudaGetErrorString(e)); return MGB_ERR_CUDA; }
   return MGB_OK;
