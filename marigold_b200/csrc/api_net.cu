@@ -148,8 +148,29 @@ struct Loader {
     r.n1 = norm(p + ".norm1", cin);
     r.c1 = conv(p + ".conv1", cin, cout);
     r.n2 = norm(p + ".norm2", cout);
-    r.c2 = conv(p + ".conv2", cout, cout);
-    if (cin != cout) { r.has_sc = true; r.sc = lin(p + ".conv_shortcut", cout, cin, true, true); }
+    if (cin == cout) {
+      r.c2 = conv(p + ".conv2", cout, cout);
+    } else {
+      // conv2 and the 1x1 conv_shortcut as one K-concatenated weight [cout, 9 * cout + cin], bias b2 + bsc
+      r.has_sc = true;
+      r.c2.cin = cout; r.c2.cin_pad = cout; r.c2.cout = cout; r.c2.k_extra = cin;
+      const HostTensor *w2 = get(p + ".conv2.weight"), *b2 = get(p + ".conv2.bias"),
+                       *ws = get(p + ".conv_shortcut.weight"), *bs = get(p + ".conv_shortcut.bias");
+      if (cin % 64 != 0) { if (rc == MGB_OK) { set_error("resnet %s: shortcut input channels %d not a multiple of 64", p.c_str(), cin); rc = MGB_ERR_UNSUPPORTED; } }
+      else if (shape_is(w2, {cout, cout, 3, 3}, p + ".conv2.weight") && shape_is(b2, {cout}, p + ".conv2.bias") &&
+               shape_is(ws, {cout, cin, 1, 1}, p + ".conv_shortcut.weight") && shape_is(bs, {cout}, p + ".conv_shortcut.bias")) {
+        const std::vector<float> taps = pack_conv(w2->data, cout, cout, cout);
+        const size_t k1 = size_t(9) * cout, kt = k1 + cin;
+        std::vector<float> w(size_t(cout) * kt), b(cout);
+        for (int co = 0; co < cout; ++co) {
+          memcpy(&w[co * kt], &taps[co * k1], k1 * 4);
+          memcpy(&w[co * kt + k1], &ws->data[size_t(co) * cin], size_t(cin) * 4);
+          b[co] = b2->data[co] + bs->data[co];
+        }
+        r.c2.w = up_bf16(w);
+        r.c2.b = up_f32(b);
+      }
+    }
     if (temb_dim > 0) {
       const HostTensor* w = get(p + ".time_emb_proj.weight");
       const HostTensor* b = get(p + ".time_emb_proj.bias");
@@ -168,7 +189,7 @@ struct Loader {
     XfmrW x; x.C = C;
     x.gn = norm(p + ".norm", C);
     x.proj_in = lin(p + ".proj_in", C, C, true);
-    x.proj_out = lin(p + ".proj_out", C, C, true);
+
     const std::string t = p + ".transformer_blocks.0";
     x.ln1 = norm(t + ".norm1", C); x.ln2 = norm(t + ".norm2", C); x.ln3 = norm(t + ".norm3", C);
     // fused QKV [3C, C]
@@ -210,7 +231,35 @@ struct Loader {
       x.ff1.n = N; x.ff1.k = C; x.ff1.geglu = true;
       x.ff1.w = up_bf16(w); x.ff1.b = up_f32(b);
     }
-    x.ff2 = lin(t + ".ff.net.2", C, 4 * C, true);
+    {
+      // y = x + proj_out(hs0 + ff.net.2(m)) = x + hs0 W_po^T + m (W_po W_ff2)^T + (b_po + W_po b_ff2): one GEMM over the
+      // K-concatenated operand [hs0 | m] with the folded weight (product in fp32 on the device, then bf16)
+      const HostTensor *wpo = get(p + ".proj_out.weight"), *bpo = get(p + ".proj_out.bias"),
+                       *w2 = get(t + ".ff.net.2.weight"), *b2 = get(t + ".ff.net.2.bias");
+      if (shape_is(wpo, {C, C}, p + ".proj_out.weight") && shape_is(bpo, {C}, p + ".proj_out.bias") &&
+          shape_is(w2, {C, 4 * C}, t + ".ff.net.2.weight") && shape_is(b2, {C}, t + ".ff.net.2.bias")) {
+        const int K = 5 * C;
+        std::vector<float> wl(size_t(C) * K, 0.f), b(C);
+        for (int n = 0; n < C; ++n) {
+          memcpy(&wl[size_t(n) * K], &wpo->data[size_t(n) * C], size_t(C) * 4);
+          double acc = bpo->data[n];
+          for (int j = 0; j < C; ++j) acc += double(wpo->data[size_t(n) * C + j]) * b2->data[j];
+          b[n] = float(acc);
+        }
+        x.ffpo.n = C; x.ffpo.k = K;
+        x.ffpo.w = up_bf16(wl);
+        x.ffpo.b = up_f32(b);
+        float *dA = nullptr, *dB = nullptr;
+        if (x.ffpo.w && cudaMalloc(&dA, size_t(C) * C * 4) == cudaSuccess && cudaMalloc(&dB, size_t(C) * 4 * C * 4) == cudaSuccess &&
+            cudaMemcpy(dA, wpo->data.data(), size_t(C) * C * 4, cudaMemcpyHostToDevice) == cudaSuccess &&
+            cudaMemcpy(dB, w2->data.data(), size_t(C) * 4 * C * 4, cudaMemcpyHostToDevice) == cudaSuccess &&
+            launch_fold_matmul(dA, dB, x.ffpo.w, C, 4 * C, C, K, C, nullptr) == MGB_OK &&
+            cudaDeviceSynchronize() == cudaSuccess) {
+        } else if (rc == MGB_OK) { set_error("folding proj_out . ff.net.2 failed for %s", p.c_str()); rc = MGB_ERR_CUDA; }
+        if (dA) cudaFree(dA);
+        if (dB) cudaFree(dB);
+      }
+    }
     return x;
   }
   VaeAttnW vae_attn(const std::string& p, int C) {

@@ -194,6 +194,30 @@ int launch_pack_rgb(const float* rgb_nchw, bf16* out, int NB, int HW, cudaStream
   MGB_LAUNCH_CHECK("pack_rgb");
 }
 
+// One-time weight folding: P[M, N] = A[M, K] B[K, N] in fp32 (32 x 32 tiles through shared memory), written as bf16 into
+// a wider row-major matrix: out[m * ldo + col0 + n]. Used at finalize_weights for W_proj_out . W_ff2 (see net.cu).
+__global__ void __launch_bounds__(1024) fold_matmul_kernel(const float* __restrict__ A, const float* __restrict__ B,
+                                                            bf16* __restrict__ out, int M, int N, int K, int ldo, int col0) {
+  __shared__ float sa[32][33], sb[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int m = blockIdx.y * 32 + ty, n = blockIdx.x * 32 + tx;
+  float acc = 0.f;
+  for (int k0 = 0; k0 < K; k0 += 32) {
+    sa[ty][tx] = (m < M && k0 + tx < K) ? A[(size_t)m * K + k0 + tx] : 0.f;
+    sb[ty][tx] = (k0 + ty < K && n < N) ? B[(size_t)(k0 + ty) * N + n] : 0.f;
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 32; ++k) acc = fmaf(sa[ty][k], sb[k][tx], acc);
+    __syncthreads();
+  }
+  if (m < M && n < N) out[(size_t)m * ldo + col0 + n] = __float2bfloat16(acc);
+}
+int launch_fold_matmul(const float* A, const float* B, bf16* out, int M, int N, int K, int ldo, int col0, cudaStream_t stream) {
+  dim3 grid((N + 31) / 32, (M + 31) / 32);
+  fold_matmul_kernel<<<grid, 1024, 0, stream>>>(A, B, out, M, N, K, ldo, col0);
+  MGB_LAUNCH_CHECK("fold_matmul");
+}
+
 // y[M, N] = act_out(act_in(x)[M, K] W[N, K]^T + b); fp32 everywhere; one warp per output element.
 __global__ void __launch_bounds__(256) linear_small_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                            const float* __restrict__ b, float* __restrict__ y, int M,

@@ -241,6 +241,7 @@ __global__ void __launch_bounds__(kGemmThreads, MINB) gemm_tc_kernel(const __gri
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tmap_a);
     tma_prefetch_desc(&p.tmap_b);
+    if (p.num_kb1 < p.num_kb) tma_prefetch_desc(&p.tmap_a2);
 #pragma unroll 1
     for (int s = 0; s < stages; ++s) {
       mbar_init(&full_bar[s], 1);
@@ -308,7 +309,9 @@ __global__ void __launch_bounds__(kGemmThreads, MINB) gemm_tc_kernel(const __gri
             mbar_expect_tx_a(fb, kABytes + kBBytes);
             tma_load_2d_a(sb0 + stage * kBBytes, &p.tmap_b, fb, kc, ncol);
           }
-          tma_load_2d_a(sa0 + stage * kABytes, &p.tmap_a, fb, kc, mrow);
+          // K concatenation of two row-major operands (A = [A1 | A2]): blocks past num_kb1 come from the second map
+          if (kb < p.num_kb1) tma_load_2d_a(sa0 + stage * kABytes, &p.tmap_a, fb, kc, mrow);
+          else tma_load_2d_a(sa0 + stage * kABytes, &p.tmap_a2, fb, (kb - p.num_kb1) * BLOCK_K, mrow);
           if (++stage == ustages) { stage = 0; phase ^= 1; }
         }
       } else if (p.mode == 1) {
@@ -322,9 +325,14 @@ __global__ void __launch_bounds__(kGemmThreads, MINB) gemm_tc_kernel(const __gri
             mbar_expect_tx_a(fb, kABytes + kBBytes);
             tma_load_2d_a(sb0 + stage * kBBytes, &p.tmap_b, fb, kc, ncol);
           }
-          tma_load_5d_a(sa0 + stage * kABytes, &p.tmap_a, fb, cb * BLOCK_K, x0 + p.tap_dx[tap], y0 + p.tap_dy[tap],
-                        p.tap_p[tap], img);
-          if (++cb == cblocks) { cb = 0; ++tap; }
+          if (kb < p.num_kb1) {
+            tma_load_5d_a(sa0 + stage * kABytes, &p.tmap_a, fb, cb * BLOCK_K, x0 + p.tap_dx[tap], y0 + p.tap_dy[tap],
+                          p.tap_p[tap], img);
+            if (++cb == cblocks) { cb = 0; ++tap; }
+          } else {
+            // K blocks of the second operand (the 1x1 shortcut over the block input): same pixels, no tap shift
+            tma_load_5d_a(sa0 + stage * kABytes, &p.tmap_a2, fb, (kb - p.num_kb1) * BLOCK_K, x0, y0, 0, img);
+          }
           if (++stage == ustages) { stage = 0; phase ^= 1; }
         }
       } else {

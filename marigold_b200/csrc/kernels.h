@@ -49,10 +49,14 @@ struct GemmEpilogue {
 struct GemmParams {
   CUtensorMap tmap_a;  // mode 0: 2D {K, M}; mode 1: 5D {C, W, H, P, NB}
   CUtensorMap tmap_b;  // 2D {K, N}
+  CUtensorMap tmap_a2; // mode 0, optional: 2D {K2, M}, A = [A1 | A2] along K. Mode 1, optional second A operand: 5D {C2, W, H, 1, NB} of a 1x1 convolution over the same output
+                       // pixels whose K blocks follow the 3x3 taps (K concatenation: a ResnetBlock's conv2 + conv_shortcut
+                       // as ONE implicit GEMM with weights [W2 | Wsc])
   int mode;            // 0 = row-major activations, 1 = implicit conv (one A tile per tap), 2 = implicit 3x3 conv
                        // whose 9 taps read ONE shared-memory halo per channel block (see gemm_tc.cu)
   int M, N;            // logical GEMM rows / accumulator columns
   int num_kb;          // total K blocks of 64
+  int num_kb1;         // K blocks of the first A operand (== num_kb without tmap_a2)
   int kb_per_split;    // K blocks per blockIdx.z
   int stages;          // smem pipeline depth
   // conv geometry (mode 1)
@@ -118,8 +122,8 @@ int launch_gn_fused(const float* xa, int Ca, const float* xb, int Cb, bf16* y, b
 int launch_layernorm(const float* x, bf16* y, const float* gamma, const float* beta, int M, int C, float eps,
                      cudaStream_t stream);
 // Collapsed cross attention against the fixed 2-token context, fused with norm2 and norm3 (norm.cu):
-//   y = x + c1 + sum_h sigmoid(scale * LN2(x) . G_h) U_h ;  a_out = bf16(LN3(y))
-int launch_xattn2_fused(const float* x, float* y, bf16* a_out, const float* g2, const float* b2, const float* g3,
+//   y = bf16(x + c1 + sum_h sigmoid(scale * LN2(x) . G_h) U_h) ;  a_out = bf16(LN3(y in fp32))
+int launch_xattn2_fused(const float* x, bf16* y, bf16* a_out, const float* g2, const float* b2, const float* g3,
                         const float* b3, const bf16* GU, const float* c1, int M, int C, int H, float scale, float eps,
                         cudaStream_t stream);
 int launch_xattn2_fold(const float* wq, const float* wo, const float* bo, const float* kv, bf16* GU, float* c1, int C,
@@ -147,6 +151,8 @@ int launch_pack_decoder_latent(const float* latent_nchw, const float* w, const f
 int launch_select_step(const float* bias_table, int bias_total, const float* sched_k, float* cur_bias, float* cur_k,
                        const int* counter, int step, cudaStream_t stream);
 int launch_advance_counter(int* counter, cudaStream_t stream);
+// One-time fp32 product P = A[M,K] B[K,N], stored as bf16 at out[m * ldo + col0 + n] (weight folding at finalize)
+int launch_fold_matmul(const float* A, const float* B, bf16* out, int M, int N, int K, int ldo, int col0, cudaStream_t stream);
 // Tiny dense layer for M <= 16 rows (time MLP, text K/V): y[M,N] = act(x[M,K]) W[N,K]^T + b ; fp32
 int launch_linear_small(const float* x, const float* w, const float* b, float* y, int M, int N, int K,
                         int silu_in, int silu_out, cudaStream_t stream);

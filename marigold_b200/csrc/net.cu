@@ -79,7 +79,9 @@ static int gemm_common(Ctx& c, GemmParams& p, int bn, int splits, const Epi& e, 
 }
 
 // y = a[M,K] W^T (+ epilogue); ldo = row stride of the outputs (0: W.n, or W.n / 2 for GEGLU)
-static int linear(Ctx& c, const bf16* a, int M, const LinW& W, const Epi& e, int ldo = 0) {
+static int linear(Ctx& c, const bf16* a, int M, const LinW& W, const Epi& e, int ldo = 0, const bf16* a2 = nullptr,
+                  int K1 = 0) {
+  // a2 != nullptr: K concatenation, A = [a (K1 columns) | a2 (W.k - K1 columns)]
   int bn, sp, st;
   const bool geglu = (e.flags & EPI_GEGLU) != 0;
   choose_tile((M + 127) / 128, W.n, W.k / 64, geglu, true, &bn, &sp, &st);
@@ -87,7 +89,8 @@ static int linear(Ctx& c, const bf16* a, int M, const LinW& W, const Epi& e, int
   if (sp > 1) c.splitk_need = std::max(c.splitk_need, size_t(sp) * M * W.n * sizeof(float));
   if (c.dry) return MGB_OK;
   GemmParams p;
-  TRY(fill_linear_params(&p, a, W.w, M, W.n, W.k, bn, sp, st));
+  if (a2) TRY(fill_linear_params(&p, a, W.w, M, W.n, K1, bn, sp, st, a2, W.k - K1));
+  else TRY(fill_linear_params(&p, a, W.w, M, W.n, W.k, bn, sp, st));
   return gemm_common(c, p, bn, effective_splits(p), e, ldo > 0 ? ldo : (geglu ? W.n / 2 : W.n));
 }
 
@@ -102,19 +105,21 @@ static int matmul_nt(Ctx& c, const bf16* a, const bf16* b, int M, int N, int K, 
 
 // 3x3 conv on NHWC bf16; Hout x Wout output; kind per ops.cu
 static int conv3x3(Ctx& c, const bf16* x, int NB, int Hout, int Wout, const ConvW& W, int kind, const Epi& e,
-                   int Hsrc = 0, int Wsrc = 0) {
+                   int Hsrc = 0, int Wsrc = 0, const bf16* x2 = nullptr) {
   int tw, th;
   conv_tile_shape(Hout, Wout, &tw, &th, kind);
   const int m_tiles = NB * ((Wout + tw - 1) / tw) * ((Hout + th - 1) / th);
   int bn, sp, st;
   const bool special = (e.flags & (EPI_SCHED | EPI_DEPTH | EPI_NORMALS | EPI_NCHW)) != 0;
-  choose_tile(m_tiles, W.cout, 9 * W.cin_pad / 64, false, !special, &bn, &sp, &st, conv_halo_ring_bytes(kind));
+  if ((x2 != nullptr) != (W.k_extra > 0)) { set_error("conv3x3: second operand / weight layout mismatch"); return MGB_ERR_STATE; }
+  choose_tile(m_tiles, W.cout, (9 * W.cin_pad + W.k_extra) / 64, false, !special, &bn, &sp, &st,
+              x2 ? 0 : conv_halo_ring_bytes(kind));
   if (special) bn = 16;
   const size_t M = size_t(NB) * Hout * Wout;
   if (sp > 1) c.splitk_need = std::max(c.splitk_need, size_t(sp) * M * W.cout * sizeof(float));
   if (c.dry) return MGB_OK;
   GemmParams p;
-  TRY(fill_conv_params(&p, x, W.w, NB, Hout, Wout, W.cin_pad, W.cout, kind, bn, sp, st, Hsrc, Wsrc));
+  TRY(fill_conv_params(&p, x, W.w, NB, Hout, Wout, W.cin_pad, W.cout, kind, bn, sp, st, Hsrc, Wsrc, x2, W.k_extra));
   Epi e2 = e;
   e2.hw = Hout * Wout;
   return gemm_common(c, p, bn, effective_splits(p), e2, W.cout);
@@ -168,21 +173,19 @@ static int resnet_forward(Ctx& c, const ResnetW& R, Act& x, Act* skip, Act& y, i
   bf16* raw = R.has_sc ? aalloc<bf16>(c, M * R.cin) : nullptr;
   Act h = act_alloc(c, M, R.cout);
   bf16* t2 = aalloc<bf16>(c, M * R.cout);
-  float* sc = R.has_sc ? aalloc<float>(c, M * R.cout) : nullptr;
   TRY(groupnorm(c, x, skip, t1, raw, R.n1, NB, H * W, R.eps, 1));
   Epi e1;
   e1.bias = (R.bias_off >= 0 && c.cur_bias) ? c.cur_bias + R.bias_off : R.c1.b;
   e1.out_f32 = h.p;
   TRY(conv3x3(c, t1, NB, H, W, R.c1, 0, e1));
   TRY(groupnorm(c, h, nullptr, t2, nullptr, R.n2, NB, H * W, R.eps, 1));
-  const float* residual = x.p;
-  if (R.has_sc) {
-    Epi es; es.bias = R.sc.b; es.out_f32 = sc;
-    TRY(linear(c, raw, int(M), R.sc, es));
-    residual = sc;
-  }
-  Epi e2; e2.bias = R.c2.b; e2.residual = residual; e2.out_f32 = y.p;
-  TRY(conv3x3(c, t2, NB, H, W, R.c2, 0, e2));
+  // conv2 (+ residual). Where the block changes the channel count, diffusers adds conv_shortcut(x), a 1x1 convolution:
+  // its K blocks are appended to conv2's implicit GEMM (weights [W2 | Wsc], bias b2 + bsc, second A operand = the raw
+  // bf16 copy of the block input), which removes a GEMM launch (plus a split-K reduce on the small levels) and the
+  // fp32 round trip of its output
+  Epi e2; e2.bias = R.c2.b; e2.out_f32 = y.p;
+  if (!R.has_sc) e2.residual = x.p;
+  TRY(conv3x3(c, t2, NB, H, W, R.c2, 0, e2, 0, 0, R.has_sc ? raw : nullptr));
   c.arena->release(mk);
   return MGB_OK;
 }
@@ -213,17 +216,17 @@ static int xfmr_forward(Ctx& c, const XfmrW& X, Act& x, Act& y, int NB, int T) {
   if (!no_attn) LAUNCH(launch_flash_attn64(qkv, o, NB, T, C, 0.125f, attn_ws, attn_ws_bytes, c.stream), attn_ws ? 2 : 1);
   { Epi e; e.bias = X.o1.b; e.residual = hs0; e.out_f32 = hs1; TRY(linear(c, o, int(M), X.o1, e)); }
   // cross attention against the empty-prompt context, collapsed (norm.cu: xattn2_fused_kernel): LN2, to_q, the 2-key
-  // softmax, to_out + residual and LN3 are one launch; hs0 = trunk after attn2, a = LN3(hs0) for the feed-forward
+  // softmax, to_out + residual and LN3 are one launch; hsb = bf16 trunk after attn2, a = LN3 of it for the feed-forward
   if (!no_x) {
-    LAUNCH(launch_xattn2_fused(hs1, hs0, a, X.ln2.g, X.ln2.b, X.ln3.g, X.ln3.b, X.xGU, X.xc1, int(M), C, C / 64, 0.125f,
+    LAUNCH(launch_xattn2_fused(hs1, hsb, a, X.ln2.g, X.ln2.b, X.ln3.g, X.ln3.b, X.xGU, X.xc1, int(M), C, C / 64, 0.125f,
                                1e-5f, c.stream), 1);
   }
   // GEGLU feed-forward
   { Epi e; e.bias = X.ff1.b; e.out_bf16 = ffm; e.flags = EPI_GEGLU; TRY(linear(c, a, int(M), X.ff1, e)); }
-  { Epi e; e.bias = X.ff2.b; e.residual = hs0; e.out_bf16 = hsb; TRY(linear(c, ffm, int(M), X.ff2, e)); }
+  // ff.net.2 + proj_out + the block residual: ONE GEMM over [hs0 | ffm] with the folded weight (api_net.cu)
   {
-    Epi e; e.bias = X.proj_out.b; e.residual = x.p; e.out_f32 = y.p;
-    TRY(linear(c, hsb, int(M), X.proj_out, e));
+    Epi e; e.bias = X.ffpo.b; e.residual = x.p; e.out_f32 = y.p;
+    TRY(linear(c, hsb, int(M), X.ffpo, e, 0, ffm, C));
   }
   c.arena->release(mk);
   return MGB_OK;

@@ -19,10 +19,11 @@ struct HostTensor {
 };
 
 // ---- device-side weights ------------------------------------------------------------------------
-struct ConvW {   // 3x3 conv, tap-major bf16 [cout, 9 * cin_pad]
+struct ConvW {   // 3x3 conv, tap-major bf16 [cout, 9 * cin_pad (+ k_extra)]
   bf16* w = nullptr;
   float* b = nullptr;
   int cin = 0, cin_pad = 0, cout = 0;
+  int k_extra = 0;   // columns of a 1x1 convolution over a second operand appended after the taps (conv2 + conv_shortcut)
 };
 struct LinW {    // bf16 [n, k]
   bf16* w = nullptr;
@@ -38,7 +39,6 @@ struct NormW {
 struct ResnetW {
   NormW n1, n2;
   ConvW c1, c2;
-  LinW sc;              // 1x1 shortcut as a linear layer (cin != cout)
   bool has_sc = false;
   int cin = 0, cout = 0;
   // time embedding projection (UNet only): fp32 [cout, temb_dim]; bias already includes conv1.bias
@@ -50,7 +50,8 @@ struct ResnetW {
 struct XfmrW {
   int C = 0;
   NormW gn, ln1, ln2, ln3;
-  LinW proj_in, qkv, o1, ff1, ff2, proj_out;
+  LinW proj_in, qkv, o1, ff1;
+  LinW ffpo;             // ff.net.2 folded with proj_out: bf16 [C, C + 4C] = [W_po | W_po W_ff2], bias b_po + W_po b_ff2
   // cross attention (attn2): fp32 masters, folded against the empty-prompt context at set_text_embedding
   float* q2w = nullptr;  // to_q   fp32 [C, C]
   float* o2w = nullptr;  // to_out fp32 [C, C]

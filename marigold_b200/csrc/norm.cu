@@ -365,7 +365,8 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
 //       Wo a + bo = c1 + sum_h w0_h U_h, c1 = Wo v1 + bo,  U_h = Wo[:, h-block] (v0 - v1)_h   (U: [H, C])
 //   so the block is   y = x + c1 + sum_h sigmoid(scale * LN2(x) . G_h) U_h   — exact, C (2 H) MACs per token instead of
 //   2 C^2, all in fp32 (the two GEMMs it replaces rounded z, q, a to bf16).
-// x fp32 [M, C] -> y fp32 [M, C] (residual trunk) and a_out bf16 [M, C] = LN3(y) (operand of the feed-forward GEMM).
+// x fp32 [M, C] -> y bf16 [M, C] (the trunk after attn2: first K-operand of the folded ff.net.2 + proj_out GEMM) and
+// a_out bf16 [M, C] = LN3(y) (operand of the feed-forward GEMM).
 // -------------------------------------------------------------------------------------------------
 // Persistent blocks with the folded tables in shared memory (G, U as bf16 [H][C]; c1 and the two LayerNorm affines fp32):
 // the first versions re-read G and U from L1 / L2 for every token (13-205 KB per token against 1-5 KB of activations)
@@ -380,7 +381,7 @@ __device__ __forceinline__ float4 bf16x4_to_f4(uint2 v) {
 // 4 blocks per SM (the generic 10-slot version needed 128 registers: 16 warps per SM for a latency-bound kernel)
 template <int QL>
 __global__ void __launch_bounds__(256, QL <= 3 ? 4 : QL <= 5 ? 3 : 1)
-    xattn2_fused_kernel(const float* __restrict__ x, float* __restrict__ y, bf16* __restrict__ a_out,
+    xattn2_fused_kernel(const float* __restrict__ x, bf16* __restrict__ y, bf16* __restrict__ a_out,
                         const float* __restrict__ g2, const float* __restrict__ b2, const float* __restrict__ g3,
                         const float* __restrict__ b3, const bf16* __restrict__ GU /* [2][H][C] */,
                         const float* __restrict__ c1, int M, int C, int H, float scale, float eps) {
@@ -483,12 +484,15 @@ __global__ void __launch_bounds__(256, QL <= 3 ? 4 : QL <= 5 ? 3 : 1)
       }
     }
     // store the trunk, then LN3 of the same row
-    float4* yr = reinterpret_cast<float4*>(y + (size_t)tok * C);
+    uint2* yr = reinterpret_cast<uint2*>(y + (size_t)tok * C);
     s = 0.f;
 #pragma unroll
     for (int k = 0; k < QL; ++k) {
       const int q = lane + 32 * k;
-      if (q < Q) { yr[q] = acc[k]; s += acc[k].x + acc[k].y + acc[k].z + acc[k].w; }
+      if (q < Q) {
+        yr[q] = make_uint2(pack_bf16x2(acc[k].x, acc[k].y), pack_bf16x2(acc[k].z, acc[k].w));
+        s += acc[k].x + acc[k].y + acc[k].z + acc[k].w;
+      }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
@@ -518,14 +522,14 @@ __global__ void __launch_bounds__(256, QL <= 3 ? 4 : QL <= 5 ? 3 : 1)
   }
 }
 
-int launch_xattn2_fused(const float* x, float* y, bf16* a_out, const float* g2, const float* b2, const float* g3,
+int launch_xattn2_fused(const float* x, bf16* y, bf16* a_out, const float* g2, const float* b2, const float* g3,
                         const float* b3, const bf16* GU, const float* c1, int M, int C, int H, float scale, float eps,
                         cudaStream_t stream) {
   if (C % 4 != 0 || C / 4 > 32 * kLnMaxQ || H < 1) { set_error("xattn2: unsupported C=%d H=%d", C, H); return MGB_ERR_INVALID; }
   const size_t smem = size_t(2) * H * C * 2 + size_t(5) * C * 4;
   if (smem > 200 * 1024) { set_error("xattn2: C=%d H=%d needs %zu B of shared memory", C, H, smem); return MGB_ERR_INVALID; }
   const int ql = (C / 4 + 31) / 32;
-  void (*kern)(const float*, float*, bf16*, const float*, const float*, const float*, const float*, const bf16*, const float*,
+  void (*kern)(const float*, bf16*, bf16*, const float*, const float*, const float*, const float*, const bf16*, const float*,
                int, int, int, float, float) =
       ql <= 3 ? xattn2_fused_kernel<3> : ql <= 5 ? xattn2_fused_kernel<5> : xattn2_fused_kernel<10>;
   static bool attr_set[3] = {false, false, false};

@@ -60,27 +60,36 @@ void conv_tile_shape(int Hout, int Wout, int* tile_w, int* tile_h, int kind) {
 }
 
 int fill_linear_params(GemmParams* p, const bf16* a, const bf16* w, int M, int N, int K, int block_n, int splits,
-                       int stages) {
+                       int stages, const bf16* a2, int K2) {
+  // a2 (optional): second row-major operand [M, K2]; the weight is [N, K + K2] (K concatenation)
   memset(p, 0, sizeof(*p));
-  if (K % 64 != 0 || M <= 0 || N <= 0) {
-    set_error("linear: need K %% 64 == 0 (got M=%d N=%d K=%d)", M, N, K);
+  if (K % 64 != 0 || M <= 0 || N <= 0 || (a2 && (K2 % 64 != 0 || K2 <= 0))) {
+    set_error("linear: need K %% 64 == 0 (got M=%d N=%d K=%d K2=%d)", M, N, K, K2);
     return MGB_ERR_INVALID;
   }
+  if (!a2) K2 = 0;
   p->mode = 0;
   p->M = M; p->N = N;
-  p->num_kb = K / 64;
+  p->num_kb1 = K / 64;
+  p->num_kb = (K + K2) / 64;
   if (splits < 1) splits = 1;
   splits = std::min(splits, p->num_kb);
   p->kb_per_split = (p->num_kb + splits - 1) / splits;
   p->stages = stages;
   int rc = make_tmap_2d(&p->tmap_a, a, uint64_t(K), uint64_t(M), uint64_t(K) * 2, 64, 128);
   if (rc) return rc;
-  rc = make_tmap_2d(&p->tmap_b, w, uint64_t(K), uint64_t(N), uint64_t(K) * 2, 64, uint32_t(block_n));
+  if (a2) {
+    rc = make_tmap_2d(&p->tmap_a2, a2, uint64_t(K2), uint64_t(M), uint64_t(K2) * 2, 64, 128);
+    if (rc) return rc;
+  }
+  rc = make_tmap_2d(&p->tmap_b, w, uint64_t(K + K2), uint64_t(N), uint64_t(K + K2) * 2, 64, uint32_t(block_n));
   return rc;
 }
 
 int fill_conv_params(GemmParams* p, const bf16* x, const bf16* w, int NB, int Hout, int Wout, int Cin, int Cout,
-                     int kind, int block_n, int splits, int stages, int Hsrc, int Wsrc) {
+                     int kind, int block_n, int splits, int stages, int Hsrc, int Wsrc, const bf16* x2, int Cin2) {
+  // x2 (optional): bf16 NHWC [NB, Hout, Wout, Cin2], the operand of a 1x1 convolution over the same output pixels whose
+  // weight columns follow the taps in w ([Cout, ntaps * Cin + Cin2]): K concatenation (stride-1 kinds only)
   // Hsrc x Wsrc: spatial extent of the tensor the taps address (the image for stride 1; one parity plane for
   // stride 2, i.e. ceil(Hin / 2) x ceil(Win / 2), which exceeds the output by one for the VAE's pad-(0,1,0,1) conv
   // on an odd input). <= 0: same as the output.
@@ -131,12 +140,17 @@ int fill_conv_params(GemmParams* p, const bf16* x, const bf16* w, int NB, int Ho
     set_error("conv2d: unknown kind %d", kind);
     return MGB_ERR_INVALID;
   }
-  p->num_kb = p->ntaps * p->cblocks;
+  p->num_kb1 = p->ntaps * p->cblocks;
+  if (x2 != nullptr && (Cin2 % 64 != 0 || Cin2 <= 0 || (kind != 0 && kind != 1))) {
+    set_error("conv2d: second operand needs Cin2 %% 64 == 0 and a stride-1 kind (got %d, kind %d)", Cin2, kind);
+    return MGB_ERR_INVALID;
+  }
+  p->num_kb = p->num_kb1 + (x2 ? Cin2 / 64 : 0);
   if (splits < 1) splits = 1;
   splits = std::min(splits, p->num_kb);
   p->kb_per_split = (p->num_kb + splits - 1) / splits;
   p->stages = stages;
-  const int hv = kind == 0 ? conv_halo_variant() : 0;
+  const int hv = (kind == 0 && !x2) ? conv_halo_variant() : 0;
   uint32_t box_w = uint32_t(p->tile_w), box_h = uint32_t(p->tile_h);
   if (hv > 0) {
     // operand-reuse path: K order (channel block, tap), splits in whole channel blocks
@@ -159,7 +173,15 @@ int fill_conv_params(GemmParams* p, const bf16* x, const bf16* w, int NB, int Ho
   const uint32_t box[5] = {64, box_w, box_h, 1, 1};
   int rc = make_tmap_5d(&p->tmap_a, x, dims, strides, box);
   if (rc) return rc;
-  const uint64_t Ktot = uint64_t(p->ntaps) * Cin;
+  if (x2) {
+    const uint64_t C22 = uint64_t(Cin2) * 2;
+    const uint64_t dims2[5] = {uint64_t(Cin2), uint64_t(Wout), uint64_t(Hout), 1, uint64_t(NB)};
+    const uint64_t strides2[4] = {C22, C22 * Wout, C22 * Wout * Hout, C22 * Wout * Hout};
+    const uint32_t box2[5] = {64, uint32_t(p->tile_w), uint32_t(p->tile_h), 1, 1};
+    rc = make_tmap_5d(&p->tmap_a2, x2, dims2, strides2, box2);
+    if (rc) return rc;
+  }
+  const uint64_t Ktot = uint64_t(p->ntaps) * Cin + (x2 ? uint64_t(Cin2) : 0);
   rc = make_tmap_2d(&p->tmap_b, w, Ktot, uint64_t(Cout), Ktot * 2, 64, uint32_t(block_n));
   return rc;
 }

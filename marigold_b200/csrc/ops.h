@@ -17,11 +17,12 @@ void conv_tile_shape(int Hout, int Wout, int* tile_w, int* tile_h, int kind = -1
 
 // A [M, K] bf16 row-major, W [N, K] bf16 row-major.
 int fill_linear_params(GemmParams* p, const bf16* a, const bf16* w, int M, int N, int K, int block_n, int splits,
-                       int stages);
+                       int stages, const bf16* a2 = nullptr, int K2 = 0);
 // x NHWC bf16 ([NB, Hout, Wout, Cin] for kind 0/1, [NB, 4, Hout, Wout, Cin] parity planes for kind 2/3);
 // w [Cout, taps * Cin] bf16 tap-major.
 int fill_conv_params(GemmParams* p, const bf16* x, const bf16* w, int NB, int Hout, int Wout, int Cin, int Cout,
-                     int kind, int block_n, int splits, int stages, int Hsrc = 0, int Wsrc = 0);
+                     int kind, int block_n, int splits, int stages, int Hsrc = 0, int Wsrc = 0, const bf16* x2 = nullptr,
+                     int Cin2 = 0);
 int effective_splits(const GemmParams& p);
 // Launch (plus the deferred epilogue when split-K is active). p.epi must be filled by the caller.
 int run_gemm(GemmParams& p, int block_n, float* splitk_ws, cudaStream_t stream);
