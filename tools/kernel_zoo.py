@@ -24,13 +24,13 @@ def rn(*s):
     return torch.randn(*s, device="cuda", generator=g)
 
 
-def conv(H, W, cin, cout, kind=0, flags=0, bias=True):
+def conv(H, W, cin, cout, kind=0, flags=0, bias=True, block_n=0):
     stride = 2 if kind in (2, 3) else 1
     x = rn(1, H * stride, W * stride, cin)
     xin = ops.space_to_depth(x) if stride == 2 else x.to(bf)
     w = ops.pack_conv_weight((rn(cout, cin, 3, 3) / (9 * cin) ** 0.5).to(bf))
     ws = torch.empty(16 * H * W * cout, device="cuda")
-    ops.conv2d(xin, w, rn(cout) if bias else None, 1, H, W, cin, cout, kind=kind, flags=flags, ws=ws)
+    ops.conv2d(xin, w, rn(cout) if bias else None, 1, H, W, cin, cout, kind=kind, flags=flags, block_n=block_n, ws=ws)
 
 
 def linear(M, N, K, flags=0, residual=False, bf16out=False):
@@ -66,15 +66,29 @@ ops.groupnorm(rn(1, 144, 2560), rn(2560), rn(2560), 1, 144, 2560, 32, 1e-5, 1)
 ops.upsample2x(rn(1, 48, 48, 640))
 # ---- VAE decoder, 768 x 768 (C = 128) and 384 x 384 (C = 256) ----
 conv(768, 768, 128, 128)                                 # 4608 tiles, two CTAs per SM
-conv(768, 768, 128, 3, flags=_lib.EPI_DEPTH)             # conv_out + channel mean / clip / shift head
+conv(768, 768, 128, 3, flags=_lib.EPI_DEPTH, block_n=16)  # conv_out + channel mean / clip / shift head (16-column tile)
 conv(384, 384, 256, 256)
 ops.groupnorm(rn(1, 768 * 768, 128), rn(128), rn(128), 1, 768 * 768, 128, 32, 1e-6, 1)
 # ---- test-time ensemble, E = 10 members at 768 x 768 ----
 d = torch.rand(10, 1, 768, 768, device="cuda", generator=g)
 p0 = np.concatenate([np.ones(10), np.zeros(10)])
 _, _, aux = ensemble_depth(d, return_aux=True, param=p0, output_uncertainty=True)     # minmax + reduce + renorm
-aux["cost_batch"](np.repeat(p0[None], 21, 0))            # one BFGS gradient: 21 parameter sets, one launch
+aux["cost_batch"](np.repeat(p0[None], 21, 0))            # generic batch: 21 parameter sets, one launch
+X = np.repeat(p0[None], 20, 0)
+X[np.arange(20), np.arange(20)] += 1.5e-8
+aux["cost_fd"](X)                                        # one BFGS gradient, structured: base pass + perturbation rows
 n = torch.nn.functional.normalize(rn(10, 3, 768, 768), dim=1)
 ensemble_normals(n, output_uncertainty=True)
+# ---- bookends and evaluation ----
+from marigold_b200 import imageops  # noqa: E402
+from marigold_b200.evaluation import evaluate_depth  # noqa: E402
+
+img = torch.randint(0, 256, (1, 3, 1080, 1920), dtype=torch.uint8, device="cuda")
+rgb = imageops.resize(img, (432, 768), "bilinear", post=2)                      # resize_max_res + normalise
+pred = torch.rand(1, 1, 432, 768, device="cuda", generator=g)
+full = imageops.resize(pred, (1080, 1920), "bilinear")                          # final resize
+imageops.colorize_u8(full[0, 0], 0, 1, imageops.spectral_lut_u8())
+gt = full[0, 0] * 5 + 1 + 0.05 * rn(1080, 1920)
+evaluate_depth(full[0, 0], gt, torch.rand(1080, 1920, device="cuda", generator=g) > 0.2, min_depth=0.5, max_depth=10.0)
 torch.cuda.synchronize()
 print("kernel zoo done")
