@@ -31,20 +31,20 @@
 
 namespace mgb {
 
-constexpr int kAttnThreads = 64 + 256;
+constexpr int attn_threads(int rt) { return 64 + 128 * rt; }   // producer + MMA warps, 4 RT softmax warps
 constexpr int kQBytes = 128 * 128;       // 128 rows x 64 bf16
 constexpr int kKvBytes = 64 * 128;       // 64 rows x 64 bf16
 constexpr int kPBytes = 128 * 128;       // 128 rows x 64 bf16
 constexpr int kKvStages = 3;
 constexpr float kRescaleThreshold = 8.0f;  // log2 units
-constexpr int kAttnDefaultVariant = 0;
+constexpr int kAttnDefaultRT = 2;
 // P (bf16) goes back to tensor memory and feeds the PV MMA as a TMEM A-operand: no smem round trip and no
 // generic->async proxy fence in the softmax loop.
-// The softmax is bound by the XU pipe (ncu r02: sm__inst_executed_pipe_xu 102 % of peak): MUFU.EX2 and the F2FP bf16
-// conversions share it, 1.5 XU operations per score at 16 lanes / clock / SM = 768 cycles per 128 x 64 block against 256
-// cycles of tensor work. Variants move work off it: ALU_PACK converts with integer adds + PRMT; POLY of every 4
-// exponentials are evaluated by ex2_poly on the FMA pipe (relative error 2.2e-4, below the bf16 rounding of P).
-
+// RT = softmax threads per query row (2 or 4: warps w, w+4, .. own the same TMEM lane quarter and split a block's 64
+// scores). The loop is a per-warp dependent chain (LDTM -> max -> exchange -> exp2 -> STTM), not a saturated pipe: ncu
+// reads the XU pipe (MUFU.EX2 + F2FP) at 102 %, yet converting on the integer ALU and evaluating 25-50 % of the
+// exponentials as an FMA-pipe polynomial made the kernel 7-18 % SLOWER (r01 and r02). More, shorter chains per row are
+// the lever: RT = 4 halves every thread's share and doubles the warps per scheduler.
 struct AttnParams {
   CUtensorMap tmap_q;   // 3D {3C, T, NB}, box {64, 128, 1}
   CUtensorMap tmap_kv;  // 3D {3C, T, NB}, box {64, 64, 1}
@@ -60,17 +60,18 @@ struct AttnParams {
 };
 
 // 64-thread named barrier of one TMEM lane quarter (constant ids: a register id makes ptxas reserve all 16)
+template <int N>
 __device__ __forceinline__ void quarter_barrier(int q) {
   switch (q) {
-    case 0: asm volatile("bar.sync 1, 64;" ::: "memory"); break;
-    case 1: asm volatile("bar.sync 2, 64;" ::: "memory"); break;
-    case 2: asm volatile("bar.sync 3, 64;" ::: "memory"); break;
-    default: asm volatile("bar.sync 4, 64;" ::: "memory"); break;
+    case 0: asm volatile("bar.sync 1, %0;" ::"n"(N) : "memory"); break;
+    case 1: asm volatile("bar.sync 2, %0;" ::"n"(N) : "memory"); break;
+    case 2: asm volatile("bar.sync 3, %0;" ::"n"(N) : "memory"); break;
+    default: asm volatile("bar.sync 4, %0;" ::"n"(N) : "memory"); break;
   }
 }
 
-template <bool ALU_PACK, int POLY>
-__global__ void __launch_bounds__(kAttnThreads, 2) flash_attn64_kernel(const __grid_constant__ AttnParams p) {
+template <int RT>
+__global__ void __launch_bounds__(attn_threads(RT), 2) flash_attn64_kernel(const __grid_constant__ AttnParams p) {
   pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -105,7 +106,7 @@ __global__ void __launch_bounds__(kAttnThreads, 2) flash_attn64_kernel(const __g
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&s_full[b], 1);
-      mbar_init(&p_full[b], 256);
+      mbar_init(&p_full[b], 128 * RT);
       mbar_init(&p_empty[b], 1);
     }
     fence_mbar_init();
@@ -195,8 +196,9 @@ __global__ void __launch_bounds__(kAttnThreads, 2) flash_attn64_kernel(const __g
     __syncwarp();
   } else {
     // ===================== softmax =====================
+    constexpr int NS = 64 / RT;             // scores (and O columns) per thread
     const int q = warp & 3;                 // TMEM lane quarter
-    const int h = (warp - 2) >> 2;          // which half of the block's 64 scores / of O's 64 columns
+    const int h = (warp - 2) >> 2;          // which part of the block's 64 scores / of O's 64 columns
     const int row = q * 32 + lane;
     const uint32_t lane_off = uint32_t(q * 32) << 16;
     float m_ref = 0.f, l_run = 0.f;
@@ -204,36 +206,37 @@ __global__ void __launch_bounds__(kAttnThreads, 2) flash_attn64_kernel(const __g
       const int b = j & 1, u = j >> 1;
       mbar_wait(&s_full[b], u & 1);
       tc_fence_after();
-      uint32_t r[32];
-      tmem_ld32(tmem_base + lane_off + b * 64 + h * 32, r);
+      uint32_t r[NS];
+      TmemIO<NS>::ld(tmem_base + lane_off + b * 64 + h * NS, r);
       tmem_wait_ld();
-      const int kv_valid = p.T - (jb0 + j) * 64 - h * 32;   // >= 32 except possibly in the last block
-      if (kv_valid < 32) {                          // ragged tail (T % 64 != 0): mask once, then share the fast path
+      const int kv_valid = p.T - (jb0 + j) * 64 - h * NS;   // >= NS except possibly in the last block
+      if (kv_valid < NS) {                          // ragged tail (T % 64 != 0): mask once, then share the fast path
 #pragma unroll
-        for (int i = 0; i < 32; ++i)
+        for (int i = 0; i < NS; ++i)
           if (i >= kv_valid) r[i] = 0xff800000u;    // -inf
       }
-      // partial row max with 4 independent chains, then the exchange with the warp owning the other 32 scores
+      // partial row max with 4 independent chains, then the exchange with the warps owning the other scores of the row
       float mxa = __uint_as_float(r[0]), mxb = __uint_as_float(r[1]), mxc = __uint_as_float(r[2]),
             mxd = __uint_as_float(r[3]);
 #pragma unroll
-      for (int i = 4; i < 32; i += 4) {
+      for (int i = 4; i < NS; i += 4) {
         mxa = fmaxf(mxa, __uint_as_float(r[i]));
         mxb = fmaxf(mxb, __uint_as_float(r[i + 1]));
         mxc = fmaxf(mxc, __uint_as_float(r[i + 2]));
         mxd = fmaxf(mxd, __uint_as_float(r[i + 3]));
       }
       float mx = fmaxf(fmaxf(mxa, mxb), fmaxf(mxc, mxd));
-      float* xs = s_xch + ((b * 4 + q) * 2) * 32;
+      float* xs = s_xch + ((b * 4 + q) * RT) * 32;
       xs[h * 32 + lane] = mx;
-      quarter_barrier(q);
-      mx = fmaxf(mx, xs[(h ^ 1) * 32 + lane]);
+      quarter_barrier<32 * RT>(q);
+#pragma unroll
+      for (int k = 1; k < RT; ++k) mx = fmaxf(mx, xs[((h + k) % RT) * 32 + lane]);
       const float m_blk = mx * p.scale_log2;
       if (j == 0) {
         m_ref = m_blk;
       } else {
         const bool need = m_blk > m_ref + kRescaleThreshold;
-        if (__any_sync(0xffffffffu, need)) {      // identical decision in both warps of the quarter
+        if (__any_sync(0xffffffffu, need)) {      // identical decision in every warp of the quarter
           // rescale O (and l) of the rows that need it; other rows multiply by 1
           const float m_new = need ? m_blk : m_ref;
           const float alpha = ex2_approx(m_ref - m_new);
@@ -241,66 +244,66 @@ __global__ void __launch_bounds__(kAttnThreads, 2) flash_attn64_kernel(const __g
           l_run *= alpha;
           mbar_wait(&p_empty[(j - 1) & 1], ((j - 1) >> 1) & 1);   // every PV issued so far has completed
           tc_fence_after();
-          uint32_t o[32];
-          tmem_ld32(tmem_o + lane_off + h * 32, o);
+          uint32_t o[NS];
+          TmemIO<NS>::ld(tmem_o + lane_off + h * NS, o);
           tmem_wait_ld();
 #pragma unroll
-          for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-          tmem_st32(tmem_o + lane_off + h * 32, o);
+          for (int i = 0; i < NS; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+          TmemIO<NS>::st(tmem_o + lane_off + h * NS, o);
           tmem_wait_st();
         }
       }
       // P = exp2(S * c - m_ref) (exp2(-inf) = 0 masks the tail); bf16 pairs; 4 partial row sums
-      uint32_t pk[16];
+      uint32_t pk[NS / 2];
       float ls0 = 0.f, ls1 = 0.f, ls2 = 0.f, ls3 = 0.f;
       const float nm = -m_ref;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float e0 = fmaf(__uint_as_float(r[4 * i]), p.scale_log2, nm), e1 = fmaf(__uint_as_float(r[4 * i + 1]), p.scale_log2, nm),
-                    e2 = fmaf(__uint_as_float(r[4 * i + 2]), p.scale_log2, nm), e3 = fmaf(__uint_as_float(r[4 * i + 3]), p.scale_log2, nm);
-        const float a0 = POLY >= 1 ? ex2_poly(e0) : ex2_approx(e0);
-        const float a1 = ex2_approx(e1);
-        const float a2 = POLY >= 2 ? ex2_poly(e2) : ex2_approx(e2);
-        const float a3 = ex2_approx(e3);
+      for (int i = 0; i < NS / 4; ++i) {
+        const float a0 = ex2_approx(fmaf(__uint_as_float(r[4 * i]), p.scale_log2, nm));
+        const float a1 = ex2_approx(fmaf(__uint_as_float(r[4 * i + 1]), p.scale_log2, nm));
+        const float a2 = ex2_approx(fmaf(__uint_as_float(r[4 * i + 2]), p.scale_log2, nm));
+        const float a3 = ex2_approx(fmaf(__uint_as_float(r[4 * i + 3]), p.scale_log2, nm));
         ls0 += a0; ls1 += a1; ls2 += a2; ls3 += a3;
-        pk[2 * i] = ALU_PACK ? pack_bf16x2_pos_alu(a0, a1) : pack_bf16x2(a0, a1);
-        pk[2 * i + 1] = ALU_PACK ? pack_bf16x2_pos_alu(a2, a3) : pack_bf16x2(a2, a3);
+        pk[2 * i] = pack_bf16x2(a0, a1);
+        pk[2 * i + 1] = pack_bf16x2(a2, a3);
       }
       l_run += (ls0 + ls1) + (ls2 + ls3);
       // P buffer b was last read by PV(j-2)
       mbar_wait(&p_empty[b], (u & 1) ^ 1);
-      tmem_st16(tmem_base + 192 + b * 32 + h * 16 + lane_off, pk);
+      TmemIO<NS / 2>::st(tmem_base + 192 + b * 32 + h * (NS / 2) + lane_off, pk);
       tmem_wait_st();
       tc_fence_before();
       mbar_arrive(&p_full[b]);
     }
-    // epilogue: O / l. The two halves of a row add their partial sums through the exchange buffer
+    // epilogue: O / l. The parts of a row add their partial sums through the exchange buffer
     // (slot (nkv & 1): not the one the last block's max exchange used).
-    float* xl = s_xch + (((nkv & 1) * 4 + q) * 2) * 32;
+    float* xl = s_xch + (((nkv & 1) * 4 + q) * RT) * 32;
     xl[h * 32 + lane] = l_run;
-    quarter_barrier(q);
-    const float l_tot = l_run + xl[(h ^ 1) * 32 + lane];
+    quarter_barrier<32 * RT>(q);
+    float l_tot = 0.f;
+#pragma unroll
+    for (int k = 0; k < RT; ++k) l_tot += xl[k * 32 + lane];      // same order in every part: identical l_tot
     mbar_wait(&p_empty[(nkv - 1) & 1], ((nkv - 1) >> 1) & 1);
     tc_fence_after();
     const int qrow = q0 + row;
-    uint32_t o0[32];
-    tmem_ld32(tmem_o + lane_off + h * 32, o0);
+    uint32_t o0[NS];
+    TmemIO<NS>::ld(tmem_o + lane_off + h * NS, o0);
     tmem_wait_ld();
     if (qrow < p.T) {
       if (p.splits == 1) {
         const float inv = 1.f / l_tot;
-        uint4* dst = reinterpret_cast<uint4*>(p.out + ((size_t)img * p.T + qrow) * p.C + head * 64 + h * 32);
+        uint4* dst = reinterpret_cast<uint4*>(p.out + ((size_t)img * p.T + qrow) * p.C + head * 64 + h * NS);
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
+        for (int i = 0; i < NS / 8; ++i)
           dst[i] = make_uint4(pack_bf16x2(__uint_as_float(o0[8 * i]) * inv, __uint_as_float(o0[8 * i + 1]) * inv),
                               pack_bf16x2(__uint_as_float(o0[8 * i + 2]) * inv, __uint_as_float(o0[8 * i + 3]) * inv),
                               pack_bf16x2(__uint_as_float(o0[8 * i + 4]) * inv, __uint_as_float(o0[8 * i + 5]) * inv),
                               pack_bf16x2(__uint_as_float(o0[8 * i + 6]) * inv, __uint_as_float(o0[8 * i + 7]) * inv));
       } else {
         const size_t prow = ((size_t(split) * gridDim.z / p.splits + img) * gridDim.y + head) * p.T + qrow;
-        uint4* dst = reinterpret_cast<uint4*>(p.part_o + prow * 64 + h * 32);
+        uint4* dst = reinterpret_cast<uint4*>(p.part_o + prow * 64 + h * NS);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) dst[i] = make_uint4(o0[4 * i], o0[4 * i + 1], o0[4 * i + 2], o0[4 * i + 3]);
+        for (int i = 0; i < NS / 4; ++i) dst[i] = make_uint4(o0[4 * i], o0[4 * i + 1], o0[4 * i + 2], o0[4 * i + 3]);
         if (h == 0) *reinterpret_cast<float2*>(p.part_ml + prow * 2) = make_float2(m_ref, l_tot);
       }
     }
@@ -391,11 +394,10 @@ int launch_flash_attn64(const bf16* qkv, bf16* out, int NB, int T, int C, float 
     }
   }
   static const size_t dbg_pad = getenv("MGB_ATTN_SMEM_PAD") ? size_t(atoi(getenv("MGB_ATTN_SMEM_PAD"))) : 0;   // debug: force 1 CTA/SM
-  const size_t smem = 1024 + kQBytes + 2 * kKvStages * kKvBytes + 256 + 2048 + dbg_pad;
-  // variant: 0 = F2FP + MUFU only, 1 = ALU pack, 2 = ALU pack + 1/4 polynomial, 3 = ALU pack + 1/2 polynomial
-  static const int variant = getenv("MGB_ATTN_VARIANT") ? atoi(getenv("MGB_ATTN_VARIANT")) : kAttnDefaultVariant;
-  void (*kern)(AttnParams) = variant == 0 ? flash_attn64_kernel<false, 0> : variant == 1 ? flash_attn64_kernel<true, 0>
-                             : variant == 2 ? flash_attn64_kernel<true, 1> : flash_attn64_kernel<true, 2>;
+  const size_t smem = 1024 + kQBytes + 2 * kKvStages * kKvBytes + 256 + 4096 + dbg_pad;
+  // softmax threads per row: MGB_ATTN_RT = 2 | 4
+  static const int rt = getenv("MGB_ATTN_RT") ? atoi(getenv("MGB_ATTN_RT")) : kAttnDefaultRT;
+  void (*kern)(AttnParams) = rt == 4 ? flash_attn64_kernel<4> : flash_attn64_kernel<2>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
@@ -403,7 +405,7 @@ int launch_flash_attn64(const bf16* qkv, bf16* out, int NB, int T, int C, float 
     attr_set = true;
   }
   dim3 grid((T + 127) / 128, C / 64, NB * p.splits);
-  cudaError_t e = launch_k(kern, grid, kAttnThreads, smem, stream, p);
+  cudaError_t e = launch_k(kern, grid, attn_threads(rt == 4 ? 4 : 2), smem, stream, p);
   if (e == cudaSuccess) e = cudaGetLastError();
   if (e != cudaSuccess) { set_error("flash_attn64 launch: %s", cudaGetErrorString(e)); return MGB_ERR_CUDA; }
   if (p.splits > 1) {

@@ -308,6 +308,25 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32
       : "memory");
 }
 
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+               ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+// size-generic wrappers (N columns of 32 bits per lane)
+template <int N> struct TmemIO;
+template <> struct TmemIO<32> {
+  static __device__ __forceinline__ void ld(uint32_t a, uint32_t (&r)[32]) { tmem_ld32(a, r); }
+  static __device__ __forceinline__ void st(uint32_t a, const uint32_t (&r)[32]);
+};
+template <> struct TmemIO<16> {
+  static __device__ __forceinline__ void ld(uint32_t a, uint32_t (&r)[16]) { tmem_ld16(a, r); }
+  static __device__ __forceinline__ void st(uint32_t a, const uint32_t (&r)[16]);
+};
+template <> struct TmemIO<8> {
+  static __device__ __forceinline__ void st(uint32_t a, const uint32_t (&r)[8]) { tmem_st8(a, r); }
+};
+
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
   asm volatile(
       "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
@@ -316,6 +335,9 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16
       "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
       : "memory");
 }
+
+__device__ __forceinline__ void TmemIO<32>::st(uint32_t a, const uint32_t (&r)[32]) { tmem_st32(a, r); }
+__device__ __forceinline__ void TmemIO<16>::st(uint32_t a, const uint32_t (&r)[16]) { tmem_st16(a, r); }
 
 // ------------------------------------------------------------------------------------------------
 // math helpers
@@ -344,27 +366,6 @@ __device__ __forceinline__ float gelu_erf_f(float x) {
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
-}
-
-// exp2 on the FMA/ALU pipes (Cody-Waite split + degree-3 polynomial, max relative error 2.2e-4: an order of
-// magnitude below bf16 rounding of the result). Used for HALF of the flash-attention scores: the softmax is bound
-// by the XU pipe (MUFU.EX2 retires one warp instruction per 16 cycles and scheduler on B200), and the FMA pipe
-// idles. x <= ~100; anything below -125 returns ~2^-125.
-__device__ __forceinline__ float ex2_poly(float x) {
-  x = fmaxf(x, -125.0f);
-  const float t = x + 12582912.0f;            // 1.5 * 2^23: nearest integer of x lands in the low mantissa bits
-  const float f = x - (t - 12582912.0f);      // [-0.5, 0.5]
-  float p = fmaf(0.05286743491888046f, f, 0.2421518862247467f);
-  p = fmaf(p, f, 0.6935867667198181f);
-  p = fmaf(p, f, 0.9999627470970154f);
-  return __uint_as_float(__float_as_uint(p) + (__float_as_uint(t) << 23));
-}
-
-// bf16x2 pack of two NON-NEGATIVE finite floats on the integer ALU (round half up; differs from RN-even only on exact
-// ties). The flash-attention softmax is bound by the XU pipe, which executes MUFU.EX2 *and* the F2FP conversions
-// (ncu r01: xu pipe saturated, 1.5 XU ops per score); this moves the conversion off it.
-__device__ __forceinline__ uint32_t pack_bf16x2_pos_alu(float lo, float hi) {
-  return __byte_perm(__float_as_uint(lo) + 0x8000u, __float_as_uint(hi) + 0x8000u, 0x7632);
 }
 
 #define MGB_CUDA_CHECK(expr)                                                                      \
