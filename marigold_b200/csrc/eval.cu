@@ -47,11 +47,20 @@ __global__ void __launch_bounds__(kEvThreads)
 }
 
 // scale, shift of min || [p 1] [s t]^T - g ||^2 over the valid pixels (np.linalg.lstsq in alignment.py:66-69)
+// Sum of quantity k over the blocks' partials by one warp: lane l takes blocks l, l + 32, ... (independent loads), xor tree.
+// (A single thread walking 296 x 12 dependent loads took 100 us.)
+__device__ __forceinline__ double warp_sum_partials(const double* __restrict__ part, int nblocks, int k) {
+  double t = 0.0;
+  for (int b = threadIdx.x & 31; b < nblocks; b += 32) t += part[(size_t)b * kEvSums + k];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+  return t;
+}
+
 __global__ void eval_align_solve_kernel(const double* __restrict__ part, int nblocks, int do_align, double* __restrict__ st) {
+  double s[5];
+  for (int k = 0; k < 5; ++k) s[k] = warp_sum_partials(part, nblocks, k);
   if (threadIdx.x != 0) return;
-  double s[5] = {0, 0, 0, 0, 0};
-  for (int b = 0; b < nblocks; ++b)
-    for (int k = 0; k < 5; ++k) s[k] += part[(size_t)b * kEvSums + k];
   double scale = 1.0, shift = 0.0;
   if (do_align) {
     const double n = s[0], sp = s[1], spp = s[2], sg = s[3], spg = s[4];
@@ -104,10 +113,9 @@ __global__ void __launch_bounds__(kEvThreads)
 
 __global__ void eval_metric_final_kernel(const double* __restrict__ part, int nblocks, const double* __restrict__ st,
                                          double* __restrict__ out) {
-  if (threadIdx.x != 0) return;
   double s[kEvSums] = {0};
-  for (int b = 0; b < nblocks; ++b)
-    for (int k = 0; k < 11; ++k) s[k] += part[(size_t)b * kEvSums + k];
+  for (int k = 0; k < 11; ++k) s[k] = warp_sum_partials(part, nblocks, k);
+  if (threadIdx.x != 0) return;
   const double n = s[0] > 0 ? s[0] : 1.0;
   out[0] = st[0]; out[1] = st[1]; out[2] = s[0];
   out[3] = s[1] / n;                                     // abs_relative_difference
