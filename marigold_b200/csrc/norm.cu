@@ -522,12 +522,185 @@ __global__ void __launch_bounds__(256, QL <= 3 ? 4 : QL <= 5 ? 3 : 1)
   }
 }
 
+// Wide rows (C = 1280, few tokens): FOUR warps per token, each owning a contiguous quarter of the channels; LayerNorm
+// sums and the per-head partial dot products meet in shared memory behind a 128-thread named barrier per token group.
+// (One warp per token left these levels at 28 us per launch: 576 tokens x a 20-head serial chain on 8 warps per SM.)
+constexpr int kXwMaxH = 32;
+__device__ __forceinline__ void xw_barrier(int g) {
+  if (g == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
+  else asm volatile("bar.sync 2, 128;" ::: "memory");
+}
+__device__ __forceinline__ float xw_allsum(float v, float* red /* [4] of this group */, int w, int lane, int g) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  xw_barrier(g);                 // previous readers of red[] are done
+  if (lane == 0) red[w] = v;
+  xw_barrier(g);
+  return (red[0] + red[1]) + (red[2] + red[3]);     // same order in all four warps
+}
+
+__global__ void __launch_bounds__(256, 1)
+    xattn2_wide_kernel(const float* __restrict__ x, bf16* __restrict__ y, bf16* __restrict__ a_out,
+                       const float* __restrict__ g2, const float* __restrict__ b2, const float* __restrict__ g3,
+                       const float* __restrict__ b3, const bf16* __restrict__ GU, const float* __restrict__ c1, int M,
+                       int C, int H, float scale, float eps) {
+  constexpr int QW = 3;                          // quads per lane within a warp's channel quarter (C / 16 <= 96 quads)
+  extern __shared__ __align__(16) uint8_t xs_raw[];
+  pdl_launch_dependents();
+  const int Q = C / 4, Qq = Q / 4;               // quads per row, per warp quarter
+  uint2* sG = reinterpret_cast<uint2*>(xs_raw);
+  uint2* sU = sG + (size_t)H * Q;
+  float4* sP = reinterpret_cast<float4*>(sU + (size_t)H * Q);
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ float s_red[2][4];
+  __shared__ float s_dot[2][4][kXwMaxH];
+  if (threadIdx.x == 0) {
+    mbar_init(&bar, 1);
+    fence_mbar_init();
+    const uint32_t gu_bytes = uint32_t(2) * H * C * 2, p_bytes = uint32_t(C) * 4;
+    mbar_arrive_expect_tx(&bar, gu_bytes + 5 * p_bytes);
+    bulk_copy_g2s(sG, GU, gu_bytes, &bar);
+    const float* ps[5] = {c1, g2, b2, g3, b3};
+    for (int k = 0; k < 5; ++k) bulk_copy_g2s(sP + (size_t)k * Q, ps[k], p_bytes, &bar);
+  }
+  __syncthreads();
+  mbar_wait(&bar, 0);
+  pdl_wait();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = warp >> 2, w = warp & 3;         // token group of this block (0 / 1), channel quarter
+  const int q0 = w * Qq;
+  float* red = s_red[g];
+  const int iters = (M + 2 * gridDim.x - 1) / (2 * gridDim.x);
+  for (int it = 0; it < iters; ++it) {
+    const int tok = (it * gridDim.x + blockIdx.x) * 2 + g;
+    const bool live = tok < M;                   // dead groups still take part in their own barriers
+    const float4* xr = reinterpret_cast<const float4*>(x + (size_t)(live ? tok : 0) * C) + q0;
+    float4 z[QW], acc[QW];
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < QW; ++k) {
+      const int q = lane + 32 * k;
+      acc[k] = (live && q < Qq) ? __ldg(xr + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+      s += acc[k].x + acc[k].y + acc[k].z + acc[k].w;
+    }
+    float mean = xw_allsum(s, red, w, lane, g) / C, ss = 0.f;
+#pragma unroll
+    for (int k = 0; k < QW; ++k) {
+      if (lane + 32 * k < Qq) {
+        const float a = acc[k].x - mean, b = acc[k].y - mean, c = acc[k].z - mean, d = acc[k].w - mean;
+        ss += a * a + b * b + c * c + d * d;
+      }
+    }
+    float rstd = rsqrtf(xw_allsum(ss, red, w, lane, g) / C + eps);
+#pragma unroll
+    for (int k = 0; k < QW; ++k) {
+      const int q = lane + 32 * k;
+      if (q < Qq) {
+        const float4 cc = sP[q0 + q], ga = sP[Q + q0 + q], be = sP[2 * Q + q0 + q];
+        z[k] = make_float4((acc[k].x - mean) * rstd * ga.x + be.x, (acc[k].y - mean) * rstd * ga.y + be.y,
+                           (acc[k].z - mean) * rstd * ga.z + be.z, (acc[k].w - mean) * rstd * ga.w + be.w);
+        acc[k] = make_float4(acc[k].x + cc.x, acc[k].y + cc.y, acc[k].z + cc.z, acc[k].w + cc.w);
+      } else {
+        z[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+    // partial logits of every head over this warp's channel quarter
+    for (int h0 = 0; h0 < H; h0 += 4) {
+      float d[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        d[j] = 0.f;
+        if (h0 + j < H) {
+          const uint2* Gh = sG + (size_t)(h0 + j) * Q + q0;
+#pragma unroll
+          for (int k = 0; k < QW; ++k) {
+            const int q = lane + 32 * k;
+            if (q < Qq) {
+              const float4 gg = bf16x4_to_f4(Gh[q]);
+              d[j] += z[k].x * gg.x + z[k].y * gg.y + z[k].z * gg.z + z[k].w * gg.w;
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) d[j] += __shfl_xor_sync(0xffffffffu, d[j], o);
+      if (lane == 0) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) if (h0 + j < H) s_dot[g][w][h0 + j] = d[j];
+      }
+    }
+    xw_barrier(g);
+    for (int h = 0; h < H; ++h) {
+      const float dsum = (s_dot[g][0][h] + s_dot[g][1][h]) + (s_dot[g][2][h] + s_dot[g][3][h]);
+      const float w0 = 1.0f / (1.0f + __expf(-dsum * scale));
+      const uint2* Uh = sU + (size_t)h * Q + q0;
+#pragma unroll
+      for (int k = 0; k < QW; ++k) {
+        const int q = lane + 32 * k;
+        if (q < Qq) {
+          const float4 u = bf16x4_to_f4(Uh[q]);
+          acc[k].x = fmaf(w0, u.x, acc[k].x); acc[k].y = fmaf(w0, u.y, acc[k].y);
+          acc[k].z = fmaf(w0, u.z, acc[k].z); acc[k].w = fmaf(w0, u.w, acc[k].w);
+        }
+      }
+    }
+    // trunk (bf16) and LN3
+    uint2* yr = reinterpret_cast<uint2*>(y + (size_t)(live ? tok : 0) * C) + q0;
+    s = 0.f;
+#pragma unroll
+    for (int k = 0; k < QW; ++k) {
+      const int q = lane + 32 * k;
+      if (q < Qq) {
+        if (live) yr[q] = make_uint2(pack_bf16x2(acc[k].x, acc[k].y), pack_bf16x2(acc[k].z, acc[k].w));
+        s += acc[k].x + acc[k].y + acc[k].z + acc[k].w;
+      }
+    }
+    mean = xw_allsum(s, red, w, lane, g) / C; ss = 0.f;
+#pragma unroll
+    for (int k = 0; k < QW; ++k) {
+      if (lane + 32 * k < Qq) {
+        const float a = acc[k].x - mean, b = acc[k].y - mean, c = acc[k].z - mean, d2 = acc[k].w - mean;
+        ss += a * a + b * b + c * c + d2 * d2;
+      }
+    }
+    rstd = rsqrtf(xw_allsum(ss, red, w, lane, g) / C + eps);
+    uint2* ar = reinterpret_cast<uint2*>(a_out + (size_t)(live ? tok : 0) * C) + q0;
+#pragma unroll
+    for (int k = 0; k < QW; ++k) {
+      const int q = lane + 32 * k;
+      if (live && q < Qq) {
+        const float4 ga = sP[3 * Q + q0 + q], be = sP[4 * Q + q0 + q];
+        const float o0 = (acc[k].x - mean) * rstd * ga.x + be.x, o1 = (acc[k].y - mean) * rstd * ga.y + be.y;
+        const float o2 = (acc[k].z - mean) * rstd * ga.z + be.z, o3 = (acc[k].w - mean) * rstd * ga.w + be.w;
+        ar[q] = make_uint2(pack_bf16x2(o0, o1), pack_bf16x2(o2, o3));
+      }
+    }
+    xw_barrier(g);               // s_dot is rewritten by the next token
+  }
+}
+
 int launch_xattn2_fused(const float* x, bf16* y, bf16* a_out, const float* g2, const float* b2, const float* g3,
                         const float* b3, const bf16* GU, const float* c1, int M, int C, int H, float scale, float eps,
                         cudaStream_t stream) {
   if (C % 4 != 0 || C / 4 > 32 * kLnMaxQ || H < 1) { set_error("xattn2: unsupported C=%d H=%d", C, H); return MGB_ERR_INVALID; }
   const size_t smem = size_t(2) * H * C * 2 + size_t(5) * C * 4;
   if (smem > 200 * 1024) { set_error("xattn2: C=%d H=%d needs %zu B of shared memory", C, H, smem); return MGB_ERR_INVALID; }
+  if (C % 16 == 0 && C / 16 > 40 && C / 16 <= 96 && H <= kXwMaxH) {
+    // wide rows: four warps per token (C = 1280: 80 quads per warp quarter)
+    static bool wide_attr = false;
+    if (!wide_attr) {
+      cudaError_t e = cudaFuncSetAttribute(xattn2_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      if (e != cudaSuccess) { set_error("xattn2 attr: %s", cudaGetErrorString(e)); return MGB_ERR_CUDA; }
+      wide_attr = true;
+    }
+    const int blocks = std::max(1, std::min((M + 1) / 2, 148));
+    cudaError_t e = launch_k(xattn2_wide_kernel, blocks, 256, smem, stream, x, y, a_out, g2, b2, g3, b3, GU, c1, M, C, H, scale, eps);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e != cudaSuccess) { set_error("xattn2 launch: %s", cudaGetErrorString(e)); return MGB_ERR_CUDA; }
+    return MGB_OK;
+  }
   const int ql = (C / 4 + 31) / 32;
   void (*kern)(const float*, bf16*, bf16*, const float*, const float*, const float*, const float*, const bf16*, const float*,
                int, int, int, float, float) =
