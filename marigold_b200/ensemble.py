@@ -55,34 +55,22 @@ def _scipy_fd_points(x: np.ndarray) -> np.ndarray:
     return x + h
 
 
-def _fd_jac(cost_fn, cost_batch, cost_fd=None):
-    """scipy's 2-point forward difference with an absolute step (approx_derivative as BFGS calls it with jac=None:
-    `abs_step=eps`, f0 = f(x)) restated for scipy versions without the `workers=` hook; the 2E points are one batch."""
-    def jac(x):
-        x = np.asarray(x, dtype=np.float64)
-        xp = _scipy_fd_points(x)
-        xs = np.repeat(x[None], x.size, 0)
-        xs[np.arange(x.size), np.arange(x.size)] = xp
-        f0 = cost_fn(x)
-        f = cost_fd(xs) if cost_fd is not None else None
-        if f is None:
-            f = cost_batch(xs)
-        return (f - f0) / (xp - x)
-    return jac
+def _fd_grad(x: np.ndarray, f0: float, costs: np.ndarray, pert: np.ndarray) -> np.ndarray:
+    """scipy's 2-point forward difference (approx_derivative as BFGS calls it with jac=None: f0 = f(x),
+    df_i = f(x + h_i e_i) - f0 over dx_i = (x_i + h_i) - x_i), from costs already evaluated at `pert = x + h`."""
+    return (np.asarray(costs, dtype=np.float64) - f0) / (pert - x)
 
 
-def _bfgs(cost_fn, cost_batch, fd_map, param0, tol, max_iter, cost_fd=None):
-    """scipy.optimize.minimize(..., method="BFGS", tol=tol, options={"maxiter": max_iter}) exactly as the reference
-    calls it (ensemble.py:165-171), with the finite-difference points evaluated as one device batch."""
+def _bfgs(cost_fn, grad_fn, param0, tol, max_iter):
+    """scipy.optimize.minimize(..., method="BFGS", tol=tol, options={"maxiter": max_iter}) as the reference calls it
+    (ensemble.py:165-171). The reference leaves jac=None, i.e. scipy's forward differences; `grad_fn` restates exactly
+    those (`_scipy_fd_points`, `_fd_grad`: same points, same arithmetic, hence the same trajectory bit for bit) from
+    one batched device pass, and handing it over as `jac` keeps approx_derivative's per-call Python overhead
+    (~2x the device time of a cost pass) out of the loop."""
     import scipy.optimize
 
-    opts = {"maxiter": max_iter, "disp": False}
-    ver = tuple(int(v) for v in scipy.__version__.split(".")[:2])
-    if ver >= (1, 16):
-        res = scipy.optimize.minimize(cost_fn, param0, method="BFGS", tol=tol, options={**opts, "workers": fd_map})
-    else:
-        res = scipy.optimize.minimize(cost_fn, param0, jac=_fd_jac(cost_fn, cost_batch, cost_fd), method="BFGS", tol=tol,
-                                      options=opts)
+    res = scipy.optimize.minimize(cost_fn, param0, jac=grad_fn, method="BFGS", tol=tol,
+                                  options={"maxiter": max_iter, "disp": False})
     return res.x, res.nit
 
 
@@ -151,7 +139,7 @@ def ensemble_depth(
             n_eval[1] += 1
             return out
 
-        spec = {"x": None, "pert": None, "costs": None}   # last speculative (f, forward-difference points) evaluation
+        memo = {"x": None, "f": None, "pert": None, "costs": None}   # the last point evaluated
 
         def _fd_call(base: np.ndarray, pert: np.ndarray) -> np.ndarray:
             out = np.empty(base.size + 1, dtype=np.float64)
@@ -163,46 +151,55 @@ def ensemble_depth(
             n_eval[1] += 1
             return out
 
+        def _fd_rows(x: np.ndarray, pert: np.ndarray) -> np.ndarray:
+            xs = np.repeat(x[None], x.size, 0)
+            xs[np.arange(x.size), np.arange(x.size)] = pert
+            return xs
+
         def cost_fn(param: np.ndarray) -> float:
-            """The objective at `param`. BFGS asks for the gradient at (almost) every point it evaluates, so the 2E
-            forward-difference points scipy will request next (x + h e_i with its default absolute step) ride along in
-            the same pass and the same synchronisation; `fd_map` serves them from here when the request matches."""
+            """The objective at `param`. BFGS asks for the gradient at (almost) every point it evaluates, so the
+            forward-difference points of that gradient (x + h e_i, scipy's default absolute step) ride along in the
+            same pass and the same synchronisation; `grad_fn` is then served from here."""
             x = np.ascontiguousarray(param, dtype=np.float64)
-            if speculate and E <= 16 and x.size >= 2:
-                pert = _scipy_fd_points(x)
-                out = _fd_call(x, pert)
-                spec.update(x=x.copy(), pert=pert, costs=out[1:])
-                return float(out[0])
-            return float(cost_batch(x)[0])
+            if not speculate:
+                f = float(cost_batch(x)[0])
+                memo.update(x=x.copy(), f=f, pert=None, costs=None)
+                return f
+            pert = _scipy_fd_points(x)
+            if E <= 16 and x.size >= 2:
+                out = _fd_call(x, pert)                         # structured pass: base + one perturbed coordinate per row
+            else:
+                out = cost_batch(np.concatenate([x[None], _fd_rows(x, pert)]))
+            memo.update(x=x.copy(), f=float(out[0]), pert=pert, costs=out[1:])
+            return memo["f"]
 
         def cost_fd(xs: np.ndarray) -> Optional[np.ndarray]:
-            """xs [n, n]: row i = a common base point with coordinate i perturbed (what scipy's 2-point scheme
-            evaluates). One structured pass on the device (`mgb_ens_depth_cost_fd`); None if xs is not of that form."""
+            """xs [n, n]: row i = a common base point with coordinate i perturbed (what a 2-point scheme evaluates).
+            One structured pass on the device (`mgb_ens_depth_cost_fd`); None if xs is not of that form."""
             n = xs.shape[1]
             if E > 16 or xs.shape[0] != n or n < 2:
                 return None
             base = xs[1].copy()
             base[1] = xs[0][1]                                  # row 0 is unperturbed at coordinate 1
             pert = np.ascontiguousarray(np.diagonal(xs))
-            chk = np.repeat(base[None], n, 0)
-            chk[np.arange(n), np.arange(n)] = pert
-            if not np.array_equal(chk, xs):
+            if not np.array_equal(_fd_rows(base, pert), xs):
                 return None
-            if spec["x"] is not None and np.array_equal(spec["x"], base) and np.array_equal(spec["pert"], pert):
-                return spec["costs"]                            # already evaluated together with f(base)
             return _fd_call(base, pert)[1:]
 
-        def fd_map(fun, xs):
-            """scipy's finite-difference hook (`workers=`, scipy >= 1.16): all perturbed points in one call."""
-            X = np.ascontiguousarray(np.asarray(list(xs), dtype=np.float64))
-            costs = cost_fd(X)
-            if costs is None:
-                costs = cost_batch(X)
-            return [np.atleast_1d(c) for c in costs]
+        def grad_fn(param: np.ndarray) -> np.ndarray:
+            x = np.ascontiguousarray(param, dtype=np.float64)
+            if memo["x"] is None or not np.array_equal(memo["x"], x):
+                cost_fn(x)
+            if memo["costs"] is None:                           # speculate=False: the gradient points are a second pass
+                pert = _scipy_fd_points(x)
+                xs = _fd_rows(x, pert)
+                costs = cost_fd(xs)
+                memo.update(pert=pert, costs=costs if costs is not None else cost_batch(xs))
+            return _fd_grad(x, memo["f"], memo["costs"], memo["pert"])
 
         nit = 0
         if param is None:
-            param, nit = _bfgs(cost_fn, cost_batch, fd_map, param0, tol, max_iter, cost_fd)
+            param, nit = _bfgs(cost_fn, grad_fn, param0, tol, max_iter)
         param = np.ascontiguousarray(param, dtype=np.float64)   # (tests may inject the alignment)
 
         pred = torch.empty(1, 1, H, W, dtype=torch.float32, device=depth.device)

@@ -172,12 +172,12 @@ def test_iid_output_container_follows_the_reference():
 
 
 def test_bfgs_driver_follows_scipy_default_finite_differences():
-    """marigold_b200.ensemble._bfgs evaluates the 2E forward-difference points of a gradient as one batch; the
-    trajectory must be the one scipy's own default (jac=None) produces — with the `workers=` hook and with the
-    restated jac for older scipy versions alike (reference call: marigold/util/ensemble.py:165-171)."""
+    """marigold_b200.ensemble._bfgs hands scipy a gradient built from one batch of forward-difference points; the
+    trajectory must be the one scipy's own default (jac=None, as the reference calls it: marigold/util/ensemble.py:
+    165-171) produces, bit for bit."""
     import scipy.optimize
 
-    from marigold_b200.ensemble import _bfgs, _fd_jac
+    from marigold_b200.ensemble import _bfgs, _fd_grad, _scipy_fd_points
 
     rng = np.random.default_rng(0)
     A = rng.standard_normal((6, 6))
@@ -188,20 +188,18 @@ def test_bfgs_driver_follows_scipy_default_finite_differences():
         x = np.asarray(x, dtype=np.float64)
         return float(np.float32(0.5 * x @ A @ x - b @ x + 0.1 * np.abs(x).sum()))   # fp32-rounded like the device cost
 
-    def f_batch(xs):
-        return np.array([f(x) for x in np.atleast_2d(xs)])
+    batches = []
 
-    calls = []
+    def grad(x):
+        x = np.asarray(x, dtype=np.float64)
+        pert = _scipy_fd_points(x)
+        xs = np.repeat(x[None], x.size, 0)
+        xs[np.arange(x.size), np.arange(x.size)] = pert
+        batches.append(len(xs))
+        return _fd_grad(x, f(x), np.array([f(r) for r in xs]), pert)
 
-    def fd_map(fun, xs):
-        xs = list(xs)
-        calls.append(len(xs))
-        return [np.atleast_1d(c) for c in f_batch(xs)]
-
-    x0 = rng.standard_normal(6)
-    ref = scipy.optimize.minimize(f, x0, method="BFGS", tol=1e-6, options={"maxiter": 50, "disp": False})
-    x1, nit1 = _bfgs(f, f_batch, fd_map, x0, 1e-6, 50)
-    np.testing.assert_array_equal(x1, ref.x)
-    assert nit1 == ref.nit and calls and all(c == 6 for c in calls)
-    alt = scipy.optimize.minimize(f, x0, jac=_fd_jac(f, f_batch), method="BFGS", tol=1e-6, options={"maxiter": 50})
-    np.testing.assert_array_equal(alt.x, ref.x)
+    for x0 in (rng.standard_normal(6), np.array([0.0, 1e9, -1e9, 1.0, -1.0, 3e17])):   # incl. x + eps == x coordinates
+        ref = scipy.optimize.minimize(f, x0, method="BFGS", tol=1e-6, options={"maxiter": 50, "disp": False})
+        x1, nit1 = _bfgs(f, grad, x0, 1e-6, 50)
+        np.testing.assert_array_equal(x1, ref.x)
+        assert nit1 == ref.nit and batches and all(c == 6 for c in batches)
