@@ -254,20 +254,27 @@ __global__ void __launch_bounds__(attn_threads(RT), 2) flash_attn64_kernel(const
         }
       }
       // P = exp2(S * c - m_ref) (exp2(-inf) = 0 masks the tail); bf16 pairs; 4 partial row sums
+      // (the scale-and-shift and the row sums go through FFMA2 / FADD2: two scores per instruction)
       uint32_t pk[NS / 2];
-      float ls0 = 0.f, ls1 = 0.f, ls2 = 0.f, ls3 = 0.f;
-      const float nm = -m_ref;
+      f2 ls01 = f2_splat(0.f), ls23 = ls01;
+      const f2 sc2 = f2_splat(p.scale_log2), nm2 = f2_splat(-m_ref);
 #pragma unroll
       for (int i = 0; i < NS / 4; ++i) {
-        const float a0 = ex2_approx(fmaf(__uint_as_float(r[4 * i]), p.scale_log2, nm));
-        const float a1 = ex2_approx(fmaf(__uint_as_float(r[4 * i + 1]), p.scale_log2, nm));
-        const float a2 = ex2_approx(fmaf(__uint_as_float(r[4 * i + 2]), p.scale_log2, nm));
-        const float a3 = ex2_approx(fmaf(__uint_as_float(r[4 * i + 3]), p.scale_log2, nm));
-        ls0 += a0; ls1 += a1; ls2 += a2; ls3 += a3;
+        float t0, t1, t2, t3;
+        f2_split(f2_fma(f2_make(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1])), sc2, nm2), t0, t1);
+        f2_split(f2_fma(f2_make(__uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3])), sc2, nm2), t2, t3);
+        const float a0 = ex2_approx(t0), a1 = ex2_approx(t1), a2 = ex2_approx(t2), a3 = ex2_approx(t3);
+        ls01 = f2_add(ls01, f2_make(a0, a1));
+        ls23 = f2_add(ls23, f2_make(a2, a3));
         pk[2 * i] = pack_bf16x2(a0, a1);
         pk[2 * i + 1] = pack_bf16x2(a2, a3);
       }
-      l_run += (ls0 + ls1) + (ls2 + ls3);
+      {
+        float ls0, ls1, ls2, ls3;
+        f2_split(ls01, ls0, ls1);
+        f2_split(ls23, ls2, ls3);
+        l_run += (ls0 + ls1) + (ls2 + ls3);
+      }
       // P buffer b was last read by PV(j-2)
       mbar_wait(&p_empty[b], (u & 1) ^ 1);
       TmemIO<NS / 2>::st(tmem_base + 192 + b * 32 + h * (NS / 2) + lane_off, pk);

@@ -348,20 +348,74 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 __device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
-// Exact-erf GELU (diffusers GEGLU: F.gelu(gate), default approximate="none"). erf by Abramowitz-Stegun 7.1.26
-// (|error| <= 1.5e-7, far below the bf16 rounding of the product that follows): one MUFU.RCP + one MUFU.EX2 + 8 FMA
-// instead of erff's ~35 instructions; this epilogue runs 11.8 M times per 96 x 96 feed-forward.
+// Packed fp32 pairs (sm_100: FFMA2 / FADD2 / FMUL2 issue one instruction for two lanes of a 64-bit register pair)
+using f2 = unsigned long long;
+__device__ __forceinline__ f2 f2_make(float lo, float hi) {
+  f2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ f2 f2_splat(float v) { return f2_make(v, v); }
+__device__ __forceinline__ void f2_split(f2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f2 f2_fma(f2 a, f2 b, f2 c) {
+  f2 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ f2 f2_add(f2 a, f2 b) {
+  f2 r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f2 f2_sub(f2 a, f2 b) {
+  f2 r;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f2 f2_mul(f2 a, f2 b) {
+  f2 r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+
+// Exact-erf GELU (diffusers GEGLU: F.gelu(gate), default approximate="none"), two values per call.
+//   gelu(x) = x/2 (1 + erf(x / sqrt 2)) = (h + |h|) - |h| erfc(|x| / sqrt 2),  h = x / 2
+//   erfc(a / sqrt 2) = 2^-Q(a), Q a degree-8 polynomial without constant term, weighted minimax fit on [0, 6]
+//   (monotone beyond, so large |x| just underflows to 0): |erf error| <= 8.4e-8, |gelu error| <= 2.6e-7 in fp32 Horner
+//   (tests/test_host.py checks the restated formula against math.erf) - far below the bf16 rounding of the product
+//   that follows. Evaluated in n = -|h| (coefficients pre-multiplied by -(-2)^k) so that no negation is needed:
+//   7 FFMA2 + 3 FMUL2/FADD2 + 1 FFMA2 per PAIR and ONE MUFU.EX2 per value, against erff's ~35 instructions and the
+//   2 MUFU + 14 scalar FMA-pipe instructions of the Abramowitz-Stegun 7.1.26 form used before: the GEGLU epilogue
+//   runs 11.8 M times per 96 x 96 feed-forward and was bound by instruction issue and the XU pipe.
+constexpr float kGeluK1 = 2.302210726e+00f;
+constexpr float kGeluK2 = -1.836824726e+00f;
+constexpr float kGeluK3 = 4.200355922e-01f;
+constexpr float kGeluK4 = 1.132606439e-01f;
+constexpr float kGeluK5 = 4.850499795e-03f;
+constexpr float kGeluK6 = -1.144385853e-02f;
+constexpr float kGeluK7 = -4.803082033e-03f;
+constexpr float kGeluK8 = -6.790186621e-04f;
+__device__ __forceinline__ f2 gelu_erf_f2(f2 x) {
+  const f2 h = f2_mul(x, f2_splat(0.5f));
+  float h0, h1;
+  f2_split(h, h0, h1);
+  const f2 n = f2_make(-fabsf(h0), -fabsf(h1));
+  f2 p = f2_fma(f2_splat(kGeluK8), n, f2_splat(kGeluK7));
+  p = f2_fma(p, n, f2_splat(kGeluK6));
+  p = f2_fma(p, n, f2_splat(kGeluK5));
+  p = f2_fma(p, n, f2_splat(kGeluK4));
+  p = f2_fma(p, n, f2_splat(kGeluK3));
+  p = f2_fma(p, n, f2_splat(kGeluK2));
+  p = f2_fma(p, n, f2_splat(kGeluK1));
+  float q0, q1;
+  f2_split(f2_mul(p, n), q0, q1);                               // -Q(|x|)
+  const f2 e = f2_make(ex2_approx(q0), ex2_approx(q1));         // erfc(|x| / sqrt 2)
+  return f2_fma(n, e, f2_sub(h, n));
+}
 __device__ __forceinline__ float gelu_erf_f(float x) {
-  const float z = fabsf(x) * 0.70710678118654752f;
-  float t;                                                        // 1 / (1 + p z) in (0, 1]: one MUFU.RCP (the IEEE
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));   // __frcp_rn adds a refinement + a branchy slow path)
-  float poly = fmaf(1.061405429f, t, -1.453152027f);
-  poly = fmaf(poly, t, 1.421413741f);
-  poly = fmaf(poly, t, -0.284496736f);
-  poly = fmaf(poly, t, 0.254829592f);
-  const float e = ex2_approx(-1.4426950408889634f * z * z);      // exp(-z^2)
-  const float erf_abs = fmaf(-poly * t, e, 1.0f);                  // erf(|x| / sqrt 2)
-  return 0.5f * x * (1.0f + copysignf(erf_abs, x));
+  float lo, hi;
+  f2_split(gelu_erf_f2(f2_make(x, x)), lo, hi);
+  return lo;
 }
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);

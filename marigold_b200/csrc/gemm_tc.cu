@@ -575,10 +575,15 @@ __global__ void __launch_bounds__(kGemmThreads, MINB) gemm_tc_kernel(const __gri
             }
 #pragma unroll
             for (int it = 0; it < RB; ++it) {
-              float4 v = x[it];
-              v.x = fmaf(v.x, scale, b4.x); v.y = fmaf(v.y, scale, b4.y);
-              v.z = fmaf(v.z, scale, b4.z); v.w = fmaf(v.w, scale, b4.w);
-              if (residual) { v.x += rr[it].x; v.y += rr[it].y; v.z += rr[it].z; v.w += rr[it].w; }
+              f2 v01 = f2_fma(f2_make(x[it].x, x[it].y), f2_splat(scale), f2_make(b4.x, b4.y));
+              f2 v23 = f2_fma(f2_make(x[it].z, x[it].w), f2_splat(scale), f2_make(b4.z, b4.w));
+              if (residual) {
+                v01 = f2_add(v01, f2_make(rr[it].x, rr[it].y));
+                v23 = f2_add(v23, f2_make(rr[it].z, rr[it].w));
+              }
+              float4 v;
+              f2_split(v01, v.x, v.y);
+              f2_split(v23, v.z, v.w);
               if ((vm >> it) & 1u) {
                 const long long o = ob[it] + col;
                 if (out_f32) *reinterpret_cast<float4*>(out_f32 + o) = v;
@@ -596,8 +601,13 @@ __global__ void __launch_bounds__(kGemmThreads, MINB) gemm_tc_kernel(const __gri
             float4 x = *reinterpret_cast<const float4*>(s_rd + it * (4 * kEpiPitch));
             if (geglu) {
               const float4 g = *reinterpret_cast<const float4*>(s_rd + 32 * kEpiPitch + it * (4 * kEpiPitch));
-              x.x = (x.x + b4.x) * gelu_erf_f(g.x + g4.x); x.y = (x.y + b4.y) * gelu_erf_f(g.y + g4.y);
-              x.z = (x.z + b4.z) * gelu_erf_f(g.z + g4.z); x.w = (x.w + b4.w) * gelu_erf_f(g.w + g4.w);
+              // (value + bias) * gelu(gate + bias), packed pairs (FFMA2 / FADD2 / FMUL2)
+              const f2 y01 = f2_mul(f2_add(f2_make(x.x, x.y), f2_make(b4.x, b4.y)),
+                                    gelu_erf_f2(f2_add(f2_make(g.x, g.y), f2_make(g4.x, g4.y))));
+              const f2 y23 = f2_mul(f2_add(f2_make(x.z, x.w), f2_make(b4.z, b4.w)),
+                                    gelu_erf_f2(f2_add(f2_make(g.z, g.w), f2_make(g4.z, g4.w))));
+              f2_split(y01, x.x, x.y);
+              f2_split(y23, x.z, x.w);
             } else {
               x.x = fmaf(x.x, scale, b4.x); x.y = fmaf(x.y, scale, b4.y);
               x.z = fmaf(x.z, scale, b4.z); x.w = fmaf(x.w, scale, b4.w);

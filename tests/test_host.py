@@ -203,3 +203,28 @@ def test_bfgs_driver_follows_scipy_default_finite_differences():
         x1, nit1 = _bfgs(f, grad, x0, 1e-6, 50)
         np.testing.assert_array_equal(x1, ref.x)
         assert nit1 == ref.nit and batches and all(c == 6 for c in batches)
+
+
+def test_gelu_exponent_polynomial_matches_erf():
+    """The GEGLU epilogue's erf (csrc/common.cuh gelu_erf_f2: erfc(|x|/sqrt 2) = 2^-Q(|x|), degree-8 Q evaluated in
+    n = -|x|/2) restated in fp32 numpy with the constants read from the source: |gelu error| <= 5e-7 against the exact
+    erf form diffusers' GEGLU uses (F.gelu, approximate="none"), over [-12, 12] and at the extremes."""
+    import math
+    import re
+    from pathlib import Path
+
+    src = (Path(__file__).resolve().parents[1] / "marigold_b200" / "csrc" / "common.cuh").read_text()
+    K = {int(k): np.float32(float(v)) for k, v in re.findall(r"constexpr float kGeluK(\d) = ([-+0-9.e]+)f;", src)}
+    assert sorted(K) == list(range(1, 9))
+    x = np.concatenate([np.linspace(-12, 12, 400001), [0.0, -0.0, 1e-30, -1e-30, 50.0, -50.0, 1e4, -1e4]]).astype(np.float32)
+    h = np.float32(0.5) * x
+    n = -np.abs(h)
+    p = K[8] * n + K[7]
+    for k in range(6, 0, -1):
+        p = (p * n + K[k]).astype(np.float32)
+    with np.errstate(over="ignore", under="ignore"):
+        e = np.exp2((p * n).astype(np.float32).astype(np.float64)).astype(np.float32)
+        g = (n * e + (h - n)).astype(np.float32)
+    exact = np.array([0.5 * v * (1.0 + math.erf(v / math.sqrt(2.0))) for v in x.astype(np.float64)])
+    assert np.isfinite(g).all()
+    assert np.abs(g - exact).max() <= 5e-7
