@@ -12,7 +12,6 @@ import concurrent.futures as cf
 import os
 import shutil
 import subprocess
-import sys
 from pathlib import Path
 
 PKG = Path(__file__).resolve().parent

@@ -11,7 +11,6 @@ vectors), so the trajectory semantics are the reference's.
 from __future__ import annotations
 
 import ctypes as C
-from functools import partial
 from typing import Optional, Tuple
 
 import numpy as np

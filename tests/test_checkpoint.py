@@ -9,7 +9,7 @@ import torch
 
 from marigold_b200 import checkpoint as ck
 from marigold_b200.schedulers import DDIMScheduler, LCMScheduler
-from tests.helpers import oracle_models, rel_err
+from tests.helpers import oracle_models
 
 
 def _configs(unet, vae):

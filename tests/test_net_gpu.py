@@ -1,7 +1,6 @@
 """GPU parity of the network graphs (through the C ABI) against the fp32 CPU oracle on identical
 seeded weights and inputs. Tolerances are bf16-operand tolerances, stated per test; the tight 1e-3
 bar of north_star is checked (and its feasibility reported) in test_pipeline_gpu.py."""
-import numpy as np
 import pytest
 import torch
 

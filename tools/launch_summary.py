@@ -5,7 +5,6 @@ import argparse
 import csv
 import io
 import re
-import sys
 from collections import defaultdict
 
 
