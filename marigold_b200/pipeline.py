@@ -19,7 +19,6 @@ import numpy as np
 import torch
 import torch.nn.functional as F
 
-from . import _lib
 from .engine import Engine
 from .ensemble import ensemble_depth, ensemble_iid, ensemble_normals
 from .schedulers import DDIMScheduler, LCMScheduler
