@@ -687,7 +687,11 @@ int launch_xattn2_fused(const float* x, bf16* y, bf16* a_out, const float* g2, c
   if (C % 4 != 0 || C / 4 > 32 * kLnMaxQ || H < 1) { set_error("xattn2: unsupported C=%d H=%d", C, H); return MGB_ERR_INVALID; }
   const size_t smem = size_t(2) * H * C * 2 + size_t(5) * C * 4;
   if (smem > 200 * 1024) { set_error("xattn2: C=%d H=%d needs %zu B of shared memory", C, H, smem); return MGB_ERR_INVALID; }
-  if (C % 16 == 0 && C / 16 > 40 && C / 16 <= 96 && H <= kXwMaxH) {
+  // Four warps per token pay while the launch is latency-bound (few tokens: one member's 24^2 / 12^2 levels, 25 vs 28 us);
+  // with many tokens (batched members) one warp per token has the higher throughput (c3, 8 members: 312 vs 316 steps/s).
+  // MGB_XATTN_WIDE_MAXM overrides the token count up to which the wide kernel is used.
+  static const int wide_max_m = getenv("MGB_XATTN_WIDE_MAXM") ? atoi(getenv("MGB_XATTN_WIDE_MAXM")) : 1024;
+  if (C % 16 == 0 && C / 16 > 40 && C / 16 <= 96 && H <= kXwMaxH && M <= wide_max_m) {
     // wide rows: four warps per token (C = 1280: 80 quads per warp quarter)
     static bool wide_attr = false;
     if (!wide_attr) {
