@@ -207,6 +207,14 @@ int mgb_op_groupnorm(const float* x_dev, void* y_bf16_dev, const float* gamma_de
                      void* stream);
 int mgb_op_layernorm(const float* x_dev, void* y_bf16_dev, const float* gamma_dev, const float* beta_dev, int32_t M,
                      int32_t C, float eps, void* stream);
+/* attn2 of diffusers' BasicTransformerBlock against the FIXED two-token context CLIP(""), collapsed (marigold_depth_pipeline.py
+ * :381-394,438-442,461-463), with the LayerNorm before it (norm2) and after it (norm3):
+ *   z = LN2(x);  y = x + c1 + sum_h sigmoid(scale * z . G_h) U_h;  a = LN3(y)        (y, a stored as bf16)
+ * GU_bf16_dev: [2][H][C] (G rows, then U rows) and c1_dev [C] are what mgb_set_text_embedding folds from to_q / to_k / to_v /
+ * to_out and the text embedding. One launch; one warp per token, or four for C = 1280 with few tokens. */
+int mgb_op_xattn2(const float* x_dev, void* y_bf16_dev, void* a_bf16_dev, const float* ln2_g_dev, const float* ln2_b_dev,
+                  const float* ln3_g_dev, const float* ln3_b_dev, const void* GU_bf16_dev, const float* c1_dev, int32_t M,
+                  int32_t C, int32_t H, float scale, float eps, void* stream);
 int mgb_op_space_to_depth(const float* x_dev, void* y_bf16_dev, int32_t NB, int32_t H, int32_t W, int32_t C,
                           void* stream);
 int mgb_op_upsample2x(const float* x_dev, void* y_bf16_dev, int32_t NB, int32_t H, int32_t W, int32_t C,

@@ -119,6 +119,17 @@ int mgb_op_layernorm(const float* x, void* y, const float* gamma, const float* b
   return rc;
 }
 
+int mgb_op_xattn2(const float* x, void* y, void* a_out, const float* ln2_g, const float* ln2_b, const float* ln3_g,
+                  const float* ln3_b, const void* GU, const float* c1, int32_t M, int32_t C, int32_t H, float scale, float eps,
+                  void* stream) {
+  if (!x || !y || !a_out || !GU || !c1) { set_error("op_xattn2: null pointer"); return MGB_ERR_INVALID; }
+  int rc = launch_xattn2_fused(x, reinterpret_cast<bf16*>(y), reinterpret_cast<bf16*>(a_out), ln2_g, ln2_b, ln3_g, ln3_b,
+                               reinterpret_cast<const bf16*>(GU), c1, M, C, H, scale, eps,
+                               reinterpret_cast<cudaStream_t>(stream));
+  if (!rc) count_launch(1);
+  return rc;
+}
+
 /* ---- pre / post-processing and evaluation (image.cu, eval.cu) ---- */
 int mgb_resize(const void* src, int32_t src_is_u8, int32_t NC, int32_t H, int32_t W, float* dst, int32_t h, int32_t w,
                int32_t mode, int32_t post, float* tmp, void* stream) {

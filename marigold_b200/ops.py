@@ -60,6 +60,17 @@ def groupnorm(x, gamma, beta, NB, HW, C, G, eps, silu):
     return y
 
 
+def xattn2(x, ln2_g, ln2_b, ln3_g, ln3_b, GU, c1, H, scale, eps=1e-5):
+    """Collapsed cross-attention against the fixed 2-token context, fused with norm2 / norm3 (see include/marigold_b200.h)."""
+    lib = _lib.load()
+    M, Cc = x.shape
+    y = torch.empty(M, Cc, dtype=torch.bfloat16, device=x.device)
+    a = torch.empty(M, Cc, dtype=torch.bfloat16, device=x.device)
+    check(lib.mgb_op_xattn2(ptr(x), ptr(y), ptr(a), ptr(ln2_g), ptr(ln2_b), ptr(ln3_g), ptr(ln3_b), ptr(GU), ptr(c1), M, Cc,
+                            H, float(scale), float(eps), stream_ptr()), "mgb_op_xattn2")
+    return y, a
+
+
 def layernorm(x, gamma, beta, eps=1e-5):
     lib = _lib.load()
     M, Cc = x.shape

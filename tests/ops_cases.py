@@ -54,6 +54,12 @@ def cases():
     add("groupnorm_1920", case_groupnorm, NB=1, HW=576, C=1920, G=32, eps=1e-5, silu=1)
     add("groupnorm_2560", case_groupnorm, NB=1, HW=144, C=2560, G=32, eps=1e-6, silu=0)
     add("groupnorm_128_big", case_groupnorm, NB=1, HW=147456, C=128, G=32, eps=1e-6, silu=1)
+    # collapsed cross-attention (+ norm2 / norm3): one warp per token at three register sizes, four warps per token
+    add("xattn2_c320", case_xattn2, M=9216, C=320)
+    add("xattn2_c640", case_xattn2, M=2304, C=640)
+    add("xattn2_c1280_wide", case_xattn2, M=576, C=1280)
+    add("xattn2_c1280_wide_odd", case_xattn2, M=145, C=1280)
+    add("xattn2_c1280_batched", case_xattn2, M=2 * 576, C=1280)
     add("layernorm_320", case_layernorm, M=9216, C=320)
     add("layernorm_1280", case_layernorm, M=576, C=1280)
     add("s2d", case_s2d, NB=2, H=24, W=16, C=128)
@@ -239,6 +245,32 @@ def case_groupnorm(NB, HW, C, G, eps, silu):
     res["ms"] = _timeit(run)
     res["gbs"] = NB * HW * C * (4 + 4 + 2) / res["ms"] / 1e6
     res["ok"] = res["bf16"]["rel_to_max"] < 6e-3 and not res["bf16"]["nan"]
+    return res
+
+
+def case_xattn2(M, C):
+    import torch
+    import torch.nn.functional as F
+    from marigold_b200 import ops
+
+    H = C // 64
+    g = torch.Generator(device="cuda").manual_seed(9)
+    x = torch.randn(M, C, device="cuda", generator=g) * 1.5 + 0.2
+    p = [torch.randn(C, device="cuda", generator=g) * s + o for s, o in ((0.3, 1.0), (0.3, 0.0), (0.3, 1.0), (0.3, 0.0))]
+    G = (torch.randn(H, C, device="cuda", generator=g) / C ** 0.5 * 4).to(torch.bfloat16)
+    U = (torch.randn(H, C, device="cuda", generator=g) * 0.5).to(torch.bfloat16)
+    c1 = torch.randn(C, device="cuda", generator=g) * 0.5
+    GU = torch.stack([G, U]).contiguous()
+    z = F.layer_norm(x.double(), (C,), p[0].double(), p[1].double(), 1e-5)
+    w = torch.sigmoid(0.125 * z @ G.double().t())
+    yf = x.double() + c1.double() + w @ U.double()
+    af = F.layer_norm(yf, (C,), p[2].double(), p[3].double(), 1e-5)
+    run = lambda: ops.xattn2(x, p[0], p[1], p[2], p[3], GU, c1, H, 0.125)
+    y, a = run()
+    torch.cuda.synchronize()
+    res = {"y": _err(y, yf.float()), "a": _err(a, af.float())}
+    res["ms"] = _timeit(run)
+    res["ok"] = res["y"]["rel_to_max"] < 6e-3 and res["a"]["rel_to_max"] < 6e-3 and not res["y"]["nan"] and not res["a"]["nan"]
     return res
 
 
