@@ -23,6 +23,7 @@
 
 namespace mgb {
 
+constexpr int kGnPartLoads = 12;  // partial-sum loads in flight per lane in phase 2
 constexpr int kGnCtasPerSm = 2;   // __launch_bounds__ below guarantees this residency (<= 128 registers, <= 40 KB smem)
 
 static __device__ __noinline__ void gn_barrier_timeout(unsigned seen, unsigned want) {
@@ -148,19 +149,20 @@ __global__ void __launch_bounds__(kGnThreads, kGnCtasPerSm)
   float* s_stat = reinterpret_cast<float*>(s_ch);
   {
     // every CTA of the image sums the same partials in the same (CTA index) order: identical statistics everywhere,
-    // independent of scheduling. Loads bypass L1 (written by other SMs) and are issued 4 at a time.
+    // independent of scheduling. Loads bypass L1 (written by other SMs) and are issued kGnPartLoads at a time (this phase
+    // is a chain of L2 round trips right behind the barrier: 192 chunks / 8 lanes = 24 entries per lane).
     double s = 0.0, q = 0.0;
     if (gi < G) {
       const float2* pp = part + (size_t)img * chunks * G + gi;
-      for (int c0 = lane8; c0 < chunks; c0 += 32) {
-        float2 t[4];
+      for (int c0 = lane8; c0 < chunks; c0 += 8 * kGnPartLoads) {
+        float2 t[kGnPartLoads];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < kGnPartLoads; ++u) {
           const int c = c0 + 8 * u;
           t[u] = c < chunks ? __ldcg(pp + (size_t)c * G) : make_float2(0.f, 0.f);
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) { s += double(t[u].x); q += double(t[u].y); }
+        for (int u = 0; u < kGnPartLoads; ++u) { s += double(t[u].x); q += double(t[u].y); }
       }
     }
 #pragma unroll
